@@ -1,0 +1,181 @@
+/*
+ * kwage_cuda.h -- C ABI of libkwage_cuda.so, the B200 (sm_100a) implementation of KWAGE's k-mer
+ * Bloom-filter hot path.  This is the drop-in boundary: plain pointers and sizes, no C++ or torch
+ * types.  The reference has no FFI/plugin interface; each group of entry points
+ * below replaces the body of one reference function, cited as file:line into the reference tree.
+ *
+ * Conventions
+ *   - every function returns 0 (KWG_OK) or a negative kwg_status; kwg_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread.  Nothing
+ *     ever throws across this boundary; the reference-side shim turns non-zero into
+ *     `throw __FILE__ ":...";` so the reference's existing catch blocks keep working
+ *     (make_bloom.cpp:454-501, build_db.cpp:435-453, kwage.cpp:180-187).
+ *   - the library owns all device memory; the caller owns every host buffer.  Host input buffers
+ *     may be reused as soon as the call returns.
+ *   - one handle = one CUDA stream, no global mutable state: handles may be used from different
+ *     host threads concurrently (kwage.cpp:76-87 enters search() from an OpenMP region); a single
+ *     handle must not be used by two threads at once.
+ *   - there is NO CPU fallback: with no usable CUDA device every call fails with KWG_ERR_CUDA.
+ *   - bit order everywhere is the reference's BitVector order (bloom.h:131-163): bit i of a
+ *     vector lives in byte i/8 at bit position i%8.
+ *   - functions suffixed _dev take DEVICE pointers (already resident in HBM) and run
+ *     asynchronously on the handle's stream unless stated otherwise.
+ */
+#ifndef KWAGE_CUDA_H
+#define KWAGE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KWG_MAX_KMER_LEN 32   /* reference word.h:10 */
+#define KWG_MAX_NUM_HASH 8    /* reference hash.cpp:7 (construction uses <= 5: bloom.h:21) */
+#define KWG_COUNT_NUM_HASH 5  /* hashes evaluated per k-mer in counting mode: bloom.h:21 */
+
+typedef enum {
+	KWG_OK = 0,
+	KWG_ERR_INVALID_ARG = -1,   /* argument outside the reference's limits */
+	KWG_ERR_CUDA = -2,          /* CUDA runtime error / no device */
+	KWG_ERR_NO_MEMORY = -3,     /* device or pinned-host allocation failed */
+	KWG_ERR_UNSUPPORTED = -4,   /* valid for the reference but not implemented on the device yet */
+	KWG_ERR_STATE = -5          /* call sequence error (e.g. add_reads after finalize) */
+} kwg_status;
+
+const char* kwg_last_error(void);
+const char* kwg_version(void);
+int kwg_device_count(int* count);
+/* Number of kernels this library has launched from the calling process so far (monotonic). */
+uint64_t kwg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Bloom construction.  Replaces, inside make_bloom_filter() (make_bloom.cpp:76): the table
+ * allocation 151-166, every count_words() call 201-203/239-241/281-283 (body 506-621), the
+ * num_kmer bookkeeping that feeds the max_num_kmer checks 208/246/288, and the fold 337-354.
+ * NGS iteration, number_of_bases(), optimal_bloom_param(), crc32 and file writing stay on host.
+ *
+ * Counting mode (kwg_bloom_create) reproduces the reference's pair of 4-bit counting Bloom
+ * filters with conservative update (make_bloom.cpp:63-69,546-601) followed by the 5-vector
+ * fold, bit-exactly, for min_kmer_count == 1.  min_kmer_count in [2,15] is order dependent in a
+ * way that has no parallel form and returns KWG_ERR_UNSUPPORTED (hard part 1).
+ *   log2_count_len : log2 of the counting-filter length, [18,32] (make_bloom.cpp:104-129)
+ *   log2_max_len   : opt.max_log_2_filter_len, <= 32 (make_bloom.cpp:137-140)
+ *
+ * Raw mode (kwg_bloom_create_raw) sets bit (murmur3(kmer, seed=h) & (2^log2_len - 1)) for
+ * h < num_hash for every valid canonical k-mer: the ground-truth construction of the reference's
+ * own rig (bloom_test.cpp:268-275).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kwg_bloom kwg_bloom_t;
+
+int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t min_kmer_count,
+	uint32_t log2_count_len, uint32_t log2_max_len);
+int kwg_bloom_create_raw(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len);
+
+/* Reads/fragments as ASCII, concatenated; read r is bases[offsets[r] .. offsets[r+1]).  n_reads+1
+ * offsets.  Stream order = array order (it matters in counting mode).  Any byte other than
+ * ACGTacgt breaks k-mers exactly like word.h:98-100. */
+int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offsets, uint64_t n_reads);
+/* Same, inputs already in HBM.  offsets[0] must be 0 and offsets[n_reads] == n_bases. */
+int kwg_bloom_add_reads_dev(kwg_bloom_t* b, const char* d_bases, const uint64_t* d_offsets,
+	uint64_t n_reads, uint64_t n_bases);
+
+/* Counting mode: number of "valid" k-mers so far == BloomProgress::num_kmer (make_bloom.cpp:563).
+ * Raw mode: number of k-mer occurrences inserted.  Synchronises the handle's stream. */
+int kwg_bloom_num_valid(kwg_bloom_t* b, uint64_t* n);
+
+/* Counting mode: build the final filter for the parameters the host chose with
+ * optimal_bloom_param(); identical to folding valid_bits[h < num_hash] (make_bloom.cpp:337-354).
+ * Raw mode: log2_len/num_hash must equal the creation values.  out_bits: 2^log2_len/8 bytes.
+ * May be called more than once (e.g. with different parameters). */
+int kwg_bloom_finalize(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* out_bits);
+int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* d_out_bits);
+
+/* Forget everything added so far; keeps the allocations for the next accession. */
+int kwg_bloom_reset(kwg_bloom_t* b);
+int kwg_bloom_sync(kwg_bloom_t* b);
+void kwg_bloom_destroy(kwg_bloom_t* b);
+
+/* ------------------------------------------------------------------------------------------
+ * Transposition.  Replaces the body of build_db()'s chunk loop, build_db.cpp:267-304 (memset of
+ * dest + the bit-by-bit scatter 288-303).  File validation, per-filter crc32_z (281-282), the
+ * output crc32_z (307) and all file I/O stay on host.
+ *   filter_chunks : n_filters host pointers, each to chunk_bits/8 bytes of one filter
+ *   chunk_bits    : number of slices in this chunk, a multiple of 8 (build_db.cpp:238-243)
+ *   dest          : chunk_bits * ceil(n_filters/8) bytes, FULLY overwritten, padding bits zero
+ * ------------------------------------------------------------------------------------------ */
+int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_filters,
+	uint64_t chunk_bits, uint8_t* dest);
+/* Device-resident variant: filter j starts at d_filters + j*filter_pitch (pitch % 16 == 0), slice
+ * k is written at d_dest + k*dest_pitch (dest_pitch % 16 == 0, >= ceil(n_filters/8)); bytes of a
+ * slice beyond ceil(n_filters/8) up to dest_pitch are zero-filled.  chunk_bits % 32 == 0.
+ * Runs on `stream` (a cudaStream_t, may be NULL) and does not synchronise. */
+int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitch, uint32_t n_filters,
+	uint64_t chunk_bits, uint8_t* d_dest, uint64_t dest_pitch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Search.  Replaces, inside search() (kwage.cpp:340): k-mer extraction 352-366, the per-k-mer
+ * slice loops 404-483 and the match decision 489-503.  Option parsing, FASTA iteration,
+ * FilterInfo lookup 505-515, MatchResult sorting and CSV/JSON output stay on host.
+ *
+ * A kwg_db_t is the slice region of one database file (or one column slab of it) resident in
+ * HBM: 2^log2_len slices of ceil(n_filters/8) bytes (kwage.h:30-72, build_db.cpp:259-314).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kwg_db kwg_db_t;
+
+typedef struct {
+	uint32_t query;      /* index into the queries of the call */
+	uint32_t filter;     /* column index within this kwg_db_t (add the slab's first column) */
+	uint32_t num_match;  /* MatchResult::num_kmers_found (kwage.cpp:519-520) */
+} kwg_hit_t;
+
+/* slices: host pointer to the file's slice region, 2^log2_len rows of ceil(n_filters_total/8)
+ * bytes.  Only columns [col_begin, col_end) are kept on this device (col_begin % 8 == 0); pass
+ * 0, n_filters_total for the whole file. */
+int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer_len, uint32_t num_hash,
+	uint32_t log2_len, uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end);
+/* Use slices that are already in HBM (e.g. written by kwg_transpose_dev); row k at
+ * d_slices + k*row_pitch, row_pitch % 16 == 0, bits >= n_filters in a row must be zero.
+ * The memory is borrowed, not owned. */
+int kwg_db_attach_dev(kwg_db_t** out, int device, const uint8_t* d_slices, uint64_t row_pitch,
+	uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len, uint32_t n_filters);
+void kwg_db_unload(kwg_db_t* db);
+
+/* queries: concatenated ASCII, query q is bases[offsets[q] .. offsets[q+1]).
+ * n_query_kmers[q] (may be NULL) receives the number of unique canonical k-mers of query q
+ * (kwage.cpp:368).  threshold in (0,1] with the reference's float arithmetic (kwage.cpp:349,388):
+ * 1.0f -> every k-mer must match; otherwise num_match >= (unsigned)(threshold * n).
+ * *hits is allocated by the library (release with kwg_free_hits), ordered by (query, filter). */
+int kwg_search(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
+	uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits);
+/* Same with one pointer per query (the shape search() is called with, kwage.cpp:119,137). */
+int kwg_search_ptrs(kwg_db_t* db, const char* const* queries, const uint64_t* query_len, uint32_t n_queries,
+	float threshold, uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits);
+/* Raw per-filter counts (parity tests, multi-GPU gather): counts[q*n_filters + f]. */
+int kwg_search_counts(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries,
+	uint32_t* n_query_kmers, uint32_t* counts);
+/* Device-resident variant: d_counts is n_queries * count_pitch uint32 (count_pitch >= n_filters,
+ * multiple of 4).  d_n_query_kmers: n_queries uint32.  Asynchronous on the db's stream. */
+int kwg_search_counts_dev(kwg_db_t* db, const char* d_bases, const uint64_t* d_offsets, uint32_t n_queries,
+	uint64_t n_bases, uint32_t* d_n_query_kmers, uint32_t* d_counts, uint64_t count_pitch);
+int kwg_db_sync(kwg_db_t* db);
+void kwg_free_hits(kwg_hit_t* hits);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-side synthetic inputs for benchmarks (same generators as oracle/kwage_oracle.c).
+ * ------------------------------------------------------------------------------------------ */
+int kwg_synth_reads_dev(int device, uint64_t seed, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
+	char* d_bases, uint64_t* d_offsets /* n_reads+1, may be NULL */, void* stream);
+int kwg_synth_filter_bits_dev(int device, uint64_t seed, uint64_t first_filter, uint32_t n_filters,
+	uint64_t filter_bytes, uint64_t filter_pitch, uint8_t* d_filters, void* stream);
+
+/* Elapsed-time helpers on a handle's stream, so that callers that only see the C ABI can time
+ * device work with CUDA events on the stream the kernels actually run on. */
+int kwg_bloom_stream(kwg_bloom_t* b, void** stream);
+int kwg_db_stream(kwg_db_t* db, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KWAGE_CUDA_H */

@@ -1,0 +1,64 @@
+// Shared device helpers and host-side error plumbing for libkwage_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/kwage_cuda.h"
+#include "bitops.cuh"
+
+namespace kwg {
+
+// ---------------------------------------------------------------- host: errors and launch count
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define KWG_CUDA(expr)                                                                              \
+	do {                                                                                            \
+		cudaError_t _e = (expr);                                                                    \
+		if (_e != cudaSuccess) {                                                                    \
+			return ::kwg::fail(_e == cudaErrorMemoryAllocation ? KWG_ERR_NO_MEMORY : KWG_ERR_CUDA,  \
+				std::string(#expr) + ": " + cudaGetErrorString(_e));                                \
+		}                                                                                           \
+	} while (0)
+
+#define KWG_LAUNCHED()                                   \
+	do {                                                 \
+		::kwg::g_launches.fetch_add(1);                  \
+		KWG_CUDA(cudaGetLastError());                    \
+	} while (0)
+
+static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline uint64_t round_up(uint64_t a, uint64_t b) { return ceil_div(a, b) * b; }
+
+int select_device(int device);   // cudaSetDevice with validation
+int sm_count(int device);
+
+// ---------------------------------------------------------------- device: memory access helpers
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ uint32_t ld_nc_u32(const void* p)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void st_na_v4(void* p, uint4 v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+	             :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_na_u32(void* p, uint32_t v)
+{
+	asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+} // namespace kwg

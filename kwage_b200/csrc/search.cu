@@ -1,0 +1,572 @@
+// Bit-sliced search (reference kwage.cpp:340-541) on sm_100a over an HBM-resident slice slab.
+//
+//   query_kmers_kernel : ASCII query -> canonical k-mers -> de-duplicated with a hash set (the
+//                        reference sorts + std::unique, kwage.cpp:362-366; only the SET matters for
+//                        counts) -> murmur3 row indices for every unique k-mer (kwage.cpp:411-412)
+//   search_count_kernel: THE hot kernel.  For every unique query k-mer gather its num_hash slices
+//                        (rows) with 128-bit loads, AND them, and accumulate the per-filter match
+//                        bits in bit-sliced carry-save counters (Harley-Seal, 16 k-mers per block)
+//                        instead of the reference's per-bit increment_count (bloom.h:291-330).
+//                        One thread owns 128 filter columns; the counters are expanded to the
+//                        reference's uint32 counts once per (query, column chunk).
+//   hit kernels        : threshold with the reference's float arithmetic (kwage.cpp:349,388,
+//                        489-503) and compact (query, filter, num_match) in (query, filter) order.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace kwg {
+
+constexpr uint64_t SET_EMPTY = ~0ull;      // never a canonical word: T^32 is not canonical (A^32 is)
+constexpr int QK_THREADS = 128;
+
+// ------------------------------------------------------------------------------------------
+// query -> unique canonical k-mers -> row indices
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t base_code(uint32_t ch)   // 0..3, or 4 for anything else (word.h:80-101)
+{
+	const uint32_t u = ch & 0xDFu;
+	const uint32_t x = (ch >> 1) & 3u;
+	const uint32_t c = x ^ (x >> 1);
+	return (u == 'A' || u == 'C' || u == 'G' || u == 'T') ? c : 4u;
+}
+
+template <int NH>
+__global__ void __launch_bounds__(QK_THREADS)
+query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t k, uint32_t filter_mask,
+	uint64_t* __restrict__ table,       // 2 slots per base: query q owns table[2*o0 .. 2*o1)
+	uint64_t* __restrict__ kmers,       // unique words of query q at kmers[o0 ..)
+	uint32_t* __restrict__ rows,        // row indices at rows[(o0 + i) * NH + h]
+	uint32_t* __restrict__ n_kmers)     // per query, zero-initialised
+{
+	const uint32_t q = blockIdx.x;
+	const uint64_t o0 = offsets[q] - offsets[0], o1 = offsets[q + 1] - offsets[0];
+	const uint64_t len = o1 - o0;
+	if (len < k) return;
+	const uint64_t n_pos = len - k + 1;
+	const uint64_t tsize = 2 * len;
+	uint64_t* tab = table + 2 * o0;
+	const char* s = bases + o0;
+
+	for (uint64_t p = (uint64_t)blockIdx.y * QK_THREADS + threadIdx.x; p < n_pos; p += (uint64_t)gridDim.y * QK_THREADS) {
+		uint64_t sense = 0;
+		bool ok = true;
+		for (uint32_t j = 0; j < k; ++j) {
+			const uint32_t c = base_code((uint8_t)s[p + j]);
+			ok = ok && (c < 4u);
+			sense = (sense << 2) | (c & 3u);
+		}
+		if (!ok) continue;
+		const Canon c = canonical(sense, k);
+		uint64_t slot = mix64(c.word) % tsize;
+		for (;;) {
+			const unsigned long long old = atomicCAS((unsigned long long*)(tab + slot), (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
+			if (old == SET_EMPTY) {
+				const uint32_t i = atomicAdd(n_kmers + q, 1u);
+				kmers[o0 + i] = c.word;
+				uint32_t h[NH];
+				murmur3_multi<NH>(c.low, k, h);
+#pragma unroll
+				for (int t = 0; t < NH; ++t) rows[(o0 + i) * NH + t] = h[t] & filter_mask;
+				break;
+			}
+			if (old == c.word) break;
+			slot = (slot + 1 == tsize) ? 0 : slot + 1;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// gather + AND + bit-sliced count
+// ------------------------------------------------------------------------------------------
+constexpr int SC_WARPS = 8;
+constexpr int SC_THREADS = SC_WARPS * 32;
+constexpr int SC_LOW = 4;                  // ones, twos, fours, eights
+constexpr int SC_UP = 6;                   // 16s .. 512s  -> <= 1024 k-mers per substream per segment
+constexpr int SC_PLANES = SC_LOW + SC_UP;
+constexpr int SC_TOT = 16;                 // planes of the merged per-segment total (< 65536)
+constexpr uint32_t SC_SUB_CAP = 1024;      // k-mers per substream per segment
+constexpr uint32_t SC_SEG_CAP = 32768;     // k-mers per segment (merged counts stay below 2^16)
+
+struct SearchParams {
+	const uint8_t* slab;          // rows of row_pitch bytes
+	uint64_t row_pitch;
+	uint32_t vec_per_row;         // row_pitch / 16
+	uint32_t lanes_per_row;       // power of two <= 32
+	uint32_t n_chunks;            // ceil(vec_per_row / lanes_per_row)
+	const uint64_t* offsets;      // per query, base offsets (device)
+	const uint32_t* rows;         // [(o0 + i) * NH + h]
+	const uint32_t* n_kmers;      // per query
+	uint32_t* counts;             // [q * count_pitch + f]
+	uint64_t count_pitch;         // multiple of 4
+};
+
+template <int NH>
+__global__ void __launch_bounds__(SC_THREADS, 2)
+search_count_kernel(const SearchParams P)
+{
+	extern __shared__ uint32_t sm_planes[];   // [substream][plane][lanes_per_row * 4]
+
+	const uint32_t q = blockIdx.x / P.n_chunks;
+	const uint32_t chunk = blockIdx.x % P.n_chunks;
+	const uint32_t n = P.n_kmers[q];
+	const uint64_t o0 = P.offsets[q] - P.offsets[0];
+
+	const uint32_t lpr = P.lanes_per_row;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t groups = 32u / lpr;
+	const uint32_t nsub = SC_WARPS * groups;
+	const uint32_t sub = warp * groups + lane / lpr;
+	const uint32_t cl = lane % lpr;
+	const uint32_t col4 = chunk * lpr + cl;                 // uint4 index within a row
+	const bool active = col4 < P.vec_per_row;
+	const uint8_t* col_ptr = P.slab + (uint64_t)col4 * 16;
+	const uint32_t words_per_chunk = lpr * 4;               // 32-bit column words handled by this block
+	const uint32_t seg_cap = min(SC_SEG_CAP, nsub * SC_SUB_CAP);
+
+	for (uint32_t seg0 = 0; seg0 == 0 || seg0 < n; seg0 += seg_cap) {
+		const uint32_t seg_n = (n > seg0) ? min(seg_cap, n - seg0) : 0u;
+		const uint32_t* rows = P.rows + (o0 + seg0) * NH;
+
+		uint4 pl[SC_PLANES];
+#pragma unroll
+		for (int i = 0; i < SC_PLANES; ++i) pl[i] = make_uint4(0, 0, 0, 0);
+
+		const uint32_t n_blk = (seg_n + 16 * nsub - 1) / (16 * nsub);
+		if (active) {
+#pragma unroll 1
+			for (uint32_t blk = 0; blk < n_blk; ++blk) {
+				uint4 fA = make_uint4(0, 0, 0, 0), eA = make_uint4(0, 0, 0, 0);
+#pragma unroll
+				for (int quad = 0; quad < 4; ++quad) {
+					uint4 v[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						const uint32_t i = (blk * 16 + quad * 4 + u) * nsub + sub;
+						v[u] = make_uint4(0, 0, 0, 0);
+						if (i < seg_n) {
+							const uint32_t* r = rows + (uint64_t)i * NH;
+							uint4 acc = ld_nc_v4(col_ptr + (uint64_t)__ldg(r) * P.row_pitch);
+#pragma unroll
+							for (int h = 1; h < NH; ++h) acc = and4(acc, ld_nc_v4(col_ptr + (uint64_t)__ldg(r + h) * P.row_pitch));
+							v[u] = acc;
+						}
+					}
+					uint4 tA, tB, f;
+					csa(pl[0], tA, v[0], v[1]);
+					csa(pl[0], tB, v[2], v[3]);
+					csa(pl[1], f, tA, tB);
+					if (quad == 0 || quad == 2) fA = f;
+					else {
+						uint4 e;
+						csa(pl[2], e, fA, f);
+						if (quad == 1) eA = e;
+						else {
+							uint4 c16;
+							csa(pl[3], c16, eA, e);
+							// ripple the "sixteens" carry into the upper planes
+#pragma unroll
+							for (int up = SC_LOW; up < SC_PLANES; ++up) {
+								const uint4 t = and4(pl[up], c16);
+								pl[up].x ^= c16.x; pl[up].y ^= c16.y; pl[up].z ^= c16.z; pl[up].w ^= c16.w;
+								c16 = t;
+							}
+						}
+					}
+				}
+			}
+		}
+
+		// ---- merge the substreams bit-sliced, expand to uint32 counts, write once per segment
+		__syncthreads();   // previous segment's readers are done with sm_planes
+		if (active) {
+#pragma unroll
+			for (int i = 0; i < SC_PLANES; ++i) {
+				uint32_t* dst = sm_planes + ((uint64_t)(sub * SC_PLANES + i) * words_per_chunk) + cl * 4;
+				*reinterpret_cast<uint4*>(dst) = pl[i];
+			}
+		}
+		__syncthreads();
+
+		for (uint32_t w = threadIdx.x; w < words_per_chunk; w += SC_THREADS) {
+			const uint32_t vec = chunk * lpr + (w >> 2);
+			if (vec >= P.vec_per_row) continue;
+			uint32_t tot[SC_TOT];
+#pragma unroll
+			for (int i = 0; i < SC_TOT; ++i) tot[i] = 0;
+			for (uint32_t s = 0; s < nsub; ++s) {
+				uint32_t x[SC_PLANES];
+#pragma unroll
+				for (int i = 0; i < SC_PLANES; ++i) x[i] = sm_planes[(uint64_t)(s * SC_PLANES + i) * words_per_chunk + w];
+				bitsliced_add<SC_PLANES>(tot, x);
+			}
+			const uint64_t col0 = (uint64_t)vec * 128 + (w & 3) * 32;
+			uint32_t* out = P.counts + (uint64_t)q * P.count_pitch + col0;
+#pragma unroll
+			for (int nb = 0; nb < 8; ++nb) {
+				if (col0 + 4 * nb + 4 <= P.count_pitch) {
+					uint4 c = expand_counts4(tot, nb);
+					uint4* o4 = reinterpret_cast<uint4*>(out + 4 * nb);
+					if (seg0 != 0) {
+						const uint4 prev = *o4;
+						c.x += prev.x; c.y += prev.y; c.z += prev.z; c.w += prev.w;
+					}
+					*o4 = c;
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// threshold + compaction
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_hit(uint32_t cnt, uint32_t n, float threshold, bool complete, uint32_t thr)
+{
+	return complete ? (cnt == n) : (cnt >= thr);
+}
+
+// one warp per query; pass 0 counts, pass 1 writes at hit_base[q] in filter order
+template <int PASS>
+__global__ void __launch_bounds__(256)
+hits_kernel(const uint32_t* __restrict__ counts, uint64_t count_pitch, uint32_t n_filters, const uint32_t* __restrict__ n_kmers,
+	uint32_t n_queries, float threshold, uint32_t* __restrict__ hit_count, const uint64_t* __restrict__ hit_base,
+	kwg_hit_t* __restrict__ hits)
+{
+	const uint32_t q = (blockIdx.x * 256 + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (q >= n_queries) return;
+	const uint32_t n = n_kmers[q];
+	if (n == 0) {                                       // kwage.cpp:370-372: query shorter than k
+		if (PASS == 0 && lane == 0) hit_count[q] = 0;
+		return;
+	}
+	const bool complete = (threshold == 1.0f);          // kwage.cpp:349
+	const uint32_t thr = (uint32_t)__fmul_rn(threshold, (float)n);   // kwage.cpp:388
+	const uint32_t* row = counts + (uint64_t)q * count_pitch;
+	uint64_t at = (PASS == 1) ? hit_base[q] : 0;
+	uint32_t total = 0;
+	for (uint32_t f0 = 0; f0 < n_filters; f0 += 32) {
+		const uint32_t f = f0 + lane;
+		const uint32_t cnt = (f < n_filters) ? row[f] : 0u;
+		const bool hit = (f < n_filters) && is_hit(cnt, n, threshold, complete, thr);
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+		if (PASS == 1 && hit) {
+			kwg_hit_t h;
+			h.query = q; h.filter = f; h.num_match = complete ? n : cnt;   // kwage.cpp:519-520
+			hits[at + __popc(m & ((1u << lane) - 1u))] = h;
+		}
+		at += __popc(m);
+		total += __popc(m);
+	}
+	if (PASS == 0 && lane == 0) hit_count[q] = total;
+}
+
+} // namespace kwg
+
+using namespace kwg;
+
+struct kwg_db {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	uint8_t* slab = nullptr;
+	bool owns_slab = false;
+	uint64_t row_pitch = 0;
+	uint32_t k = 0, num_hash = 0, log2_len = 0, n_filters = 0;
+	// per-call scratch, grown on demand
+	char* d_bases = nullptr;          size_t bases_cap = 0;
+	uint64_t* d_offsets = nullptr;    size_t offsets_cap = 0;
+	uint64_t* d_table = nullptr;      size_t table_cap = 0;
+	uint64_t* d_kmers = nullptr;      size_t kmers_cap = 0;
+	uint32_t* d_rows = nullptr;       size_t rows_cap = 0;
+	uint32_t* d_nk = nullptr;         size_t nk_cap = 0;
+	uint32_t* d_counts = nullptr;     size_t counts_cap = 0;
+	uint32_t* d_hit_count = nullptr;  size_t hit_count_cap = 0;
+	uint64_t* d_hit_base = nullptr;   size_t hit_base_cap = 0;
+	kwg_hit_t* d_hits = nullptr;      size_t hits_cap = 0;
+};
+
+static int grow_db(void** p, size_t* cap, size_t need)
+{
+	if (need <= *cap) return KWG_OK;
+	if (*p) KWG_CUDA(cudaFree(*p));
+	*p = nullptr; *cap = 0;
+	const size_t want = round_up(need + need / 8, 256);
+	KWG_CUDA(cudaMalloc(p, want));
+	*cap = want;
+	return KWG_OK;
+}
+
+static int db_common_init(kwg_db* db, int device, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len, uint32_t n_filters)
+{
+	if (kmer_len < 1 || kmer_len > KWG_MAX_KMER_LEN) return fail(KWG_ERR_INVALID_ARG, "kmer_len must be in [1,32] (reference word.h:10)");
+	if (num_hash < 1 || num_hash > KWG_MAX_NUM_HASH) return fail(KWG_ERR_INVALID_ARG, "num_hash must be in [1,8]");
+	if (log2_len > 32) return fail(KWG_ERR_INVALID_ARG, "log2_len must be <= 32 (32-bit hash)");
+	if (n_filters == 0) return fail(KWG_ERR_INVALID_ARG, "n_filters must be > 0");
+	int rc = select_device(device);
+	if (rc) return rc;
+	db->device = device; db->k = kmer_len; db->num_hash = num_hash; db->log2_len = log2_len; db->n_filters = n_filters;
+	KWG_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+	return KWG_OK;
+}
+
+// Device-side pipeline shared by every search entry point.  d_bases/d_offsets on the device.
+static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t* d_offsets, uint32_t n_queries,
+	uint64_t n_bases, uint32_t max_query_len, uint32_t* d_nk, uint32_t* d_counts, uint64_t count_pitch)
+{
+	int rc;
+	if ((rc = grow_db((void**)&db->d_table, &db->table_cap, std::max<uint64_t>(n_bases, 1) * 2 * sizeof(uint64_t)))) return rc;
+	if ((rc = grow_db((void**)&db->d_kmers, &db->kmers_cap, std::max<uint64_t>(n_bases, 1) * sizeof(uint64_t)))) return rc;
+	if ((rc = grow_db((void**)&db->d_rows, &db->rows_cap, std::max<uint64_t>(n_bases, 1) * db->num_hash * sizeof(uint32_t)))) return rc;
+	KWG_CUDA(cudaMemsetAsync(db->d_table, 0xFF, n_bases * 2 * sizeof(uint64_t), db->stream));
+	KWG_CUDA(cudaMemsetAsync(d_nk, 0, (size_t)n_queries * sizeof(uint32_t), db->stream));
+
+	const uint32_t filter_mask = (db->log2_len >= 32) ? 0xFFFFFFFFu : ((1u << db->log2_len) - 1u);
+	const uint32_t parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ceil_div(max_query_len, 8 * QK_THREADS), 1), 256);
+	const dim3 qgrid(n_queries, parts);
+	switch (db->num_hash) {
+#define KWG_CASE(N) case N: query_kmers_kernel<N><<<qgrid, QK_THREADS, 0, db->stream>>>(d_bases, d_offsets, db->k, filter_mask, \
+		db->d_table, db->d_kmers, db->d_rows, d_nk); break;
+		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
+#undef KWG_CASE
+	}
+	KWG_LAUNCHED();
+
+	SearchParams P{};
+	P.slab = db->slab;
+	P.row_pitch = db->row_pitch;
+	P.vec_per_row = (uint32_t)(db->row_pitch / 16);
+	uint32_t lpr = 1;
+	while (lpr < 32 && lpr < P.vec_per_row) lpr <<= 1;
+	P.lanes_per_row = lpr;
+	P.n_chunks = (uint32_t)ceil_div(P.vec_per_row, lpr);
+	P.offsets = d_offsets;
+	P.rows = db->d_rows;
+	P.n_kmers = d_nk;
+	P.counts = d_counts;
+	P.count_pitch = count_pitch;
+	const uint64_t blocks = (uint64_t)n_queries * P.n_chunks;
+	if (blocks > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "too many (query, column chunk) pairs for one launch");
+	const uint32_t nsub = SC_WARPS * (32 / lpr);
+	const size_t smem = (size_t)nsub * SC_PLANES * lpr * 4 * sizeof(uint32_t);
+	switch (db->num_hash) {
+#define KWG_CASE(N) case N: \
+		KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		search_count_kernel<N><<<(unsigned)blocks, SC_THREADS, smem, db->stream>>>(P); break;
+		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
+#undef KWG_CASE
+	}
+	KWG_LAUNCHED();
+	return KWG_OK;
+}
+
+// Host inputs -> device scratch; returns n_bases and the longest query.
+static int stage_queries(kwg_db* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, uint64_t* n_bases_out,
+	uint32_t* max_len_out)
+{
+	const uint64_t off0 = offsets[0];
+	uint64_t max_len = 0;
+	for (uint32_t q = 0; q < n_queries; ++q) {
+		if (offsets[q + 1] < offsets[q]) return fail(KWG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+		max_len = std::max(max_len, offsets[q + 1] - offsets[q]);
+	}
+	if (max_len >= 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "a single query of 2^31 bases or more is not supported");
+	const uint64_t n_bases = offsets[n_queries] - off0;
+	int rc;
+	if ((rc = grow_db((void**)&db->d_bases, &db->bases_cap, n_bases + 16))) return rc;
+	if ((rc = grow_db((void**)&db->d_offsets, &db->offsets_cap, ((size_t)n_queries + 1) * sizeof(uint64_t)))) return rc;
+	if ((rc = grow_db((void**)&db->d_nk, &db->nk_cap, std::max<size_t>(n_queries, 1) * sizeof(uint32_t)))) return rc;
+	if (n_bases) KWG_CUDA(cudaMemcpyAsync(db->d_bases, bases + off0, n_bases, cudaMemcpyHostToDevice, db->stream));
+	KWG_CUDA(cudaMemcpyAsync(db->d_offsets, offsets, ((size_t)n_queries + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, db->stream));
+	*n_bases_out = n_bases;
+	*max_len_out = (uint32_t)max_len;
+	return KWG_OK;
+}
+
+extern "C" {
+
+void kwg_db_unload(kwg_db_t* db)
+{
+	if (!db) return;
+	cudaSetDevice(db->device);
+	if (db->stream) cudaStreamSynchronize(db->stream);
+	if (db->owns_slab) cudaFree(db->slab);
+	cudaFree(db->d_bases); cudaFree(db->d_offsets); cudaFree(db->d_table); cudaFree(db->d_kmers); cudaFree(db->d_rows);
+	cudaFree(db->d_nk); cudaFree(db->d_counts); cudaFree(db->d_hit_count); cudaFree(db->d_hit_base); cudaFree(db->d_hits);
+	if (db->stream) cudaStreamDestroy(db->stream);
+	delete db;
+}
+
+int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer_len, uint32_t num_hash,
+	uint32_t log2_len, uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end)
+{
+	if (!out || !slices) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*out = nullptr;
+	if (col_begin >= col_end || col_end > n_filters_total) return fail(KWG_ERR_INVALID_ARG, "bad column range");
+	if (col_begin % 8) return fail(KWG_ERR_INVALID_ARG, "col_begin must be a multiple of 8");
+	kwg_db* db = new kwg_db();
+	int rc = db_common_init(db, device, kmer_len, num_hash, log2_len, col_end - col_begin);
+	if (rc) { kwg_db_unload(db); return rc; }
+	const uint64_t n_rows = 1ull << log2_len;
+	const uint64_t src_pitch = ceil_div(n_filters_total, 8);
+	const uint64_t width = ceil_div(col_end - col_begin, 8);
+	db->row_pitch = round_up(width, 16);
+	db->owns_slab = true;
+	cudaError_t e = cudaMalloc(&db->slab, (size_t)(n_rows * db->row_pitch));
+	if (e != cudaSuccess) {
+		rc = fail(KWG_ERR_NO_MEMORY, std::string("slice slab: ") + cudaGetErrorString(e));
+		kwg_db_unload(db);
+		return rc;
+	}
+	e = cudaSuccess;
+	if (db->row_pitch != width) e = cudaMemsetAsync(db->slab, 0, (size_t)(n_rows * db->row_pitch), db->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpy2DAsync(db->slab, db->row_pitch, slices + col_begin / 8, src_pitch, width, n_rows, cudaMemcpyHostToDevice, db->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+	if (e != cudaSuccess) {
+		rc = fail(KWG_ERR_CUDA, std::string("slab upload: ") + cudaGetErrorString(e));
+		kwg_db_unload(db);
+		return rc;
+	}
+	*out = db;
+	return KWG_OK;
+}
+
+int kwg_db_attach_dev(kwg_db_t** out, int device, const uint8_t* d_slices, uint64_t row_pitch,
+	uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len, uint32_t n_filters)
+{
+	if (!out || !d_slices) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*out = nullptr;
+	if (row_pitch % 16 || row_pitch < ceil_div(n_filters, 8)) return fail(KWG_ERR_INVALID_ARG, "row_pitch must be a multiple of 16 and cover a slice");
+	if (reinterpret_cast<uintptr_t>(d_slices) & 15u) return fail(KWG_ERR_INVALID_ARG, "d_slices must be 16-byte aligned");
+	kwg_db* db = new kwg_db();
+	int rc = db_common_init(db, device, kmer_len, num_hash, log2_len, n_filters);
+	if (rc) { kwg_db_unload(db); return rc; }
+	db->slab = const_cast<uint8_t*>(d_slices);
+	db->owns_slab = false;
+	db->row_pitch = row_pitch;
+	*out = db;
+	return KWG_OK;
+}
+
+int kwg_search_counts_dev(kwg_db_t* db, const char* d_bases, const uint64_t* d_offsets, uint32_t n_queries,
+	uint64_t n_bases, uint32_t* d_n_query_kmers, uint32_t* d_counts, uint64_t count_pitch)
+{
+	if (!db || !d_bases || !d_offsets || !d_n_query_kmers || !d_counts) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	if (count_pitch % 4 || count_pitch < db->n_filters) return fail(KWG_ERR_INVALID_ARG, "count_pitch must be a multiple of 4 and >= n_filters");
+	if (reinterpret_cast<uintptr_t>(d_counts) & 15u) return fail(KWG_ERR_INVALID_ARG, "d_counts must be 16-byte aligned");
+	if (n_queries == 0) return KWG_OK;
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	// without the host copy of the offsets the longest query is unknown: assume the worst case
+	return search_counts_device(db, d_bases, d_offsets, n_queries, n_bases, (uint32_t)std::min<uint64_t>(n_bases, 0x7FFFFFFFull),
+		d_n_query_kmers, d_counts, count_pitch);
+}
+
+int kwg_search_counts(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries,
+	uint32_t* n_query_kmers, uint32_t* counts)
+{
+	if (!db || !bases || !offsets || !counts) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	if (n_queries == 0) return KWG_OK;
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	uint64_t n_bases = 0;
+	uint32_t max_len = 0;
+	if ((rc = stage_queries(db, bases, offsets, n_queries, &n_bases, &max_len))) return rc;
+	const uint64_t pitch = round_up(db->n_filters, 4);
+	if ((rc = grow_db((void**)&db->d_counts, &db->counts_cap, (size_t)n_queries * pitch * sizeof(uint32_t)))) return rc;
+	if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, n_queries, n_bases, max_len, db->d_nk, db->d_counts, pitch))) return rc;
+	KWG_CUDA(cudaMemcpy2DAsync(counts, (size_t)db->n_filters * sizeof(uint32_t), db->d_counts, pitch * sizeof(uint32_t),
+		(size_t)db->n_filters * sizeof(uint32_t), n_queries, cudaMemcpyDeviceToHost, db->stream));
+	if (n_query_kmers)
+		KWG_CUDA(cudaMemcpyAsync(n_query_kmers, db->d_nk, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	return KWG_OK;
+}
+
+int kwg_search(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
+	uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits)
+{
+	if (!db || !bases || !offsets || !hits || !n_hits) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*hits = nullptr; *n_hits = 0;
+	if (!(threshold > 0.0f && threshold <= 1.0f)) return fail(KWG_ERR_INVALID_ARG, "threshold must be in (0,1] (reference options.cpp:186-191)");
+	if (n_queries == 0) return KWG_OK;
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	uint64_t n_bases = 0;
+	uint32_t max_len = 0;
+	if ((rc = stage_queries(db, bases, offsets, n_queries, &n_bases, &max_len))) return rc;
+	const uint64_t pitch = round_up(db->n_filters, 4);
+	if ((rc = grow_db((void**)&db->d_counts, &db->counts_cap, (size_t)n_queries * pitch * sizeof(uint32_t)))) return rc;
+	if ((rc = grow_db((void**)&db->d_hit_count, &db->hit_count_cap, (size_t)n_queries * sizeof(uint32_t)))) return rc;
+	if ((rc = grow_db((void**)&db->d_hit_base, &db->hit_base_cap, (size_t)n_queries * sizeof(uint64_t)))) return rc;
+	if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, n_queries, n_bases, max_len, db->d_nk, db->d_counts, pitch))) return rc;
+
+	const unsigned hgrid = (unsigned)ceil_div((uint64_t)n_queries * 32, 256);
+	hits_kernel<0><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, n_queries, threshold,
+		db->d_hit_count, nullptr, nullptr);
+	KWG_LAUNCHED();
+	std::vector<uint32_t> hc(n_queries);
+	KWG_CUDA(cudaMemcpyAsync(hc.data(), db->d_hit_count, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+	if (n_query_kmers)
+		KWG_CUDA(cudaMemcpyAsync(n_query_kmers, db->d_nk, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	std::vector<uint64_t> base(n_queries);
+	uint64_t total = 0;
+	for (uint32_t q = 0; q < n_queries; ++q) { base[q] = total; total += hc[q]; }
+	if (total == 0) return KWG_OK;
+	if ((rc = grow_db((void**)&db->d_hits, &db->hits_cap, (size_t)total * sizeof(kwg_hit_t)))) return rc;
+	kwg_hit_t* h = (kwg_hit_t*)std::malloc((size_t)total * sizeof(kwg_hit_t));
+	if (!h) return fail(KWG_ERR_NO_MEMORY, "host allocation of the hit list failed");
+	cudaError_t e = cudaMemcpyAsync(db->d_hit_base, base.data(), (size_t)n_queries * sizeof(uint64_t), cudaMemcpyHostToDevice, db->stream);
+	if (e == cudaSuccess) {
+		hits_kernel<1><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, n_queries, threshold,
+			db->d_hit_count, db->d_hit_base, db->d_hits);
+		g_launches.fetch_add(1);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(h, db->d_hits, (size_t)total * sizeof(kwg_hit_t), cudaMemcpyDeviceToHost, db->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+	if (e != cudaSuccess) {
+		std::free(h);
+		return fail(KWG_ERR_CUDA, std::string("hit compaction: ") + cudaGetErrorString(e));
+	}
+	*hits = h;
+	*n_hits = total;
+	return KWG_OK;
+}
+
+int kwg_search_ptrs(kwg_db_t* db, const char* const* queries, const uint64_t* query_len, uint32_t n_queries,
+	float threshold, uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits)
+{
+	if (!queries || !query_len) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	std::vector<uint64_t> offsets((size_t)n_queries + 1, 0);
+	for (uint32_t q = 0; q < n_queries; ++q) offsets[q + 1] = offsets[q] + query_len[q];
+	std::vector<char> flat((size_t)offsets[n_queries] + 1);
+	for (uint32_t q = 0; q < n_queries; ++q)
+		if (query_len[q]) std::memcpy(flat.data() + offsets[q], queries[q], (size_t)query_len[q]);
+	return kwg_search(db, flat.data(), offsets.data(), n_queries, threshold, n_query_kmers, hits, n_hits);
+}
+
+void kwg_free_hits(kwg_hit_t* hits) { std::free(hits); }
+
+int kwg_db_sync(kwg_db_t* db)
+{
+	if (!db) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	return KWG_OK;
+}
+
+int kwg_db_stream(kwg_db_t* db, void** stream)
+{
+	if (!db || !stream) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*stream = (void*)db->stream;
+	return KWG_OK;
+}
+
+} // extern "C"

@@ -398,6 +398,19 @@ void kwo_builder_add_reads(kwo_builder_t* b, const char* bases, const uint64_t* 
 	for (uint64_t r = 0; r < n_reads; ++r) builder_add_fragment(b, bases + offsets[r], offsets[r + 1] - offsets[r]);
 }
 
+/* Same with the reference's early-out: after every fragment make_bloom_filter() returns
+ * STATUS_BLOOM_INVALID as soon as num_kmer exceeds max_num_kmer (make_bloom.cpp:208-214,246-252,
+ * 288-294).  Returns the number of reads consumed (== n_reads when the limit was never crossed). */
+uint64_t kwo_builder_add_reads_limit(kwo_builder_t* b, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+	uint64_t max_num_kmer)
+{
+	for (uint64_t r = 0; r < n_reads; ++r) {
+		builder_add_fragment(b, bases + offsets[r], offsets[r + 1] - offsets[r]);
+		if (max_num_kmer < b->num_valid) return r + 1;
+	}
+	return n_reads;
+}
+
 uint64_t kwo_builder_num_valid(const kwo_builder_t* b) { return b->num_valid; }
 
 /* fold: make_bloom.cpp:337-354.  out_bits holds 2^log2_len/8 bytes and is overwritten. */

@@ -54,6 +54,8 @@ def lib():
         L.kwo_builder_create.argtypes = [u32, u32, u32, u32]
         L.kwo_builder_destroy.argtypes = [p]
         L.kwo_builder_add_reads.argtypes = [p, p, p, u64]
+        L.kwo_builder_add_reads_limit.restype = u64
+        L.kwo_builder_add_reads_limit.argtypes = [p, p, p, u64, u64]
         L.kwo_builder_num_valid.restype = u64
         L.kwo_builder_num_valid.argtypes = [p]
         L.kwo_builder_finalize.argtypes = [p, u32, u32, p]
@@ -161,6 +163,12 @@ class Builder:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         lib().kwo_builder_add_reads(self.h, _ptr(bases), _ptr(offsets), len(offsets) - 1)
 
+    def add_reads_limit(self, bases, offsets, max_num_kmer):
+        """Stops like the reference as soon as num_kmer > max_num_kmer; returns reads consumed."""
+        bases = _bytes_arr(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        return lib().kwo_builder_add_reads_limit(self.h, _ptr(bases), _ptr(offsets), len(offsets) - 1, max_num_kmer)
+
     def num_valid(self):
         return lib().kwo_builder_num_valid(self.h)
 
@@ -185,7 +193,7 @@ def make_bloom(bases, offsets, k, min_count, p, min_log2, max_log2, num_bp):
     max_kmer = approximate_max_kmers(p, min_log2, max_log2)
     b = Builder(k, min_count, lc, max_log2)
     try:
-        b.add_reads(bases, offsets)
+        b.add_reads_limit(bases, offsets, max_kmer)
         n = b.num_valid()
         res = dict(status="invalid", num_kmer=n, log2_count_len=lc, log2_len=0, num_hash=0, bits=None)
         if n > max_kmer:

@@ -1,0 +1,144 @@
+"""GPU parity: Bloom construction through the C ABI vs the oracle and the reference's golden digests."""
+import numpy as np
+import pytest
+
+from kwage_b200 import capi
+from oracle import oracle_py as O
+import synth_cases as S
+import util
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def ragged_case(seed, n_reads=400, max_len=170, n_rate=37, lower_rate=5):
+    flat = S.mutate(O.gen_reads(seed, 0, n_reads, max_len), seed, n_rate=n_rate, lower_rate=lower_rate)
+    return S.ragged(flat, seed, n_reads, 0, max_len)
+
+
+@pytest.mark.parametrize("k,nh,L", [(31, 3, 20), (31, 1, 12), (21, 5, 18), (32, 4, 22), (1, 2, 8), (4, 8, 10), (15, 7, 16),
+                                    (25, 3, 26), (31, 3, 29), (17, 2, 32)])
+def test_raw_insert_bit_exact(k, nh, L):
+    bases, offsets = ragged_case(1000 + k * 7 + nh)
+    exp, n = O.raw_insert(bases, offsets, k, nh, L)
+    with capi.BloomBuilder(k, raw_num_hash=nh, raw_log2_len=L) as b:
+        b.add_reads(bases, offsets)
+        assert b.num_valid() == n
+        got = b.finalize()
+    assert np.array_equal(got, exp)
+
+
+def test_raw_insert_accumulates_over_calls_and_reset():
+    k, nh, L = 31, 3, 22
+    b1, o1 = S.uniform_reads(7, 0, 3000, 150)
+    b2, o2 = ragged_case(8, n_reads=900)
+    exp, n1 = O.raw_insert(b1, o1, k, nh, L)
+    exp, n2 = O.raw_insert(b2, o2, k, nh, L, bits=exp)
+    with capi.BloomBuilder(k, raw_num_hash=nh, raw_log2_len=L) as b:
+        b.add_reads(b1, o1)
+        b.add_reads(b2, o2)
+        assert b.num_valid() == n1 + n2
+        assert np.array_equal(b.finalize(), exp)
+        b.reset()
+        assert b.num_valid() == 0
+        b.add_reads(b2, o2)
+        exp2, _ = O.raw_insert(b2, o2, k, nh, L)
+        assert np.array_equal(b.finalize(), exp2)
+
+
+def test_raw_insert_edge_inputs():
+    k, nh, L = 31, 3, 16
+    with capi.BloomBuilder(k, raw_num_hash=nh, raw_log2_len=L) as b:
+        b.add_reads(np.zeros(0, np.uint8), np.zeros(1, np.uint64))                 # no reads
+        b.add_reads(np.frombuffer(b"ACGT", np.uint8), np.array([0, 0, 4, 4], np.uint64))   # empty + too-short reads
+        assert b.num_valid() == 0 and not b.finalize().any()
+        seq = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTACG", np.uint8)          # exactly one k-mer
+        b.add_reads(seq, np.array([0, 31], np.uint64))
+        exp, n = O.raw_insert(seq, np.array([0, 31], np.uint64), k, nh, L)
+        assert n == 1 and b.num_valid() == 1 and np.array_equal(b.finalize(), exp)
+        # offsets that do not start at zero
+        b.reset()
+        two = np.concatenate([seq, seq[::-1].copy()])
+        b.add_reads(two, np.array([31, 62], np.uint64))
+        exp, _ = O.raw_insert(two, np.array([31, 62], np.uint64), k, nh, L)
+        assert np.array_equal(b.finalize(), exp)
+
+
+def run_counting(case, bases, offsets, split=None):
+    lc = O.counting_log2_len(case["num_bp"])
+    with capi.BloomBuilder(case["k"], min_kmer_count=1, log2_count_len=lc, log2_max_len=case["lmax"]) as b:
+        if split is None:
+            b.add_reads(bases, offsets)
+        else:   # the same stream delivered in several calls (the reference adds one fragment at a time)
+            n = len(offsets) - 1
+            cuts = [0] + [n * i // split for i in range(1, split)] + [n]
+            for a, z in zip(cuts[:-1], cuts[1:]):
+                b.add_reads(bases, offsets[a: z + 1])
+        n_valid = b.num_valid()
+        param = O.optimal_bloom_param(n_valid, case["p"], case["lmin"], case["lmax"])
+        bits = b.finalize(*param) if param else None
+    return lc, n_valid, param, bits
+
+
+@pytest.mark.parametrize("name", ["uniform_k31", "ragged_k21", "k32", "k15_dups", "small_count_filter", "cfg1_mt64"])
+def test_counting_mode_matches_reference_golden(name):
+    g = load_golden("make_bloom")[name]
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    lc, n_valid, param, bits = run_counting(case, bases, offsets)
+    assert lc == g["log2_count_len"]
+    assert n_valid == g["num_kmer"]
+    assert list(param) == [g["log2_len"], g["num_hash"]]
+    assert O.crc32(bits) == g["bits_crc32"]
+    assert util.sha256(bits) == g["bits_sha256"]
+
+
+@pytest.mark.parametrize("name,split", [("ragged_k21", 7), ("small_count_filter", 3), ("k15_dups", 40)])
+def test_counting_mode_is_stream_order_exact_across_calls(name, split):
+    g = load_golden("make_bloom")[name]
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    _, n_valid, param, bits = run_counting(case, bases, offsets, split=split)
+    assert n_valid == g["num_kmer"] and util.sha256(bits) == g["bits_sha256"]
+
+
+def test_counting_mode_finalize_any_parameters_equals_fold():
+    # finalize(L, h) must equal the reference's fold for ANY (L <= Lmax, h <= 5), not just the optimum
+    case = dict(S.MAKE_BLOOM_CASES["ragged_k21"])
+    bases, offsets = S.make_bloom_reads(case)
+    lc = O.counting_log2_len(case["num_bp"])
+    ob = O.Builder(case["k"], 1, lc, case["lmax"])
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(case["k"], min_kmer_count=1, log2_count_len=lc, log2_max_len=case["lmax"]) as b:
+        b.add_reads(bases, offsets)
+        assert b.num_valid() == ob.num_valid()
+        for L, h in [(18, 1), (19, 5), (22, 3), (26, 2)]:
+            assert np.array_equal(b.finalize(L, h), ob.finalize(L, h)), (L, h)
+    ob.close()
+
+
+def test_counting_mode_reset_and_invalid_statuses():
+    case = dict(S.MAKE_BLOOM_CASES["no_kmers"])
+    bases, offsets = S.make_bloom_reads(case)
+    lc = O.counting_log2_len(case["num_bp"])
+    with capi.BloomBuilder(case["k"], min_kmer_count=1, log2_count_len=lc, log2_max_len=case["lmax"]) as b:
+        b.add_reads(bases, offsets)
+        assert b.num_valid() == 0            # -> optimal_bloom_param throws -> STATUS_BLOOM_INVALID on host
+        c2 = dict(S.MAKE_BLOOM_CASES["uniform_k31"])
+        b2, o2 = S.make_bloom_reads(c2)
+        b.add_reads(b2, o2)
+        n_a = b.num_valid()
+        b.reset()
+        b.add_reads(b2, o2)
+        assert b.num_valid() == n_a
+
+
+def test_unsupported_and_bad_arguments_raise():
+    with pytest.raises(capi.KwageError) as e:
+        capi.BloomBuilder(31, min_kmer_count=5, log2_count_len=20, log2_max_len=24)
+    assert e.value.code == capi.KWG_ERR_UNSUPPORTED
+    with pytest.raises(capi.KwageError):
+        capi.BloomBuilder(33, raw_num_hash=3, raw_log2_len=20)
+    with capi.BloomBuilder(31, raw_num_hash=3, raw_log2_len=20) as b:
+        with pytest.raises(capi.KwageError):
+            b.add_reads(np.zeros(10, np.uint8), np.array([5, 2], np.uint64))      # decreasing offsets

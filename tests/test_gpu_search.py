@@ -1,0 +1,110 @@
+"""GPU parity: bit-sliced search through the C ABI vs the oracle and the reference's golden hit lists."""
+import numpy as np
+import pytest
+
+from kwage_b200 import capi
+from oracle import oracle_py as O
+import synth_cases as S
+import util
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def hits_by_query(hits):
+    out = {}
+    for h in hits:
+        out.setdefault(int(h["query"]), []).append((int(h["filter"]), int(h["num_match"])))
+    return out
+
+
+@pytest.mark.parametrize("name", list(S.SEARCH_CASES))
+def test_search_matches_reference_golden(name):
+    g = load_golden("search")[name]
+    case = S.SEARCH_CASES[name]
+    dbd = util.search_case_db(name)
+    queries = S.search_queries(case)
+    seqs = [s for _, s in queries]
+    with capi.Database.load(dbd["slices"], dbd["k"], dbd["h"], dbd["L"], dbd["n"]) as db:
+        counts, nk = db.search_counts(seqs)
+        for qi, s in enumerate(seqs):
+            exp, n = O.search_counts(dbd["slices"], dbd["n"], dbd["L"], dbd["h"], dbd["k"], s)
+            assert nk[qi] == n
+            assert np.array_equal(counts[qi], exp), (name, qi)
+        for t in case["thresholds"]:
+            hits, nk2 = db.search(seqs, t)
+            assert np.array_equal(nk2, nk)
+            assert util.golden_rows_from_hits(queries, hits_by_query(hits), nk) == g["results"][repr(t)], (name, t)
+            hits3, _ = db.search_ptrs(seqs, t)
+            assert np.array_equal(hits3, hits)
+            # ordered by (query, filter)
+            key = hits["query"].astype(np.int64) * (1 << 32) + hits["filter"]
+            assert np.all(np.diff(key) > 0)
+
+
+@pytest.mark.parametrize("n_filters,L,h,k", [(1, 10, 1, 31), (8, 12, 3, 21), (100, 14, 2, 31), (129, 12, 5, 15), (1000, 12, 3, 31),
+                                             (2048, 12, 3, 32), (4100, 10, 4, 31), (9000, 8, 8, 25)])
+def test_search_counts_shapes(n_filters, L, h, k):
+    rng = np.random.default_rng(n_filters + L)
+    row = (n_filters + 7) // 8
+    slices = rng.integers(0, 256, ((1 << L), row), dtype=np.uint8) | rng.integers(0, 256, ((1 << L), row), dtype=np.uint8)
+    if n_filters % 8:
+        slices[:, -1] &= (1 << (n_filters % 8)) - 1            # padding bits are zero in a .db (build_db.cpp:267)
+    seqs = [bytes(O.gen_reads(5, i, 1, ln)).decode() for i, ln in enumerate([0, 10, k, k + 1, 100, 333, 1000, 2500])]
+    seqs.append("ACGTN" * 50)
+    seqs.append("A" * 500)
+    with capi.Database.load(slices, k, h, L, n_filters) as db:
+        counts, nk = db.search_counts(seqs)
+        for qi, s in enumerate(seqs):
+            exp, n = O.search_counts(slices, n_filters, L, h, k, s)
+            assert nk[qi] == n
+            assert np.array_equal(counts[qi], exp), qi
+        for t in (1.0, 0.7, 0.3):
+            hits, _ = db.search(seqs, t)
+            hb = hits_by_query(hits)
+            for qi, s in enumerate(seqs):
+                hf, hm, n = O.search_matches(slices, n_filters, L, h, k, s, t)
+                assert hb.get(qi, []) == [(int(f), int(m)) for f, m in zip(hf, hm)], (qi, t)
+
+
+def test_search_long_query_many_kmers():
+    # more unique k-mers than one counter segment (32768) exercises the segment loop
+    n_filters, L, h, k = 200, 16, 2, 31
+    rng = np.random.default_rng(9)
+    row = (n_filters + 7) // 8
+    slices = rng.integers(0, 256, ((1 << L), row), dtype=np.uint8) | rng.integers(0, 256, ((1 << L), row), dtype=np.uint8) \
+        | rng.integers(0, 256, ((1 << L), row), dtype=np.uint8)
+    seq = bytes(O.gen_reads(6, 0, 1, 80000)).decode()
+    with capi.Database.load(slices, k, h, L, n_filters) as db:
+        counts, nk = db.search_counts([seq, seq[:100]])
+    exp, n = O.search_counts(slices, n_filters, L, h, k, seq)
+    assert nk[0] == n and n > 70000 and np.array_equal(counts[0], exp)
+
+
+def test_search_column_slabs_equal_whole():
+    # multi-GPU layout: every device holds a column slab; the concatenation of slab counts is the answer
+    dbd = util.search_case_db("random_n257")
+    seqs = [s for _, s in S.search_queries(S.SEARCH_CASES["random_n257"])]
+    with capi.Database.load(dbd["slices"], dbd["k"], dbd["h"], dbd["L"], dbd["n"]) as db:
+        whole, nk = db.search_counts(seqs)
+    parts = []
+    for a, z in [(0, 64), (64, 200), (200, 257)]:
+        with capi.Database.load(dbd["slices"], dbd["k"], dbd["h"], dbd["L"], dbd["n"], col_begin=a, col_end=z) as db:
+            c, nk2 = db.search_counts(seqs)
+            assert np.array_equal(nk2, nk) and c.shape[1] == z - a
+            parts.append(c)
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)
+
+
+def test_search_bad_arguments():
+    dbd = util.search_case_db("random_n257")
+    with capi.Database.load(dbd["slices"], dbd["k"], dbd["h"], dbd["L"], dbd["n"]) as db:
+        for t in (0.0, -0.5, 1.5):
+            with pytest.raises(capi.KwageError):
+                db.search(["ACGT" * 20], t)
+        hits, nk = db.search([], 0.5)
+        assert len(hits) == 0
+    with pytest.raises(capi.KwageError):
+        capi.Database.load(dbd["slices"], 33, 3, dbd["L"], dbd["n"])
+    with pytest.raises(capi.KwageError):
+        capi.Database.load(dbd["slices"], 31, 3, dbd["L"], dbd["n"], col_begin=4, col_end=64)

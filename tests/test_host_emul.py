@@ -1,0 +1,96 @@
+"""CPU: the DEVICE arithmetic (kwage_b200/csrc/bitops.cuh compiled as host C++ with intrinsic shims,
+tests/host_emul/emul.cpp) against the oracle.  Catches kernel-math bugs without a GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+import synth_cases as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def E():
+    e = C.CDLL(os.path.join(HERE, "host_emul", "libkwage_emul.so"))
+    e.emu_scan.restype = C.c_uint64
+    e.emu_synth_rnd.restype = C.c_uint64
+    e.emu_synth_rnd.argtypes = [C.c_uint64] * 3
+    return e
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def scan(E, bases, offsets, k, nh):
+    n = len(bases)
+    words = np.zeros(n + 1, np.uint64)
+    pos = np.zeros(n + 1, np.uint64)
+    hs = np.zeros((n + 1) * nh, np.uint32)
+    cnt = E.emu_scan(p(bases), C.c_uint64(n), p(offsets), C.c_uint64(len(offsets) - 1), C.c_uint32(k), C.c_uint32(nh),
+                     p(words), p(pos), p(hs))
+    return words[:cnt], pos[:cnt], hs[: cnt * nh].reshape(cnt, nh)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 21, 25, 30, 31, 32])
+def test_tile_scan_matches_oracle(E, k):
+    nh = 1 + (k % 8)
+    n_reads = 150
+    flat = S.mutate(O.gen_reads(100 + k, 0, n_reads, 160), 100 + k, n_rate=41, lower_rate=5)
+    bases, offsets = S.ragged(flat, 100 + k, n_reads, 0, 160)     # crosses several 4096-base tiles
+    w, ps, hs = scan(E, bases, offsets, k, nh)
+    ow, op = [], []
+    for r in range(n_reads):
+        a, b = int(offsets[r]), int(offsets[r + 1])
+        ww, ll = O.canonical_kmers(bases[a:b], k)
+        ow.append(ww)
+        op.append(ll + np.uint64(a))
+    ow, op = np.concatenate(ow), np.concatenate(op)
+    assert np.array_equal(w, ow) and np.array_equal(ps, op)
+    sel = np.arange(0, len(ow), max(1, len(ow) // 300))
+    exp = np.array([[O.murmur3_word(int(ow[i]), k, s) for s in range(nh)] for i in sel], dtype=np.uint32).reshape(-1, nh)
+    assert np.array_equal(hs[sel], exp)
+
+
+def test_hash_of_reference_layout_word(E):
+    for seq, k in S.HASH_KAT_INPUTS:
+        words, _ = O.canonical_kmers(seq, k)
+        for w in words[:5]:
+            out = np.zeros(5, np.uint32)
+            E.emu_hash_word(C.c_uint64(int(w)), C.c_uint32(k), p(out))
+            assert list(out) == [O.murmur3_word(w, k, s) for s in range(5)]
+
+
+def test_transpose32(E):
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        a = rng.integers(0, 2 ** 32, 32, dtype=np.uint64).astype(np.uint32)
+        out = np.zeros(32, np.uint32)
+        E.emu_transpose32(p(a), p(out))
+        bits = (a[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1      # bits[i][b]
+        exp = (bits.T.astype(np.uint64) << np.arange(32, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("n,nsub", [(0, 8), (1, 8), (15, 8), (16, 8), (17, 8), (970, 8), (4970, 8), (8192, 8), (3000, 64),
+                                    (20000, 256), (32768, 32), (32768, 256)])
+def test_bitsliced_counters(E, n, nsub):
+    rng = np.random.default_rng(n + nsub)
+    vecs = rng.integers(0, 2 ** 32, (max(n, 1), 4), dtype=np.uint64).astype(np.uint32)
+    if n > 5000:
+        vecs |= rng.integers(0, 2 ** 32, (n, 4), dtype=np.uint64).astype(np.uint32)   # dense: large counts
+    counts = np.zeros(128, np.uint32)
+    E.emu_count128(p(vecs), C.c_uint32(n), C.c_uint32(nsub), p(counts))
+    exp = np.zeros(128, np.uint64)
+    if n:
+        b = (vecs[:n, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
+        exp = b.reshape(n, 128).sum(axis=0)
+    assert np.array_equal(counts.astype(np.uint64), exp.astype(np.uint64))
+
+
+def test_synth_generator_agrees(E):
+    for seed, stream, ctr in [(0, 0, 0), (1, 2, 3), (12345, 999999, 1 << 40), (2 ** 64 - 1, 2 ** 63, 7)]:
+        assert E.emu_synth_rnd(seed, stream, ctr) == O.lib().kwo_rnd(seed, stream, ctr) == int(S.rnd(seed, stream, ctr))
