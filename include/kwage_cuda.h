@@ -135,6 +135,13 @@ typedef struct {
  * 0, n_filters_total for the whole file. */
 int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer_len, uint32_t num_hash,
 	uint32_t log2_len, uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end);
+/* Streaming variant for slice regions larger than host memory: allocate the (zeroed) slab for
+ * columns [col_begin, col_end) of a file with n_filters_total columns, then upload row ranges in
+ * any order.  rows: n_rows consecutive slices of the FILE layout (ceil(n_filters_total/8) bytes
+ * each) starting at slice row_begin. */
+int kwg_db_alloc(kwg_db_t** out, int device, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len,
+	uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end);
+int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
 /* Use slices that are already in HBM (e.g. written by kwg_transpose_dev); row k at
  * d_slices + k*row_pitch, row_pitch % 16 == 0, bits >= n_filters in a row must be zero.
  * The memory is borrowed, not owned. */
@@ -169,6 +176,20 @@ int kwg_synth_reads_dev(int device, uint64_t seed, uint64_t first_read, uint64_t
 	char* d_bases, uint64_t* d_offsets /* n_reads+1, may be NULL */, void* stream);
 int kwg_synth_filter_bits_dev(int device, uint64_t seed, uint64_t first_filter, uint32_t n_filters,
 	uint64_t filter_bytes, uint64_t filter_pitch, uint8_t* d_filters, void* stream);
+
+/* Per-kernel device timing (CUDA events on the handle's stream around every launch).  Enable, run,
+ * then get: ms[i] / launches[i] accumulate since the last get.  Kernel ids: */
+#define KWG_T_SCAN_A 0      /* bloom: kmer_scan_kernel pass A (counting) or the raw-insert scan */
+#define KWG_T_SCAN_B 1      /* bloom: kmer_scan_kernel pass B */
+#define KWG_T_INSERT 2      /* bloom: insert_words_kernel (finalize) */
+#define KWG_T_AUX 3         /* bloom: mark_read_starts / flatten;  db: query_kmers_kernel */
+#define KWG_T_SEARCH 4      /* db: search_count_kernel */
+#define KWG_T_HITS 5        /* db: hits_kernel */
+#define KWG_T_COUNT 6
+int kwg_bloom_set_timing(kwg_bloom_t* b, int enable);
+int kwg_bloom_get_timing(kwg_bloom_t* b, double* ms /* KWG_T_COUNT */, uint64_t* launches /* KWG_T_COUNT */);
+int kwg_db_set_timing(kwg_db_t* db, int enable);
+int kwg_db_get_timing(kwg_db_t* db, double* ms, uint64_t* launches);
 
 /* Elapsed-time helpers on a handle's stream, so that callers that only see the C ABI can time
  * device work with CUDA events on the stream the kernels actually run on. */

@@ -26,10 +26,12 @@ EXPORTS = [
     "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_reset",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
     "kwg_transpose", "kwg_transpose_dev",
-    "kwg_db_load", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
+    "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
     "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev",
+    "kwg_bloom_set_timing", "kwg_bloom_get_timing", "kwg_db_set_timing", "kwg_db_get_timing",
 ]
+T_SCAN_A, T_SCAN_B, T_INSERT, T_AUX, T_SEARCH, T_HITS, T_COUNT = 0, 1, 2, 3, 4, 5, 6
 
 
 class KwageError(RuntimeError):
@@ -76,6 +78,8 @@ def lib():
     L.kwg_transpose.argtypes = [i32, vp, u32, u64, vp]
     L.kwg_transpose_dev.argtypes = [i32, vp, u64, u32, u64, vp, u64, vp]
     L.kwg_db_load.argtypes = [pvp, i32, vp, u32, u32, u32, u32, u32, u32]
+    L.kwg_db_alloc.argtypes = [pvp, i32, u32, u32, u32, u32, u32, u32]
+    L.kwg_db_upload_rows.argtypes = [vp, u64, u64, vp]
     L.kwg_db_attach_dev.argtypes = [pvp, i32, vp, u64, u32, u32, u32, u32]
     L.kwg_db_unload.argtypes = [vp]
     L.kwg_db_unload.restype = None
@@ -87,6 +91,10 @@ def lib():
     L.kwg_db_stream.argtypes = [vp, pvp]
     L.kwg_free_hits.argtypes = [C.POINTER(Hit)]
     L.kwg_free_hits.restype = None
+    L.kwg_bloom_set_timing.argtypes = [vp, i32]
+    L.kwg_bloom_get_timing.argtypes = [vp, vp, vp]
+    L.kwg_db_set_timing.argtypes = [vp, i32]
+    L.kwg_db_get_timing.argtypes = [vp, vp, vp]
     L.kwg_synth_reads_dev.argtypes = [i32, u64, u64, u64, u32, vp, vp, vp]
     L.kwg_synth_filter_bits_dev.argtypes = [i32, u64, u64, u32, u64, u64, vp, vp]
     _lib = L
@@ -180,6 +188,16 @@ class BloomBuilder:
     def reset(self):
         check(lib().kwg_bloom_reset(self.h))
 
+    def set_timing(self, enable=True):
+        check(lib().kwg_bloom_set_timing(self.h, int(enable)))
+
+    def get_timing(self):
+        """-> (ms[T_COUNT], launches[T_COUNT]) accumulated since the last call; synchronises."""
+        ms = np.zeros(T_COUNT, dtype=np.float64)
+        n = np.zeros(T_COUNT, dtype=np.uint64)
+        check(lib().kwg_bloom_get_timing(self.h, _np_ptr(ms), _np_ptr(n)))
+        return ms, n
+
     def sync(self):
         check(lib().kwg_bloom_sync(self.h))
 
@@ -239,6 +257,18 @@ class Database:
         h = C.c_void_p()
         check(lib().kwg_db_load(C.byref(h), device, _np_ptr(s), kmer_len, num_hash, log2_len, n_filters_total, col_begin, col_end))
         return cls(h, col_end - col_begin, col_begin)
+
+    @classmethod
+    def alloc(cls, kmer_len, num_hash, log2_len, n_filters_total, *, device=0, col_begin=0, col_end=None):
+        if col_end is None:
+            col_end = n_filters_total
+        h = C.c_void_p()
+        check(lib().kwg_db_alloc(C.byref(h), device, kmer_len, num_hash, log2_len, n_filters_total, col_begin, col_end))
+        return cls(h, col_end - col_begin, col_begin)
+
+    def upload_rows(self, row_begin, rows):
+        r = np.ascontiguousarray(rows, dtype=np.uint8)
+        check(lib().kwg_db_upload_rows(self.h, row_begin, r.shape[0], _np_ptr(r)))
 
     @classmethod
     def attach_dev(cls, d_slices_ptr, row_pitch, kmer_len, num_hash, log2_len, n_filters, *, device=0):
@@ -305,6 +335,15 @@ class Database:
 
     def sync(self):
         check(lib().kwg_db_sync(self.h))
+
+    def set_timing(self, enable=True):
+        check(lib().kwg_db_set_timing(self.h, int(enable)))
+
+    def get_timing(self):
+        ms = np.zeros(T_COUNT, dtype=np.float64)
+        n = np.zeros(T_COUNT, dtype=np.uint64)
+        check(lib().kwg_db_get_timing(self.h, _np_ptr(ms), _np_ptr(n)))
+        return ms, n
 
     def stream(self):
         s = C.c_void_p()

@@ -224,6 +224,7 @@ struct kwg_bloom {
 	size_t offsets_cap = 0;
 	uint32_t* d_start = nullptr;
 	size_t start_cap = 0;
+	KernelTimers timers;
 };
 
 static int grow(void** p, size_t* cap, size_t need)
@@ -276,6 +277,7 @@ static int launch_scan(kwg_bloom* b, const ScanParams& P)
 	if (tiles == 0) return KWG_OK;
 	if (tiles > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "batch too large");
 	const dim3 grid((unsigned)tiles), block(SCAN_THREADS);
+	b->timers.begin(MODE == MODE_PASS_B ? KWG_T_SCAN_B : KWG_T_SCAN_A, b->stream);
 	if (MODE == MODE_RAW) {
 		switch (b->raw_nh) {
 #define KWG_CASE(N) case N: kmer_scan_kernel<MODE_RAW, N><<<grid, block, 0, b->stream>>>(P); break;
@@ -286,6 +288,7 @@ static int launch_scan(kwg_bloom* b, const ScanParams& P)
 	} else {
 		kmer_scan_kernel<MODE, 4><<<grid, block, 0, b->stream>>>(P);
 	}
+	b->timers.end(b->stream);
 	KWG_LAUNCHED();
 	return KWG_OK;
 }
@@ -303,7 +306,9 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	int rc = grow((void**)&b->d_start, &b->start_cap, start_words * sizeof(uint32_t));
 	if (rc) return rc;
 	KWG_CUDA(cudaMemsetAsync(b->d_start, 0, start_words * sizeof(uint32_t), b->stream));
+	b->timers.begin(KWG_T_AUX, b->stream);
 	mark_read_starts_kernel<<<(unsigned)ceil_div(n_reads, 256), 256, 0, b->stream>>>(d_offsets, n_reads, off0, n_bases, b->d_start);
+	b->timers.end(b->stream);
 	KWG_LAUNCHED();
 
 	ScanParams P{};
@@ -514,11 +519,13 @@ int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 		const uint32_t mask = (log2_len >= 32) ? 0xFFFFFFFFu : ((1u << log2_len) - 1u);
 		const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n_valid, 256), (uint64_t)sm_count(b->device) * 16);
 		uint32_t* f = reinterpret_cast<uint32_t*>(d_out_bits);
+		b->timers.begin(KWG_T_INSERT, b->stream);
 		switch (num_hash) {
 #define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_valid, b->k, f, mask); break;
 			KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5)
 #undef KWG_CASE
 		}
+		b->timers.end(b->stream);
 		KWG_LAUNCHED();
 	}
 	return KWG_OK;
@@ -552,6 +559,24 @@ int kwg_bloom_sync(kwg_bloom_t* b)
 	int rc = select_device(b->device);
 	if (rc) return rc;
 	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	return KWG_OK;
+}
+
+int kwg_bloom_set_timing(kwg_bloom_t* b, int enable)
+{
+	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	b->timers.enabled = enable != 0;
+	return KWG_OK;
+}
+
+int kwg_bloom_get_timing(kwg_bloom_t* b, double* ms, uint64_t* launches)
+{
+	if (!b || !ms || !launches) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	int rc = select_device(b->device);
+	if (rc) return rc;
+	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	for (int i = 0; i < KWG_T_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+	b->timers.collect(ms, launches, KWG_T_COUNT);
 	return KWG_OK;
 }
 

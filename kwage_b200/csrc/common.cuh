@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/kwage_cuda.h"
 #include "bitops.cuh"
@@ -33,6 +34,38 @@ extern std::atomic<uint64_t> g_launches;
 
 static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static inline uint64_t round_up(uint64_t a, uint64_t b) { return ceil_div(a, b) * b; }
+
+// Optional per-handle kernel timing: CUDA events recorded on the handle's own stream around each
+// kernel launch, summed per kernel id when the caller asks (kwg_*_get_timing).
+struct KernelTimers {
+	struct Span { int id; cudaEvent_t a, b; };
+	bool enabled = false;
+	std::vector<Span> spans;
+	void begin(int id, cudaStream_t s)
+	{
+		if (!enabled) return;
+		Span sp{id, nullptr, nullptr};
+		if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+		cudaEventRecord(sp.a, s);
+		spans.push_back(sp);
+	}
+	void end(cudaStream_t s)
+	{
+		if (!enabled || spans.empty()) return;
+		cudaEventRecord(spans.back().b, s);
+	}
+	// caller has synchronised the stream; adds elapsed ms into ms[id] and the launch count into n[id]
+	void collect(double* ms, uint64_t* n, int n_ids)
+	{
+		for (Span& sp : spans) {
+			float t = 0.f;
+			if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess && sp.id >= 0 && sp.id < n_ids) { ms[sp.id] += t; n[sp.id] += 1; }
+			cudaEventDestroy(sp.a);
+			cudaEventDestroy(sp.b);
+		}
+		spans.clear();
+	}
+};
 
 int select_device(int device);   // cudaSetDevice with validation
 int sm_count(int device);

@@ -276,6 +276,7 @@ struct kwg_db {
 	bool owns_slab = false;
 	uint64_t row_pitch = 0;
 	uint32_t k = 0, num_hash = 0, log2_len = 0, n_filters = 0;
+	uint32_t n_filters_total = 0, col_begin = 0;   // file geometry (kwg_db_alloc / kwg_db_load)
 	// per-call scratch, grown on demand
 	char* d_bases = nullptr;          size_t bases_cap = 0;
 	uint64_t* d_offsets = nullptr;    size_t offsets_cap = 0;
@@ -287,6 +288,7 @@ struct kwg_db {
 	uint32_t* d_hit_count = nullptr;  size_t hit_count_cap = 0;
 	uint64_t* d_hit_base = nullptr;   size_t hit_base_cap = 0;
 	kwg_hit_t* d_hits = nullptr;      size_t hits_cap = 0;
+	KernelTimers timers;
 };
 
 static int grow_db(void** p, size_t* cap, size_t need)
@@ -327,12 +329,14 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	const uint32_t filter_mask = (db->log2_len >= 32) ? 0xFFFFFFFFu : ((1u << db->log2_len) - 1u);
 	const uint32_t parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ceil_div(max_query_len, 8 * QK_THREADS), 1), 256);
 	const dim3 qgrid(n_queries, parts);
+	db->timers.begin(KWG_T_AUX, db->stream);
 	switch (db->num_hash) {
 #define KWG_CASE(N) case N: query_kmers_kernel<N><<<qgrid, QK_THREADS, 0, db->stream>>>(d_bases, d_offsets, db->k, filter_mask, \
 		db->d_table, db->d_kmers, db->d_rows, d_nk); break;
 		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
 #undef KWG_CASE
 	}
+	db->timers.end(db->stream);
 	KWG_LAUNCHED();
 
 	SearchParams P{};
@@ -352,6 +356,7 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	if (blocks > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "too many (query, column chunk) pairs for one launch");
 	const uint32_t nsub = SC_WARPS * (32 / lpr);
 	const size_t smem = (size_t)nsub * SC_PLANES * lpr * 4 * sizeof(uint32_t);
+	db->timers.begin(KWG_T_SEARCH, db->stream);
 	switch (db->num_hash) {
 #define KWG_CASE(N) case N: \
 		KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -359,6 +364,7 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
 #undef KWG_CASE
 	}
+	db->timers.end(db->stream);
 	KWG_LAUNCHED();
 	return KWG_OK;
 }
@@ -400,10 +406,10 @@ void kwg_db_unload(kwg_db_t* db)
 	delete db;
 }
 
-int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer_len, uint32_t num_hash,
-	uint32_t log2_len, uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end)
+int kwg_db_alloc(kwg_db_t** out, int device, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len,
+	uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end)
 {
-	if (!out || !slices) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	if (!out) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
 	*out = nullptr;
 	if (col_begin >= col_end || col_end > n_filters_total) return fail(KWG_ERR_INVALID_ARG, "bad column range");
 	if (col_begin % 8) return fail(KWG_ERR_INVALID_ARG, "col_begin must be a multiple of 8");
@@ -411,9 +417,9 @@ int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer
 	int rc = db_common_init(db, device, kmer_len, num_hash, log2_len, col_end - col_begin);
 	if (rc) { kwg_db_unload(db); return rc; }
 	const uint64_t n_rows = 1ull << log2_len;
-	const uint64_t src_pitch = ceil_div(n_filters_total, 8);
-	const uint64_t width = ceil_div(col_end - col_begin, 8);
-	db->row_pitch = round_up(width, 16);
+	db->n_filters_total = n_filters_total;
+	db->col_begin = col_begin;
+	db->row_pitch = round_up(ceil_div(col_end - col_begin, 8), 16);
 	db->owns_slab = true;
 	cudaError_t e = cudaMalloc(&db->slab, (size_t)(n_rows * db->row_pitch));
 	if (e != cudaSuccess) {
@@ -421,18 +427,42 @@ int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer
 		kwg_db_unload(db);
 		return rc;
 	}
-	e = cudaSuccess;
-	if (db->row_pitch != width) e = cudaMemsetAsync(db->slab, 0, (size_t)(n_rows * db->row_pitch), db->stream);
-	if (e == cudaSuccess)
-		e = cudaMemcpy2DAsync(db->slab, db->row_pitch, slices + col_begin / 8, src_pitch, width, n_rows, cudaMemcpyHostToDevice, db->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+	// padding bytes of every row must read as zero (build_db.cpp:267 zeroes them in the file too)
+	e = cudaMemsetAsync(db->slab, 0, (size_t)(n_rows * db->row_pitch), db->stream);
 	if (e != cudaSuccess) {
-		rc = fail(KWG_ERR_CUDA, std::string("slab upload: ") + cudaGetErrorString(e));
+		rc = fail(KWG_ERR_CUDA, std::string("slab clear: ") + cudaGetErrorString(e));
 		kwg_db_unload(db);
 		return rc;
 	}
 	*out = db;
 	return KWG_OK;
+}
+
+int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
+{
+	if (!db || !rows) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	if (!db->owns_slab || db->n_filters_total == 0) return fail(KWG_ERR_STATE, "handle was not created by kwg_db_alloc/kwg_db_load");
+	if (row_begin + n_rows > (1ull << db->log2_len)) return fail(KWG_ERR_INVALID_ARG, "row range outside the filter");
+	if (n_rows == 0) return KWG_OK;
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	const uint64_t src_pitch = ceil_div(db->n_filters_total, 8);
+	const uint64_t width = ceil_div(db->n_filters, 8);
+	KWG_CUDA(cudaMemcpy2DAsync(db->slab + row_begin * db->row_pitch, db->row_pitch, rows + db->col_begin / 8, src_pitch, width, n_rows,
+		cudaMemcpyHostToDevice, db->stream));
+	KWG_CUDA(cudaStreamSynchronize(db->stream));   // the caller may reuse `rows`
+	return KWG_OK;
+}
+
+int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer_len, uint32_t num_hash,
+	uint32_t log2_len, uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end)
+{
+	if (!out || !slices) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	int rc = kwg_db_alloc(out, device, kmer_len, num_hash, log2_len, n_filters_total, col_begin, col_end);
+	if (rc) return rc;
+	rc = kwg_db_upload_rows(*out, 0, 1ull << log2_len, slices);
+	if (rc) { kwg_db_unload(*out); *out = nullptr; }
+	return rc;
 }
 
 int kwg_db_attach_dev(kwg_db_t** out, int device, const uint8_t* d_slices, uint64_t row_pitch,
@@ -506,8 +536,10 @@ int kwg_search(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_
 	if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, n_queries, n_bases, max_len, db->d_nk, db->d_counts, pitch))) return rc;
 
 	const unsigned hgrid = (unsigned)ceil_div((uint64_t)n_queries * 32, 256);
+	db->timers.begin(KWG_T_HITS, db->stream);
 	hits_kernel<0><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, n_queries, threshold,
 		db->d_hit_count, nullptr, nullptr);
+	db->timers.end(db->stream);
 	KWG_LAUNCHED();
 	std::vector<uint32_t> hc(n_queries);
 	KWG_CUDA(cudaMemcpyAsync(hc.data(), db->d_hit_count, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
@@ -559,6 +591,24 @@ int kwg_db_sync(kwg_db_t* db)
 	int rc = select_device(db->device);
 	if (rc) return rc;
 	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	return KWG_OK;
+}
+
+int kwg_db_set_timing(kwg_db_t* db, int enable)
+{
+	if (!db) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	db->timers.enabled = enable != 0;
+	return KWG_OK;
+}
+
+int kwg_db_get_timing(kwg_db_t* db, double* ms, uint64_t* launches)
+{
+	if (!db || !ms || !launches) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	for (int i = 0; i < KWG_T_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+	db->timers.collect(ms, launches, KWG_T_COUNT);
 	return KWG_OK;
 }
 

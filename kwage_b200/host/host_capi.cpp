@@ -1,0 +1,101 @@
+// extern "C" view of the host layer so that tests and bench.py (Python, ctypes) can drive the same
+// C++ entry points a C++ caller uses.  Thin: no logic of its own.
+#include <cstring>
+
+#include "kwage_host.h"
+
+using namespace kwage;
+
+extern "C" {
+
+int kwh_optimal_bloom_param(uint32_t kmer_len, uint64_t num_kmer, float p, uint32_t min_log2, uint32_t max_log2,
+	uint32_t* log2_len, uint32_t* num_hash)
+{
+	try {
+		const BloomParam r = optimal_bloom_param(kmer_len, num_kmer, p, MURMUR_HASH_32, min_log2, max_log2);
+		*log2_len = r.log_2_filter_len;
+		*num_hash = r.num_hash;
+		return 0;
+	}
+	catch (...) { return -1; }
+}
+
+uint64_t kwh_approximate_max_kmers(float p, uint32_t min_log2, uint32_t max_log2)
+{
+	return approximate_max_kmers(p, MURMUR_HASH_32, min_log2, max_log2);
+}
+
+uint32_t kwh_counting_filter_log2_len(uint64_t num_bp) { return counting_filter_log2_len(num_bp); }
+
+uint64_t kwh_str_to_accession(const char* s)
+{
+	try { return str_to_accession(s); } catch (...) { return 0; }
+}
+
+void kwh_accession_to_str(uint64_t acc, char* out, size_t cap)
+{
+	const std::string s = accession_to_str(acc);
+	std::strncpy(out, s.c_str(), cap - 1);
+	out[cap - 1] = 0;
+}
+
+// make_bloom_filter() on a reads file; results through plain out-parameters
+int kwh_make_bloom_file(const char* accession, const char* reads_path, uint64_t num_bp, const char* bloom_dir, uint32_t kmer_len,
+	uint32_t min_kmer_count, float p, uint32_t min_log2, uint32_t max_log2, int device,
+	uint64_t* num_kmer, uint32_t* log2_len, uint32_t* num_hash, uint32_t* log2_count_len, char* error, size_t error_cap)
+{
+	MaestroOptions opt;
+	opt.kmer_len = kmer_len; opt.min_kmer_count = min_kmer_count; opt.false_positive_probability = p;
+	opt.min_log_2_filter_len = min_log2; opt.max_log_2_filter_len = max_log2; opt.device = device;
+	FilterInfo info;
+	BloomParam param;
+	BloomProgress progress;
+	unsigned char status = STATUS_BLOOM_FAIL;
+	try {
+		info.run_accession = str_to_accession(accession);
+		ReadSource* src = open_read_collection(reads_path);
+		status = make_bloom_filter(*src, num_bp, info.run_accession, info, param, progress, bloom_dir, opt);
+		delete src;
+	}
+	catch (const char* e) { progress.error = e; }
+	*num_kmer = progress.num_kmer; *log2_len = param.log_2_filter_len; *num_hash = param.num_hash;
+	*log2_count_len = (uint32_t)progress.log_2_counting_filter_len;
+	if (error && error_cap) { std::strncpy(error, progress.error.c_str(), error_cap - 1); error[error_cap - 1] = 0; }
+	return status;
+}
+
+// write a .bloom file for raw filter bits (metadata: run accession only)
+int kwh_write_bloom_file(const char* path, const char* accession, uint32_t kmer_len, uint32_t log2_len, uint32_t num_hash, const uint8_t* bits)
+{
+	try {
+		BloomParam param;
+		param.kmer_len = kmer_len; param.log_2_filter_len = log2_len; param.num_hash = num_hash; param.hash_func = MURMUR_HASH_32;
+		FilterInfo info;
+		info.run_accession = str_to_accession(accession);
+		std::ofstream fout(path, std::ios::binary);
+		if (!fout) return 0;
+		write_bloom_file(fout, param, info, bits);
+		return fout ? 1 : 0;
+	}
+	catch (...) { return 0; }
+}
+
+// build_db(); bloom file paths separated by '\n'
+int kwh_build_db(const char* filename, uint32_t kmer_len, uint32_t log2_len, uint32_t num_hash, const char* bloom_paths, int device)
+{
+	BloomParam param;
+	param.kmer_len = kmer_len; param.log_2_filter_len = log2_len; param.num_hash = num_hash; param.hash_func = MURMUR_HASH_32;
+	std::deque<std::string> files;
+	const char* p = bloom_paths;
+	while (*p) {
+		const char* e = std::strchr(p, '\n');
+		const std::string s = e ? std::string(p, e) : std::string(p);
+		if (!s.empty()) files.push_back(s);
+		if (!e) break;
+		p = e + 1;
+	}
+	set_build_db_device(device);
+	return build_db(filename, param, files) ? 1 : 0;
+}
+
+} // extern "C"

@@ -1,0 +1,203 @@
+// kwage -- search KWAGE bit-sliced databases with DNA queries.  Same command line as the reference's
+// kwage (options.cpp:39-192: -o, --o.csv, --o.json, -t, -d, -i, positional sequences) plus
+// --device <n>.  Output assembly follows kwage.cpp:189-319 (results sorted by num_kmers_found,
+// command-line sequences first, then file records by id).
+#include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <sstream>
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include "kwage_host.h"
+
+using namespace kwage;
+
+namespace {
+
+bool ends_with(const std::string& s, const std::string& suffix)
+{
+	return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+
+// -d accepts files or directories searched recursively for *.db (options.cpp:30-33, file_util.h)
+void collect_db_files(const std::string& path, std::deque<std::string>& out)
+{
+	struct stat st;
+	if (::stat(path.c_str(), &st) != 0) throw __FILE__ ":main: Unable to stat database path";
+	if (S_ISDIR(st.st_mode)) {
+		DIR* d = opendir(path.c_str());
+		if (!d) return;
+		std::vector<std::string> names;
+		while (struct dirent* e = readdir(d)) {
+			const std::string n = e->d_name;
+			if (n != "." && n != "..") names.push_back(n);
+		}
+		closedir(d);
+		std::sort(names.begin(), names.end());
+		for (size_t i = 0; i < names.size(); ++i) {
+			const std::string child = path + "/" + names[i];
+			struct stat cs;
+			if (::stat(child.c_str(), &cs) != 0) continue;
+			if (S_ISDIR(cs.st_mode)) collect_db_files(child, out);
+			else if (ends_with(child, ".db")) out.push_back(child);
+		}
+	} else if (ends_with(path, ".db")) {
+		out.push_back(path);
+	}
+}
+
+// FASTA / FASTQ records (gz aware), bases upper-cased, white space dropped, records without
+// bases skipped (parse_sequence.cpp:72-262)
+bool read_queries(const std::string& path, std::vector<std::string>& names, std::vector<std::string>& seqs)
+{
+	gzFile gz = gzopen(path.c_str(), "rb");
+	if (!gz) return false;
+	gzbuffer(gz, 1 << 20);
+	std::string line, name, seq;
+	char buf[1 << 16];
+	bool fastq = false, first = true, have = false;
+	int fq_line = 0;
+	for (;;) {
+		line.clear();
+		bool any = false;
+		while (gzgets(gz, buf, sizeof(buf))) {
+			any = true;
+			size_t n = std::strlen(buf);
+			const bool eol = n && buf[n - 1] == '\n';
+			while (n && (buf[n - 1] == '\n' || buf[n - 1] == '\r')) --n;
+			line.append(buf, n);
+			if (eol) break;
+		}
+		if (!any) break;
+		if (first && !line.empty()) { fastq = line[0] == '@'; first = false; }
+		if (fastq) {
+			if (fq_line == 0) { name = line; while (!name.empty() && (name[0] == '@' || std::isspace((unsigned char)name[0]))) name.erase(0, 1); }
+			else if (fq_line == 1) {
+				seq.clear();
+				for (size_t i = 0; i < line.size(); ++i) if (!std::isspace((unsigned char)line[i])) seq.push_back((char)std::toupper((unsigned char)line[i]));
+				if (!seq.empty()) { names.push_back(name); seqs.push_back(seq); }
+			}
+			fq_line = (fq_line + 1) & 3;
+			continue;
+		}
+		if (line.find('>') != std::string::npos) {
+			if (have && !seq.empty()) { names.push_back(name); seqs.push_back(seq); seq.clear(); }
+			name = line;
+			while (!name.empty() && (name[0] == '>' || std::isspace((unsigned char)name[0]))) name.erase(0, 1);
+			have = true;
+		} else {
+			for (size_t i = 0; i < line.size(); ++i) if (!std::isspace((unsigned char)line[i])) seq.push_back((char)std::toupper((unsigned char)line[i]));
+		}
+	}
+	if (!fastq && !seq.empty()) { names.push_back(name); seqs.push_back(seq); }
+	gzclose(gz);
+	return true;
+}
+
+int usage()
+{
+	std::cerr << "Usage for kwage (B200):\n"
+		"\t[-o <output file>] (default is stdout)\n"
+		"\t[--o.csv (output CSV) | --o.json (output JSON)]\n"
+		"\t[-t <search threshold>] (default is 1)\n"
+		"\t-d <database search path> (can be repeated)\n"
+		"\t[-i <input sequence file>] (can be repeated)\n"
+		"\t[--device <CUDA device>] (default is 0)\n"
+		"\t[<DNA sequence>] (can be repeated)\n";
+	return EXIT_FAILURE;
+}
+
+} // namespace
+
+int main(int argc, char* argv[])
+{
+	try {
+		SearchOptions opt;
+		std::string output_file;
+		std::deque<std::string> db_paths, query_files, query_seq;
+		for (int i = 1; i < argc; ++i) {
+			const std::string a = argv[i];
+			if (a == "-o" && i + 1 < argc) output_file = argv[++i];
+			else if (a == "--o.csv") opt.output_format = SearchOptions::OUTPUT_CSV;
+			else if (a == "--o.json") opt.output_format = SearchOptions::OUTPUT_JSON;
+			else if (a == "-t" && i + 1 < argc) opt.threshold = (float)std::atof(argv[++i]);
+			else if (a == "-d" && i + 1 < argc) db_paths.push_back(argv[++i]);
+			else if (a == "-i" && i + 1 < argc) query_files.push_back(argv[++i]);
+			else if (a == "--device" && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+			else if (a == "-h" || a == "-?") return usage();
+			else if (!a.empty() && a[0] == '-') { std::cerr << '"' << a << "\" is not a valid option!" << std::endl; return usage(); }
+			else query_seq.push_back(a);
+		}
+		if (db_paths.empty()) { std::cerr << "Please provide at least one database file to search (-d)" << std::endl; return usage(); }
+		if (query_files.empty() && query_seq.empty()) { std::cerr << "Please provide at least one query sequence or file" << std::endl; return usage(); }
+		if (!(opt.threshold > 0.0f && opt.threshold <= 1.0f)) { std::cerr << "Please provide: 0.0 < search threshold <= 1.0" << std::endl; return usage(); }
+
+		std::deque<std::string> subject_files;
+		for (size_t i = 0; i < db_paths.size(); ++i) collect_db_files(db_paths[i], subject_files);
+		if (subject_files.empty()) { std::cerr << "Did not find any database files to search" << std::endl; return EXIT_FAILURE; }
+
+		std::vector<std::string> file_names, file_seqs;
+		for (size_t i = 0; i < query_files.size(); ++i)
+			if (!read_queries(query_files[i], file_names, file_seqs)) throw __FILE__ ":main: Unable to open query file";
+		std::vector<std::string> cmd_seqs(query_seq.begin(), query_seq.end());
+		std::vector<size_t> cmd_ids(cmd_seqs.size()), file_ids(file_seqs.size());
+		for (size_t i = 0; i < cmd_ids.size(); ++i) cmd_ids[i] = i;
+		for (size_t i = 0; i < file_ids.size(); ++i) file_ids[i] = i;
+
+		std::unordered_map<size_t, std::deque<MatchResult> > cmd_results, file_results;
+		for (size_t f = 0; f < subject_files.size(); ++f) {          // one database file resident in HBM at a time
+			SubjectDatabase subject(subject_files[f], opt.device);
+			subject.search(cmd_results, cmd_seqs, cmd_ids, opt);
+			subject.search(file_results, file_seqs, file_ids, opt);
+		}
+		for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = cmd_results.begin(); i != cmd_results.end(); ++i)
+			std::sort(i->second.begin(), i->second.end());
+		for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = file_results.begin(); i != file_results.end(); ++i)
+			std::sort(i->second.begin(), i->second.end());
+
+		std::ofstream fout;
+		if (!output_file.empty()) {
+			fout.open(output_file.c_str());
+			if (!fout) throw __FILE__ ":main: Unable to open output file";
+		}
+		std::ostream& out = output_file.empty() ? std::cout : fout;
+		const bool multiple = (cmd_results.size() + file_results.size()) > 1;
+		if (opt.output_format == SearchOptions::OUTPUT_CSV) write_csv_header(out); else write_json_header(out, multiple);
+		bool first = true;
+		std::vector<size_t> ids;
+		for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = cmd_results.begin(); i != cmd_results.end(); ++i) ids.push_back(i->first);
+		std::sort(ids.begin(), ids.end());
+		for (size_t i = 0; i < ids.size(); ++i) {
+			std::stringstream name;
+			name << "command line seq " << ids[i];
+			if (opt.output_format == SearchOptions::OUTPUT_CSV) write_csv(out, name.str(), cmd_results[ids[i]]);
+			else write_json(out, name.str(), multiple, first, opt.threshold, cmd_results[ids[i]]);
+			first = false;
+		}
+		ids.clear();
+		for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = file_results.begin(); i != file_results.end(); ++i) ids.push_back(i->first);
+		std::sort(ids.begin(), ids.end());
+		for (size_t i = 0; i < ids.size(); ++i) {
+			if (opt.output_format == SearchOptions::OUTPUT_CSV) write_csv(out, file_names[ids[i]], file_results[ids[i]]);
+			else write_json(out, file_names[ids[i]], multiple, first, opt.threshold, file_results[ids[i]]);
+			first = false;
+		}
+		if (opt.output_format == SearchOptions::OUTPUT_JSON) write_json_footer(out, multiple);
+	}
+	catch (const char* error) {
+		std::cerr << "Caught the error " << error << std::endl;
+		return EXIT_FAILURE;
+	}
+	catch (const std::exception& error) {
+		std::cerr << "Caught the error " << error.what() << std::endl;
+		return EXIT_FAILURE;
+	}
+	catch (...) {
+		std::cerr << "Caught an unhandled error" << std::endl;
+		return EXIT_FAILURE;
+	}
+	return EXIT_SUCCESS;
+}
