@@ -1,0 +1,549 @@
+#!/usr/bin/env python
+"""bench.py -- KWAGE hot path on B200: Bloom construction (headline), transposition, bit-sliced search.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line
+from rank 0.  A "step" is one pass of the hot path over one batch of synthetic input:
+
+  construct (headline, BASELINE.json configs[1]): one accession = 1e6 synthetic 150 bp reads
+      (1.2e8 k-mer occurrences), k=31, counting mode with min_kmer_count=1, adaptive parameters
+      (p=0.25, L in [18,32]) -> the reference picks L=29, 3 hashes.  Accessions shard across GPUs
+      (weak scaling, no collective).
+  transpose (configs[2]): 4096 filters x 2^26 bits per GPU column slab.
+  search    (configs[3]): 10k x 1 kb queries against the per-GPU slab of the 65,536-accession DB
+      (8192 columns x 2^26 rows = 64 GiB in HBM); hit lists are gathered to rank 0 over NCCL.
+
+`value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer C-ABI calls with
+pinned host buffers (H2D/D2H inside the timed region).  `--impl reference` times the UNMODIFIED
+reference (oracle/_ref, compiled from /root/reference) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+READ_LEN = 150
+P_FALSE = 0.25
+LMIN, LMAX = 18, 32
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, windows):
+        """windows: list of (t0, t1) wall-clock intervals of the timed regions"""
+        sm, smax, reasons = [], 0.0, set()
+        for ts, line in self.lines:
+            if windows and not any(a <= ts <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    def __init__(self, n_gpus):
+        import torch
+        self.torch = torch
+        self.world = env_int("WORLD_SIZE", 1)
+        self.rank = env_int("RANK", 0)
+        self.local_rank = env_int("LOCAL_RANK", 0)
+        self.enabled = self.world > 1
+        if self.enabled:
+            import torch.distributed as dist
+            self.dist = dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+        else:
+            torch.cuda.set_device(0)
+        self.device = self.local_rank if self.enabled else 0
+
+    def barrier(self):
+        if self.enabled:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if not self.enabled:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if not self.enabled:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def finish(self):
+        if self.enabled:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed(D, stream_ptr, fn, steps, warmup, windows):
+    """W untimed + exactly K timed calls of fn(i); CUDA events on the stream the library launches on,
+    barrier + synchronize on both sides, max over ranks.  Returns seconds for the K steps."""
+    torch = D.torch
+    stream = torch.cuda.ExternalStream(stream_ptr) if stream_ptr else torch.cuda.current_stream()
+    for i in range(warmup):
+        fn(i)
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record(stream)
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record(stream)
+    D.barrier()
+    windows.append((w0, time.time()))
+    return D.max_over_ranks(e0.elapsed_time(e1) / 1e3)
+
+
+# ---------------------------------------------------------------------------------------------- construction
+def stage_construct(D, args, windows):
+    import numpy as np
+    torch = D.torch
+    from kwage_b200 import capi, hostapi as H
+    n_reads = args.reads
+    n_bases = n_reads * READ_LEN
+    kmers = n_reads * (READ_LEN - K + 1)
+    lc = H.counting_filter_log2_len(n_bases)
+    dev = D.device
+    pool = min(4, args.steps + args.warmup)
+    d_bases = [torch.empty(n_bases + 16, dtype=torch.uint8, device="cuda") for _ in range(pool)]
+    d_offsets = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    for i in range(pool):      # accession seeds follow SURVEY 8d: 12345 + accession index (distinct per rank)
+        capi.synth_reads_dev(12345 + D.rank * 100000 + i, 0, n_reads, READ_LEN, d_bases[i].data_ptr(), d_offsets.data_ptr(), device=dev)
+    torch.cuda.synchronize()
+    d_out = torch.empty((1 << LMAX) // 8, dtype=torch.uint8, device="cuda")
+    b = capi.BloomBuilder(K, device=dev, min_kmer_count=1, log2_count_len=lc, log2_max_len=LMAX)
+    state = {}
+
+    def step_dev(i):
+        b.reset()
+        b.add_reads_dev(d_bases[i % pool].data_ptr(), d_offsets.data_ptr(), n_reads, n_bases)
+        n_valid = b.num_valid()
+        L, h = H.optimal_bloom_param(K, n_valid, P_FALSE, LMIN, LMAX)     # host-side parameter choice, as in the reference
+        b.finalize_dev(L, h, d_out.data_ptr())
+        state.update(n_valid=n_valid, L=L, h=h)
+
+    # value: inputs resident in HBM
+    for i in range(args.warmup):
+        step_dev(i)
+    b.sync()
+    b.set_timing(True)
+    b.get_timing()
+    launches0 = capi.launch_count()
+    sec = timed(D, b.stream(), step_dev, args.steps, 0, windows)
+    launches = capi.launch_count() - launches0
+    ms, nl = b.get_timing()
+    b.set_timing(False)
+
+    # e2e: pinned host buffers through the host-pointer C-ABI calls
+    h_bases = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
+    h_bases.copy_(d_bases[0][:n_bases])
+    h_offsets = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
+    h_offsets.copy_(d_offsets)
+    h_out = torch.empty((1 << state["L"]) // 8, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_host(i):
+        b.reset()
+        b.add_reads_ptr(h_bases.data_ptr(), h_offsets.data_ptr(), n_reads)
+        n_valid = b.num_valid()
+        L, h = H.optimal_bloom_param(K, n_valid, P_FALSE, LMIN, LMAX)
+        b.finalize_ptr(L, h, h_out.data_ptr())
+
+    sec_e2e = timed(D, b.stream(), step_host, args.steps, min(args.warmup, 2), windows)
+    crc = None
+    if D.rank == 0:
+        import zlib
+        crc = zlib.crc32(h_out.numpy().tobytes()) & 0xFFFFFFFF
+    b.close()
+    del d_bases, d_out
+    torch.cuda.empty_cache()
+
+    n = D.world
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per k-mer occurrence of the dominant kernel (pass A), DESIGN.md section 4:
+    # 4 first-touch slots x (32 B sector read + 32 B sector write-back) + ASCII bases + start-mask bits
+    bytes_per_kmer_a = 4 * 64 + READ_LEN / (READ_LEN - K + 1) * (1 + 1 / 8)
+    t_a = ms[capi.T_SCAN_A] / max(int(nl[capi.T_SCAN_A]), 1) / 1e3
+    achieved = kmers * bytes_per_kmer_a / t_a / 1e9 if t_a > 0 else 0.0
+    step_ms = sec / args.steps * 1e3
+    kernels = {name: round(float(ms[idx]) / args.steps, 4) for name, idx in
+               (("scan_pass_a", capi.T_SCAN_A), ("scan_pass_b", capi.T_SCAN_B), ("insert_words", capi.T_INSERT), ("mark_read_starts", capi.T_AUX))}
+    return {
+        "value": n * kmers * args.steps / sec,
+        "ms_per_step": step_ms,
+        "e2e": {"value": n * kmers * args.steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
+                "d2h_bytes_per_step": (1 << state["L"]) // 8 + 8, "ms_per_step": sec_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "kmer_scan_kernel<PASS_A> (first-touch atomicMin)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_kmer": bytes_per_kmer_a, "kernel_ms": t_a * 1e3, "share_of_step": t_a * 1e3 / step_ms},
+        "kernel_ms_per_step": kernels,
+        "result": {"num_valid_kmers": state["n_valid"], "log2_filter_len": state["L"], "num_hash": state["h"], "log2_counting_filter_len": lc,
+                   "filter_crc32": crc},
+        "kmers_per_step": kmers,
+    }
+
+
+# ---------------------------------------------------------------------------------------------- transposition
+def stage_transpose(D, args, windows):
+    torch = D.torch
+    from kwage_b200 import capi
+    n_filters, L = args.tr_filters, args.tr_log2
+    fbytes = (1 << L) // 8
+    dev = D.device
+    d_in = torch.empty(n_filters * fbytes, dtype=torch.uint8, device="cuda")
+    row_pitch = (n_filters + 7) // 8
+    row_pitch = (row_pitch + 15) // 16 * 16
+    d_out = torch.empty((1 << L) * row_pitch, dtype=torch.uint8, device="cuda")
+    capi.synth_filter_bits_dev(999, D.rank * n_filters, n_filters, fbytes, fbytes, d_in.data_ptr(), device=dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+
+    def step_dev(i):
+        capi.transpose_dev(d_in.data_ptr(), fbytes, n_filters, 1 << L, d_out.data_ptr(), row_pitch, device=dev, stream=stream.cuda_stream)
+
+    steps, warmup = max(2, min(args.steps, 5)), max(3, min(args.warmup, 3))
+    launches0 = capi.launch_count()
+    sec = timed(D, 0, step_dev, steps, warmup, windows)
+    bits = n_filters * (1 << L)
+    del d_in, d_out
+    torch.cuda.empty_cache()
+
+    # e2e: one reference-sized chunk (2048 filters x 4 Mi slices, build_db.cpp:243) through kwg_transpose
+    import ctypes as C
+    nf, cbits = 2048, 1 << 22
+    h_in = torch.empty(nf * cbits // 8, dtype=torch.uint8).pin_memory()
+    h_in.random_(0, 256)
+    h_out = torch.empty(cbits * nf // 8, dtype=torch.uint8).pin_memory()
+    ptrs = (C.c_void_p * nf)(*[h_in.data_ptr() + j * (cbits // 8) for j in range(nf)])
+
+    def step_host(i):
+        capi.check(capi.lib().kwg_transpose(dev, ptrs, nf, cbits, C.c_void_p(h_out.data_ptr())))
+
+    D.barrier()
+    step_host(0)
+    D.barrier()
+    t0 = time.time()
+    for i in range(2):
+        step_host(i)
+    D.barrier()
+    sec_e2e = D.max_over_ranks(time.time() - t0)
+    windows.append((t0, time.time()))
+    n = D.world
+    peak, peak_src = measured_peaks()
+    achieved = 2 * bits / 8 * steps / sec / 1e9
+    return {"metric": "transposed bits/s", "value": n * bits * steps / sec, "unit": "bits/s", "ms_per_step": sec / steps * 1e3,
+            "config": {"n_filters_per_gpu": n_filters, "log2_filter_len": L, "hbm_bytes_per_step": 2 * bits // 8},
+            "e2e": {"value": n * nf * cbits * 2 / sec_e2e, "unit": "bits/s", "h2d_bytes_per_step": nf * cbits // 8, "d2h_bytes_per_step": nf * cbits // 8,
+                    "workload": "kwg_transpose, 2048 filters x 2^22 slices per call (the reference's chunk)"},
+            "roofline": {"bound": "hbm", "kernel": "transpose_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src},
+            "gpu_launches": int(capi.launch_count() - launches0)}
+
+
+# ---------------------------------------------------------------------------------------------- search
+def stage_search(D, args, windows):
+    import numpy as np
+    torch = D.torch
+    from kwage_b200 import capi
+    F, L, h = args.se_filters, args.se_log2, 3
+    nq, qlen = args.se_queries, 1000
+    dev = D.device
+    row_pitch = (F // 8 + 15) // 16 * 16
+    slab = torch.empty((1 << L) * row_pitch, dtype=torch.uint8, device="cuda")
+    capi.synth_filter_bits_dev(777 + D.rank, 0, 1, slab.numel(), slab.numel(), slab.data_ptr(), device=dev)
+    d_q = torch.empty(nq * qlen + 16, dtype=torch.uint8, device="cuda")
+    d_qo = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
+    capi.synth_reads_dev(4242, 0, nq, qlen, d_q.data_ptr(), d_qo.data_ptr(), device=dev)     # same queries on every rank
+    count_pitch = (F + 3) // 4 * 4
+    d_counts = torch.empty(nq * count_pitch, dtype=torch.int32, device="cuda")
+    d_nk = torch.empty(nq, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    db = capi.Database.attach_dev(slab.data_ptr(), row_pitch, K, h, L, F, device=dev)
+
+    def step_dev(i):
+        db.search_counts_dev(d_q.data_ptr(), d_qo.data_ptr(), nq, nq * qlen, d_nk.data_ptr(), d_counts.data_ptr(), count_pitch)
+
+    steps, warmup = max(2, min(args.steps, 5)), 3
+    for i in range(warmup):
+        step_dev(i)
+    db.sync()
+    db.set_timing(True)
+    db.get_timing()
+    launches0 = capi.launch_count()
+    sec = timed(D, db.stream(), step_dev, steps, 0, windows)
+    launches = capi.launch_count() - launches0
+    ms, nl = db.get_timing()
+    db.set_timing(False)
+    n_kmers = int(d_nk.to(torch.int64).sum().item())
+    tests = n_kmers * F
+
+    # e2e: host queries in, thresholded hits out, hit lists gathered on rank 0 over NCCL
+    h_q = torch.empty(nq * qlen, dtype=torch.uint8).pin_memory()
+    h_q.copy_(d_q[: nq * qlen])
+    h_qo = torch.empty(nq + 1, dtype=torch.int64).pin_memory()
+    h_qo.copy_(d_qo)
+    torch.cuda.synchronize()
+    qb, qo = h_q.numpy(), h_qo.numpy().view(np.uint64)
+    n_hits = [0]
+
+    def step_host(i):
+        hits, nk = db.search_flat(qb, qo, 0.5)
+        if D.enabled:      # the one collective of the path: per-slab hit lists -> rank 0
+            mine = torch.from_numpy(hits.view(np.uint32).reshape(-1, 3).astype(np.int32)).cuda()
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(D.world)]
+            D.dist.all_gather(sizes, torch.tensor([mine.shape[0]], dtype=torch.int64, device="cuda"))
+            cap = max(int(max(s.item() for s in sizes)), 1)
+            pad = torch.zeros((cap, 3), dtype=torch.int32, device="cuda")
+            pad[: mine.shape[0]] = mine
+            out = [torch.empty_like(pad) for _ in range(D.world)] if D.rank == 0 else None
+            D.dist.gather(pad, out, dst=0)
+            if D.rank == 0:
+                n_hits[0] = int(sum(s.item() for s in sizes))
+        else:
+            n_hits[0] = len(hits)
+
+    sec_e2e = timed(D, db.stream(), step_host, steps, 1, windows)
+    db.close()
+    del slab, d_counts
+    torch.cuda.empty_cache()
+    n = D.world
+    peak, peak_src = measured_peaks()
+    t_k = ms[capi.T_SEARCH] / max(int(nl[capi.T_SEARCH]), 1) / 1e3
+    alg_bytes = n_kmers * h * (F // 8) + nq * F * 4
+    achieved = alg_bytes / t_k / 1e9 if t_k > 0 else 0.0
+    return {"metric": "filter-kmer tests/s", "value": n * tests * steps / sec, "unit": "tests/s", "ms_per_step": sec / steps * 1e3,
+            "config": {"filters_per_gpu": F, "log2_filter_len": L, "num_hash": h, "queries": nq, "query_len": qlen, "slab_bytes": (1 << L) * row_pitch,
+                       "unique_query_kmers": n_kmers},
+            "e2e": {"value": n * tests * steps / sec_e2e, "unit": "tests/s", "h2d_bytes_per_step": nq * qlen + 8 * (nq + 1), "d2h_bytes_per_step": 12 * n_hits[0] + 4 * nq,
+                    "threshold": 0.5, "hits": n_hits[0]},
+            "roofline": {"bound": "hbm", "kernel": "search_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": t_k * 1e3, "share_of_step": t_k * 1e3 / (sec / steps * 1e3),
+                         "algorithmic_bytes": alg_bytes},
+            "kernel_ms_per_step": {"query_kmers": float(ms[capi.T_AUX]) / steps, "search_count": float(ms[capi.T_SEARCH]) / steps},
+            "gpu_launches": int(launches)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference
+def reference_construct(n_proc, reads_per_proc, steps, warmup):
+    """The UNMODIFIED reference make_bloom_filter (oracle/_ref/ref_driver), one accession per process,
+    n_proc processes at once (= the reference's MPI worker model without MPI).  Returns
+    (k-mer occurrences / s aggregate, description, kind)."""
+    import numpy as np
+    from oracle import oracle_py as O
+    kmers = reads_per_proc * (READ_LEN - K + 1)
+    tmp = tempfile.mkdtemp(prefix="kwage_ref_")
+    try:
+        nl = np.full((reads_per_proc, 1), ord("\n"), dtype=np.uint8)
+        for p in range(n_proc):
+            d = os.path.join(tmp, "p%d" % p)
+            os.makedirs(d)
+            bases = O.gen_reads(12345 + p, 0, reads_per_proc, READ_LEN).reshape(reads_per_proc, READ_LEN)
+            np.concatenate([bases, nl], axis=1).tofile(os.path.join(d, "SRR%06d.reads" % (p + 1)))
+        if not O.have_ref():
+            # the reference could not travel: time the C restatement instead (single thread)
+            t0 = time.time()
+            bases = O.gen_reads(12345, 0, reads_per_proc, READ_LEN)
+            offsets = np.arange(reads_per_proc + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+            O.make_bloom(bases, offsets, K, 1, P_FALSE, LMIN, LMAX, reads_per_proc * READ_LEN)
+            return kmers / (time.time() - t0), "oracle port, 1 accession of %d reads" % reads_per_proc, "port", 1, time.time() - t0
+
+        def one_step():
+            procs = []
+            for p in range(n_proc):
+                d = os.path.join(tmp, "p%d" % p)
+                env = dict(os.environ, KWAGE_READS_DIR=d)
+                procs.append(subprocess.Popen([os.path.join(O.REF_DIR, "ref_driver"), "make_bloom", "SRR%06d" % (p + 1), d, str(K), "1", str(P_FALSE),
+                                               str(LMIN), str(LMAX), str(reads_per_proc * READ_LEN)], stdout=subprocess.PIPE, text=True, env=env))
+            t0 = time.time()
+            outs = [json.loads(p.communicate()[0]) for p in procs]
+            wall = time.time() - t0
+            assert all(o["status"] == 14 for o in outs), outs
+            return wall
+
+        for _ in range(warmup):
+            one_step()
+        total = sum(one_step() for _ in range(steps))
+        rate = n_proc * kmers * steps / total
+        desc = "make_bloom_filter (reference, unmodified), %d processes x 1 accession of %d reads x %d bp, k=%d, min count 1, L in [%d,%d]" % (
+            n_proc, reads_per_proc, READ_LEN, K, LMIN, LMAX)
+        return rate, desc, "reference", n_proc, total / steps
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def ref_procs():
+    """as many worker processes as cores, bounded by memory (each allocates ~2.6 GiB + counting table)"""
+    cores = cpu_cores()
+    try:
+        with open("/proc/meminfo") as f:
+            avail = [int(l.split()[1]) for l in f if l.startswith("MemAvailable")][0] / 1e6
+        cores = max(1, min(cores, int(avail // 4)))
+    except Exception:
+        pass
+    return cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--stages", default="construct,transpose,search")
+    ap.add_argument("--reads", type=int, default=1000000, help="reads per accession (step)")
+    ap.add_argument("--tr-filters", type=int, default=4096)
+    ap.add_argument("--tr-log2", type=int, default=26)
+    ap.add_argument("--se-filters", type=int, default=8192)
+    ap.add_argument("--se-log2", type=int, default=26)
+    ap.add_argument("--se-queries", type=int, default=10000)
+    ap.add_argument("--cpu-baseline-reads", type=int, default=100000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    stages = [s for s in args.stages.split(",") if s]
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    config = {"workload": "configs[1] Bloom construction: one accession per step = %d synthetic %d bp reads (%.3g k-mer occurrences), "
+                          "k=%d, counting filter with min_kmer_count=1, p=%.2f, L in [%d,%d]; accessions sharded across GPUs" % (
+                              args.reads, READ_LEN, args.reads * (READ_LEN - K + 1), K, P_FALSE, LMIN, LMAX),
+              "reads_per_accession": args.reads, "read_len": READ_LEN, "kmer_len": K, "min_kmer_count": 1,
+              "parallelism": "accession-per-GPU x%d" % world,
+              "l2_policy": "inputs (150 MB reads, 8 GiB first-touch table, 64 GiB slabs) are larger than the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: the whole run should end within a few minutes
+        n_proc = ref_procs()
+        budget_s = 150.0 / max(args.steps + args.warmup, 1)
+        reads = int(min(args.reads, max(20000, budget_s * 0.9e6 / (READ_LEN - K + 1))))
+        rate, desc, kind, cores, step_s = reference_construct(n_proc, reads, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "Bloom k-mer inserts/s", "value": rate, "unit": "kmer_inserts/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": rate, "unit": "kmer_inserts/s", "cores": cores, "kind": kind, "sample": desc},
+                "e2e": {"value": rate, "unit": "kmer_inserts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    D = Dist(args.gpus)
+    from kwage_b200 import capi
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libkwage_cuda has no CPU fallback")
+    sampler = ClockSampler(D.device)
+    if D.rank == 0:
+        sampler.start()
+    windows = []
+    out = {}
+    if "construct" in stages:
+        out["construct"] = stage_construct(D, args, windows)
+    if "transpose" in stages:
+        out["transpose"] = stage_transpose(D, args, windows)
+    if "search" in stages:
+        out["search"] = stage_search(D, args, windows)
+    if D.rank == 0:
+        sampler.stop()
+    cpu = None
+    if D.rank == 0 and world == 1 and not args.no_cpu_baseline and "construct" in stages:
+        n_proc = ref_procs()
+        rate, desc, kind, cores, _ = reference_construct(n_proc, args.cpu_baseline_reads, 1, 0)
+        cpu = {"value": rate, "unit": "kmer_inserts/s", "cores": cores, "kind": kind, "sample": desc}
+    D.finish()
+    if D.rank != 0:
+        return 0
+    head = out.get("construct") or next(iter(out.values()))
+    line = {"metric": "Bloom k-mer inserts/s", "value": head["value"], "unit": "kmer_inserts/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": config, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"], "cpu_baseline": cpu, "clocks": sampler.summary(windows),
+            "stages": {k: v for k, v in out.items()}}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
