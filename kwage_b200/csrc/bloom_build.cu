@@ -6,14 +6,20 @@
 //        earlier occurrence touched it (counters only ever grow from 0 and never wrap for c == 1),
 //        so t is "valid" iff it is the FIRST toucher (minimum stream position) of at least one of
 //        its four slots {first[h0], first[h1], second[h2], second[h3]}.
-//        pass A: T[slot] = min(T[slot], stream position)            (atomicMin, HBM sector RMW)
-//        pass B: valid <=> any T[slot] == own position; valid canonical words are appended to a
+//        pass A: old = atomicMin(T[slot], stream position)          (HBM sector RMW)
+//                old > position  -> this occurrence is (so far) the first toucher: its "won" bit is set;
+//                if old was another occurrence of this batch, that one has just been displaced and
+//                is flagged for a re-check (execution order is not stream order)
+//        pass B: no random access: valid <=> won bit, except flagged occurrences, which re-read their
+//                four slots (T[slot] == own position).  Valid canonical words are appended to a
 //                compact list in HBM (instead of the reference's 5 x 2^Lmax valid_bits vectors)
 //        finalize: for every listed word set bit (hash_h & (2^L-1)), h < num_hash -- which is what
 //                the reference's fold of valid_bits[h] computes (make_bloom.cpp:337-354).
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace kwg {
@@ -45,6 +51,8 @@ struct ScanParams {
 	uint32_t epoch_base;         // stream position of base 0 of this batch within the epoch
 	uint64_t* const* list_chunks;
 	unsigned long long* counter; // valid k-mers (counting) or inserted occurrences (raw)
+	uint32_t* won;               // bit p: occurrence at batch position p was the first toucher of a slot when it ran
+	uint32_t* recheck;           // bit p: occurrence p was displaced afterwards; pass B must re-read its slots
 };
 
 template <int MODE, int NH>
@@ -115,30 +123,48 @@ kmer_scan_kernel(const ScanParams P)
 			}
 		} else {
 			const uint32_t pos = P.epoch_base + (uint32_t)(t0 + p);
-			uint32_t h[4];
-			if (ok) murmur3_multi<4>(c.low, k, h);
 			uint32_t* T1 = P.T;
 			uint32_t* T2 = P.T + P.count_len;
+			const uint32_t lane = tid & 31;
+			const uint64_t word = (t0 + p) >> 5;            // a warp owns one 32-position word of the bitmaps
 			if (MODE == MODE_PASS_A) {
+				bool won = false;
 				if (ok) {
-					atomicMin(T1 + (h[0] & P.count_mask), pos);
-					atomicMin(T1 + (h[1] & P.count_mask), pos);
-					atomicMin(T2 + (h[2] & P.count_mask), pos);
-					atomicMin(T2 + (h[3] & P.count_mask), pos);
+					uint32_t h[4];
+					murmur3_multi<4>(c.low, k, h);
+					uint32_t old[4];
+					old[0] = atomicMin(T1 + (h[0] & P.count_mask), pos);
+					old[1] = atomicMin(T1 + (h[1] & P.count_mask), pos);
+					old[2] = atomicMin(T2 + (h[2] & P.count_mask), pos);
+					old[3] = atomicMin(T2 + (h[3] & P.count_mask), pos);
+#pragma unroll
+					for (int s = 0; s < 4; ++s) {
+						if (old[s] > pos) {
+							won = true;
+							if (old[s] != T_EMPTY) {            // displaced a later occurrence of this batch
+								const uint32_t q = old[s] - P.epoch_base;
+								atomicOr(P.recheck + (q >> 5), 1u << (q & 31));
+							}
+						}
+					}
 				}
+				const uint32_t m = __ballot_sync(0xFFFFFFFFu, won);
+				if (lane == 0) P.won[word] = m;
 			} else {
 				bool valid = false;
 				if (ok) {
-					const uint32_t a = ld_nc_u32(T1 + (h[0] & P.count_mask));
-					const uint32_t b = ld_nc_u32(T1 + (h[1] & P.count_mask));
-					const uint32_t d = ld_nc_u32(T2 + (h[2] & P.count_mask));
-					const uint32_t e = ld_nc_u32(T2 + (h[3] & P.count_mask));
-					valid = (a == pos) | (b == pos) | (d == pos) | (e == pos);
+					const bool flagged = (P.recheck[word] >> lane) & 1u;
+					valid = (P.won[word] >> lane) & 1u;
+					if (flagged) {
+						uint32_t h[4];
+						murmur3_multi<4>(c.low, k, h);
+						valid = (T1[h[0] & P.count_mask] == pos) | (T1[h[1] & P.count_mask] == pos) |
+						        (T2[h[2] & P.count_mask] == pos) | (T2[h[3] & P.count_mask] == pos);
+					}
 				}
 				// warp-aggregated append of the valid canonical words
 				const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
 				if (m) {
-					const uint32_t lane = tid & 31;
 					const uint32_t leader = __ffs(m) - 1;
 					unsigned long long base = 0;
 					if (lane == leader) base = atomicAdd(P.counter, (unsigned long long)__popc(m));
@@ -224,6 +250,10 @@ struct kwg_bloom {
 	size_t offsets_cap = 0;
 	uint32_t* d_start = nullptr;
 	size_t start_cap = 0;
+	uint32_t* d_won = nullptr;
+	size_t won_cap = 0;
+	uint32_t* d_recheck = nullptr;
+	size_t recheck_cap = 0;
 	KernelTimers timers;
 };
 
@@ -336,6 +366,12 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	rc = ensure_list_capacity(b, n_valid + n_bases);
 	if (rc) return rc;
 
+	const size_t bitmap_words = (size_t)(ceil_div(n_bases, TILE_BASES) * (TILE_BASES / 32));
+	if ((rc = grow((void**)&b->d_won, &b->won_cap, bitmap_words * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_recheck, &b->recheck_cap, bitmap_words * sizeof(uint32_t)))) return rc;
+	KWG_CUDA(cudaMemsetAsync(b->d_recheck, 0, bitmap_words * sizeof(uint32_t), b->stream));
+	P.won = b->d_won;
+	P.recheck = b->d_recheck;
 	P.T = b->T;
 	P.count_len = 1ull << b->lc;
 	P.count_mask = (b->lc >= 32) ? 0xFFFFFFFFu : ((1u << b->lc) - 1u);
@@ -351,6 +387,12 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 
 static int bloom_alloc_common(kwg_bloom* b)
 {
+	if (const char* e = getenv("KWG_L2_FETCH")) {    // experiment knob: L2 fetch granularity hint (32/64/128)
+		cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+		size_t v = 0;
+		cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity);
+		fprintf(stderr, "[kwg] L2 fetch granularity = %zu\n", v);
+	}
 	KWG_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	KWG_CUDA(cudaMalloc(&b->d_counter, sizeof(unsigned long long)));
 	KWG_CUDA(cudaMallocHost(&b->h_counter, sizeof(unsigned long long)));
@@ -374,6 +416,8 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_bases);
 	cudaFree(b->d_offsets);
 	cudaFree(b->d_start);
+	cudaFree(b->d_won);
+	cudaFree(b->d_recheck);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	delete b;
 }
