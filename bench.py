@@ -364,21 +364,14 @@ def stage_search(D, args, windows):
     qb, qo = h_q.numpy(), h_qo.numpy().view(np.uint64)
     n_hits = [0]
 
+    from kwage_b200 import sharding
+
     def step_host(i):
         hits, nk = db.search_flat(qb, qo, 0.5)
-        if D.enabled:      # the one collective of the path: per-slab hit lists -> rank 0
-            mine = torch.from_numpy(hits.view(np.uint32).reshape(-1, 3).astype(np.int32)).cuda()
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(D.world)]
-            D.dist.all_gather(sizes, torch.tensor([mine.shape[0]], dtype=torch.int64, device="cuda"))
-            cap = max(int(max(s.item() for s in sizes)), 1)
-            pad = torch.zeros((cap, 3), dtype=torch.int32, device="cuda")
-            pad[: mine.shape[0]] = mine
-            out = [torch.empty_like(pad) for _ in range(D.world)] if D.rank == 0 else None
-            D.dist.gather(pad, out, dst=0)
-            if D.rank == 0:
-                n_hits[0] = int(sum(s.item() for s in sizes))
-        else:
-            n_hits[0] = len(hits)
+        # the one collective of the path: per-slab hit lists -> rank 0 (NCCL gather over NVLink)
+        merged = sharding.gather_hits(hits, D.rank * F, D.dist if D.enabled else None, dst=0, device="cuda")
+        if merged is not None:
+            n_hits[0] = len(merged)
 
     sec_e2e = timed(D, db.stream(), step_host, steps, 1, windows)
     db.close()

@@ -62,8 +62,12 @@ kmer_scan_kernel(const ScanParams P)
 	__shared__ uint32_t s_codes[TILE_VEC + 2];
 	__shared__ uint32_t s_bad[TILE_LOAD / 32 + 2];
 	__shared__ uint32_t s_start[TILE_LOAD / 32 + 2];
+	__shared__ uint64_t s_words[MODE == MODE_PASS_B ? TILE_BASES : 1];   // pass B: valid words of the tile
+	__shared__ uint32_t s_count;
+	__shared__ unsigned long long s_base;
 
 	const uint32_t tid = threadIdx.x;
+	if (tid == 0) s_count = 0;
 	const uint32_t k = P.k;
 	const uint64_t t0 = (uint64_t)blockIdx.x * TILE_BASES;
 
@@ -162,18 +166,30 @@ kmer_scan_kernel(const ScanParams P)
 						        (T2[h[2] & P.count_mask] == pos) | (T2[h[3] & P.count_mask] == pos);
 					}
 				}
-				// warp-aggregated append of the valid canonical words
+				// block-aggregated append: valid words are compacted in shared memory first, so the
+				// whole tile costs ONE atomicAdd on the global list cursor and coalesced stores
 				const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
 				if (m) {
 					const uint32_t leader = __ffs(m) - 1;
-					unsigned long long base = 0;
-					if (lane == leader) base = atomicAdd(P.counter, (unsigned long long)__popc(m));
+					uint32_t base = 0;
+					if (lane == leader) base = atomicAdd(&s_count, (uint32_t)__popc(m));
 					base = __shfl_sync(0xFFFFFFFFu, base, leader);
-					if (valid) {
-						const uint64_t at = base + __popc(m & ((1u << lane) - 1u));
-						P.list_chunks[at >> LIST_CHUNK_LOG2][at & (LIST_CHUNK - 1)] = c.word;
-					}
+					if (valid) s_words[base + __popc(m & ((1u << lane) - 1u))] = c.word;
 				}
+			}
+		}
+	}
+
+	if (MODE == MODE_PASS_B) {
+		__syncthreads();
+		const uint32_t n = s_count;
+		if (n) {
+			if (tid == 0) s_base = atomicAdd(P.counter, (unsigned long long)n);
+			__syncthreads();
+			const unsigned long long base = s_base;
+			for (uint32_t i = tid; i < n; i += SCAN_THREADS) {
+				const uint64_t at = base + i;
+				P.list_chunks[at >> LIST_CHUNK_LOG2][at & (LIST_CHUNK - 1)] = s_words[i];
 			}
 		}
 	}
