@@ -179,13 +179,15 @@ int kwg_synth_filter_bits_dev(int device, uint64_t seed, uint64_t first_filter, 
 
 /* Per-kernel device timing (CUDA events on the handle's stream around every launch).  Enable, run,
  * then get: ms[i] / launches[i] accumulate since the last get.  Kernel ids: */
-#define KWG_T_SCAN_A 0      /* bloom: kmer_scan_kernel pass A (counting) or the raw-insert scan */
-#define KWG_T_SCAN_B 1      /* bloom: kmer_scan_kernel pass B */
+#define KWG_T_SCAN_A 0      /* bloom: partition_scan_kernel (counting) or the raw-insert scan */
+#define KWG_T_SCAN_B 1      /* bloom: kmer_scan_kernel pass B (valid-word list) */
 #define KWG_T_INSERT 2      /* bloom: insert_words_kernel (finalize) */
 #define KWG_T_AUX 3         /* bloom: mark_read_starts / flatten;  db: query_kmers_kernel */
 #define KWG_T_SEARCH 4      /* db: search_count_kernel */
 #define KWG_T_HITS 5        /* db: hits_kernel */
-#define KWG_T_COUNT 6
+#define KWG_T_REGROUP 6     /* bloom: group_count + group_prefix + regroup_kernel (level-2 partition) */
+#define KWG_T_RESOLVE 7     /* bloom: resolve_kernel (first-touch resolution in shared memory) */
+#define KWG_T_COUNT 8
 int kwg_bloom_set_timing(kwg_bloom_t* b, int enable);
 int kwg_bloom_get_timing(kwg_bloom_t* b, double* ms /* KWG_T_COUNT */, uint64_t* launches /* KWG_T_COUNT */);
 int kwg_db_set_timing(kwg_db_t* db, int enable);

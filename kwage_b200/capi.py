@@ -31,7 +31,7 @@ EXPORTS = [
     "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev",
     "kwg_bloom_set_timing", "kwg_bloom_get_timing", "kwg_db_set_timing", "kwg_db_get_timing",
 ]
-T_SCAN_A, T_SCAN_B, T_INSERT, T_AUX, T_SEARCH, T_HITS, T_COUNT = 0, 1, 2, 3, 4, 5, 6
+T_SCAN_A, T_SCAN_B, T_INSERT, T_AUX, T_SEARCH, T_HITS, T_REGROUP, T_RESOLVE, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class KwageError(RuntimeError):

@@ -6,16 +6,15 @@
 //        earlier occurrence touched it (counters only ever grow from 0 and never wrap for c == 1),
 //        so t is "valid" iff it is the FIRST toucher (minimum stream position) of at least one of
 //        its four slots {first[h0], first[h1], second[h2], second[h3]}.
-//        pass A: old = atomicMin(T[slot], stream position)          (HBM sector RMW)
-//                old > position  -> this occurrence is (so far) the first toucher: its "won" bit is set;
-//                if old was another occurrence of this batch, that one has just been displaced and
-//                is flagged for a re-check (execution order is not stream order)
-//        pass B: no random access: valid <=> won bit, except flagged occurrences, which re-read their
-//                four slots (T[slot] == own position).  Valid canonical words are appended to a
-//                compact list in HBM (instead of the reference's 5 x 2^Lmax valid_bits vectors)
+//        The first toucher of every slot is found by radix-partitioning (slot, position) records and
+//        resolving each 2^15-slot bucket in shared memory (bloom_count.cuh); what persists between
+//        batches of one accession is a 1-bit-per-slot "touched" bitmap.
+//        pass B: valid <=> fewer than 4 of the occurrence's touches lost.  Valid canonical words are
+//                appended to a compact list in HBM (instead of the reference's 5 x 2^Lmax valid_bits vectors)
 //        finalize: for every listed word set bit (hash_h & (2^L-1)), h < num_hash -- which is what
 //                the reference's fold of valid_bits[h] computes (make_bloom.cpp:337-354).
 #include "common.cuh"
+#include "bloom_count.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -29,12 +28,11 @@ constexpr int TILE_BASES = 4096;                 // k-mer start positions per ti
 constexpr int TILE_HALO = 32;                    // >= KWG_MAX_KMER_LEN - 1, keeps loads 16-byte granular
 constexpr int TILE_LOAD = TILE_BASES + TILE_HALO;
 constexpr int TILE_VEC = TILE_LOAD / 16;         // 16-base groups per tile
-constexpr uint32_t T_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t LIST_CHUNK_LOG2 = 22;         // valid-word list grows in 32 MiB chunks
 constexpr uint64_t LIST_CHUNK = 1ull << LIST_CHUNK_LOG2;
 constexpr uint64_t MAX_BATCH_BASES = 1ull << 28; // host batches are cut at read boundaries near this
 
-enum ScanMode { MODE_RAW = 0, MODE_PASS_A = 1, MODE_PASS_B = 2 };
+enum ScanMode { MODE_RAW = 0, MODE_PASS_B = 2 };
 
 struct ScanParams {
 	const char* bases;           // device, 16-byte aligned
@@ -45,14 +43,11 @@ struct ScanParams {
 	uint32_t* filter;
 	uint32_t filter_mask;
 	// counting
-	uint32_t* T;                 // [2][2^lc]
-	uint32_t count_mask;
-	uint64_t count_len;
-	uint32_t epoch_base;         // stream position of base 0 of this batch within the epoch
+	uint64_t pos0;               // absolute base index of the first start position of this sub-batch
+	uint64_t n_pos;              // start positions in this sub-batch
 	uint64_t* const* list_chunks;
 	unsigned long long* counter; // valid k-mers (counting) or inserted occurrences (raw)
-	uint32_t* won;               // bit p: occurrence at batch position p was the first toucher of a slot when it ran
-	uint32_t* recheck;           // bit p: occurrence p was displaced afterwards; pass B must re-read its slots
+	const uint32_t* loss;        // 4-bit counters, 8 positions per word: touches of the occurrence that lost
 };
 
 template <int MODE, int NH>
@@ -69,7 +64,8 @@ kmer_scan_kernel(const ScanParams P)
 	const uint32_t tid = threadIdx.x;
 	if (tid == 0) s_count = 0;
 	const uint32_t k = P.k;
-	const uint64_t t0 = (uint64_t)blockIdx.x * TILE_BASES;
+	const uint64_t rel0 = (uint64_t)blockIdx.x * TILE_BASES;   // position inside the sub-batch
+	const uint64_t t0 = P.pos0 + rel0;                          // absolute base index
 
 	// ---- stage 1: 128-bit coalesced loads of the tile (+halo), encode, park in shared memory
 	for (uint32_t v = tid; v < TILE_VEC; v += SCAN_THREADS) {
@@ -108,7 +104,7 @@ kmer_scan_kernel(const ScanParams P)
 		const uint32_t p = it * SCAN_THREADS + tid;
 		// a read that starts strictly inside the window breaks it (fragments are independent,
 		// reference make_bloom.cpp:277-283 calls count_words once per fragment)
-		const bool ok = window_ok(s_bad, s_start, p, k);
+		const bool ok = (rel0 + p < P.n_pos) && window_ok(s_bad, s_start, p, k);
 
 		Canon c;
 		c.word = 0; c.low = 0;
@@ -126,56 +122,21 @@ kmer_scan_kernel(const ScanParams P)
 				++raw_local;
 			}
 		} else {
-			const uint32_t pos = P.epoch_base + (uint32_t)(t0 + p);
-			uint32_t* T1 = P.T;
-			uint32_t* T2 = P.T + P.count_len;
 			const uint32_t lane = tid & 31;
-			const uint64_t word = (t0 + p) >> 5;            // a warp owns one 32-position word of the bitmaps
-			if (MODE == MODE_PASS_A) {
-				bool won = false;
-				if (ok) {
-					uint32_t h[4];
-					murmur3_multi<4>(c.low, k, h);
-					uint32_t old[4];
-					old[0] = atomicMin(T1 + (h[0] & P.count_mask), pos);
-					old[1] = atomicMin(T1 + (h[1] & P.count_mask), pos);
-					old[2] = atomicMin(T2 + (h[2] & P.count_mask), pos);
-					old[3] = atomicMin(T2 + (h[3] & P.count_mask), pos);
-#pragma unroll
-					for (int s = 0; s < 4; ++s) {
-						if (old[s] > pos) {
-							won = true;
-							if (old[s] != T_EMPTY) {            // displaced a later occurrence of this batch
-								const uint32_t q = old[s] - P.epoch_base;
-								atomicOr(P.recheck + (q >> 5), 1u << (q & 31));
-							}
-						}
-					}
-				}
-				const uint32_t m = __ballot_sync(0xFFFFFFFFu, won);
-				if (lane == 0) P.won[word] = m;
-			} else {
-				bool valid = false;
-				if (ok) {
-					const bool flagged = (P.recheck[word] >> lane) & 1u;
-					valid = (P.won[word] >> lane) & 1u;
-					if (flagged) {
-						uint32_t h[4];
-						murmur3_multi<4>(c.low, k, h);
-						valid = (T1[h[0] & P.count_mask] == pos) | (T1[h[1] & P.count_mask] == pos) |
-						        (T2[h[2] & P.count_mask] == pos) | (T2[h[3] & P.count_mask] == pos);
-					}
-				}
-				// block-aggregated append: valid words are compacted in shared memory first, so the
-				// whole tile costs ONE atomicAdd on the global list cursor and coalesced stores
-				const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
-				if (m) {
-					const uint32_t leader = __ffs(m) - 1;
-					uint32_t base = 0;
-					if (lane == leader) base = atomicAdd(&s_count, (uint32_t)__popc(m));
-					base = __shfl_sync(0xFFFFFFFFu, base, leader);
-					if (valid) s_words[base + __popc(m & ((1u << lane) - 1u))] = c.word;
-				}
+			bool valid = false;
+			if (ok) {
+				const uint64_t rel = rel0 + p;
+				valid = ((P.loss[rel >> 3] >> ((rel & 7u) << 2)) & 0xFu) < 4u;
+			}
+			// block-aggregated append: valid words are compacted in shared memory first, so the
+			// whole tile costs ONE atomicAdd on the global list cursor and coalesced stores
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+			if (m) {
+				const uint32_t leader = __ffs(m) - 1;
+				uint32_t base = 0;
+				if (lane == leader) base = atomicAdd(&s_count, (uint32_t)__popc(m));
+				base = __shfl_sync(0xFFFFFFFFu, base, leader);
+				if (valid) s_words[base + __popc(m & ((1u << lane) - 1u))] = c.word;
 			}
 		}
 	}
@@ -211,14 +172,6 @@ __global__ void mark_read_starts_kernel(const uint64_t* __restrict__ offsets, ui
 	if (p < n_bases) atomicOr(start_mask + (p >> 5), 1u << (p & 31));
 }
 
-// epoch roll-over: every touched slot becomes "touched before anything in the new epoch"
-__global__ void flatten_epoch_kernel(uint32_t* __restrict__ T, uint64_t n)
-{
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-		if (T[i] != T_EMPTY) T[i] = 0u;
-}
-
 // finalize (counting mode): set bit (hash_h & mask) for every listed word
 template <int NH>
 __global__ void __launch_bounds__(256)
@@ -249,11 +202,22 @@ struct kwg_bloom {
 	bool raw = false;
 	uint32_t k = 0, min_count = 0, lc = 0, lmax = 0, raw_nh = 0, raw_L = 0;
 	// counting mode
-	uint32_t* T = nullptr;
-	uint64_t epoch_pos = 1;              // next free stream position in the current epoch (0 = "earlier epoch")
+	CountGeom geom{};
+	uint32_t* d_touched = nullptr;       // 2^(lc+1) bits: slot touched by an earlier batch of this accession
 	std::vector<uint64_t*> chunks;
 	uint64_t** d_chunk_table = nullptr;
 	size_t table_cap = 0;
+	// per-batch scratch of the partition pipeline (bloom_count.cuh), grown on demand
+	uint64_t* d_rec1 = nullptr;  size_t rec1_cap = 0;
+	uint64_t* d_rec2 = nullptr;  size_t rec2_cap = 0;
+	uint16_t* d_offs1 = nullptr; size_t offs1_cap = 0;
+	uint16_t* d_offs2 = nullptr; size_t offs2_cap = 0;
+	uint32_t* d_cnt1 = nullptr;  size_t cnt1_cap = 0;
+	uint64_t* d_base2 = nullptr; size_t base2_cap = 0;
+	uint32_t* d_cbase = nullptr; size_t cbase_cap = 0;
+	uint64_t* d_chunk_rec = nullptr; size_t chunk_rec_cap = 0;
+	uint32_t* d_cfirst = nullptr; size_t cfirst_cap = 0;
+	uint32_t* d_loss = nullptr;  size_t loss_cap = 0;
 	// both modes
 	unsigned long long* d_counter = nullptr;
 	unsigned long long* h_counter = nullptr;   // pinned
@@ -266,10 +230,6 @@ struct kwg_bloom {
 	size_t offsets_cap = 0;
 	uint32_t* d_start = nullptr;
 	size_t start_cap = 0;
-	uint32_t* d_won = nullptr;
-	size_t won_cap = 0;
-	uint32_t* d_recheck = nullptr;
-	size_t recheck_cap = 0;
 	KernelTimers timers;
 };
 
@@ -319,7 +279,7 @@ static int ensure_list_capacity(kwg_bloom* b, uint64_t words)
 template <int MODE>
 static int launch_scan(kwg_bloom* b, const ScanParams& P)
 {
-	const uint64_t tiles = ceil_div(P.n_bases, TILE_BASES);
+	const uint64_t tiles = ceil_div(P.n_pos, TILE_BASES);
 	if (tiles == 0) return KWG_OK;
 	if (tiles > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "batch too large");
 	const dim3 grid((unsigned)tiles), block(SCAN_THREADS);
@@ -337,6 +297,128 @@ static int launch_scan(kwg_bloom* b, const ScanParams& P)
 	b->timers.end(b->stream);
 	KWG_LAUNCHED();
 	return KWG_OK;
+}
+
+static size_t partition_smem_bytes()
+{
+	return (size_t)PT_REC * 8 + (size_t)(4 * PT_POS + PT_VEC + 2 + 2 * (PT_LOAD / 32 + 2) + PT_POS / 32 + MAX_FAN + 1 + MAX_FAN + 8) * 4;
+}
+static size_t regroup_smem_bytes()
+{
+	return (size_t)CHUNK_REC * 8 + (size_t)(MAX_FAN + (MAX_FAN + 1) + (MAX_FAN + 1) + MAX_FAN + 8) * 4;
+}
+static size_t resolve_smem_bytes()
+{
+	return (size_t)FINAL_SLOTS * 4 + (size_t)(FINAL_SLOTS / 32) * 4 + (size_t)RS_THREADS * 8 + (size_t)RS_THREADS * 4;
+}
+
+static int count_kernels_init()
+{
+	KWG_CUDA(cudaFuncSetAttribute(partition_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem_bytes()));
+	KWG_CUDA(cudaFuncSetAttribute(regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)regroup_smem_bytes()));
+	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
+	return KWG_OK;
+}
+
+// One sub-batch of the counting construction: start positions [pos0, pos0 + n_pos) of the batch in S.
+// partition (K1) -> [regroup (K2)] -> resolve (K3) -> pass B (valid-word list).
+static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos)
+{
+	const CountGeom& G = b->geom;
+	const uint32_t F1 = 1u << G.f1_log2, F2 = 1u << G.f2_log2;
+	const uint64_t n_tiles = ceil_div(n_pos, PT_POS);
+	const uint32_t ntp = (uint32_t)round_up(n_tiles, 64);
+	const bool two_level = G.f2_log2 != 0;
+	int rc;
+
+	uint64_t n_valid = 0;
+	rc = read_counter(b, &n_valid);
+	if (rc) return rc;
+	rc = ensure_list_capacity(b, n_valid + n_pos);
+	if (rc) return rc;
+
+	const size_t loss_words = (size_t)(n_tiles * PT_POS / 8);
+	if ((rc = grow((void**)&b->d_loss, &b->loss_cap, loss_words * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_rec1, &b->rec1_cap, (size_t)n_tiles * PT_REC * sizeof(uint64_t)))) return rc;
+	if ((rc = grow((void**)&b->d_offs1, &b->offs1_cap, (size_t)(F1 + 1) * ntp * sizeof(uint16_t)))) return rc;
+	KWG_CUDA(cudaMemsetAsync(b->d_loss, 0, loss_words * sizeof(uint32_t), b->stream));
+
+	PartParams K1{};
+	K1.bases = S.bases; K1.n_bases = S.n_bases; K1.start_mask = S.start_mask; K1.k = S.k;
+	K1.pos0 = pos0; K1.n_pos = n_pos;
+	K1.count_mask = G.count_mask;
+	K1.f1_log2 = G.f1_log2;
+	K1.shift1 = FINAL_LOG2 + G.f2_log2;
+	K1.table_shift = G.f1_log2 - 1;
+	K1.ntp = ntp;
+	K1.rec1 = b->d_rec1;
+	K1.offs1 = b->d_offs1;
+	b->timers.begin(KWG_T_SCAN_A, b->stream);
+	partition_scan_kernel<<<(unsigned)n_tiles, PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
+	b->timers.end(b->stream);
+	KWG_LAUNCHED();
+
+	ResolveParams K3{};
+	K3.n_buckets = 1u << G.nb_log2;
+	K3.touched = b->d_touched;
+	K3.loss = b->d_loss;
+	if (!two_level) {
+		K3.rec = b->d_rec1;
+		K3.offs = b->d_offs1;
+		K3.cfirst = nullptr;
+		K3.single_nci = (uint32_t)n_tiles;
+		K3.chunk_rec = nullptr;
+		K3.chunk_stride = PT_REC;
+		K3.row_pitch = ntp;
+		K3.f2_log2 = G.nb_log2;
+	} else {
+		const uint32_t G1 = F1;                                   // tiles per group: ~CHUNK_REC records per (bucket, group)
+		const uint32_t NG = (uint32_t)ceil_div(n_tiles, G1);
+		const size_t n_pairs = (size_t)F1 * NG;
+		const size_t max_chunks = n_pairs + (size_t)n_tiles * PT_REC / CHUNK_REC + 1;
+		if ((rc = grow((void**)&b->d_cnt1, &b->cnt1_cap, n_pairs * sizeof(uint32_t)))) return rc;
+		if ((rc = grow((void**)&b->d_base2, &b->base2_cap, n_pairs * sizeof(uint64_t)))) return rc;
+		if ((rc = grow((void**)&b->d_cbase, &b->cbase_cap, n_pairs * sizeof(uint32_t)))) return rc;
+		if ((rc = grow((void**)&b->d_cfirst, &b->cfirst_cap, (size_t)(F1 + 1) * sizeof(uint32_t)))) return rc;
+		if ((rc = grow((void**)&b->d_chunk_rec, &b->chunk_rec_cap, max_chunks * sizeof(uint64_t)))) return rc;
+		if ((rc = grow((void**)&b->d_offs2, &b->offs2_cap, max_chunks * (F2 + 1) * sizeof(uint16_t)))) return rc;
+		if ((rc = grow((void**)&b->d_rec2, &b->rec2_cap, (size_t)n_tiles * PT_REC * sizeof(uint64_t)))) return rc;
+
+		b->timers.begin(KWG_T_REGROUP, b->stream);
+		group_count_kernel<<<(unsigned)ceil_div(n_pairs, 8), 256, 0, b->stream>>>(b->d_offs1, ntp, (uint32_t)n_tiles, F1, G1, NG, b->d_cnt1);
+		KWG_LAUNCHED();
+		group_prefix_kernel<<<1, 1024, 0, b->stream>>>(b->d_cnt1, (uint32_t)n_pairs, NG, F1, b->d_base2, b->d_cbase, b->d_chunk_rec, b->d_cfirst);
+		KWG_LAUNCHED();
+		RegroupParams K2{};
+		K2.rec1 = b->d_rec1; K2.offs1 = b->d_offs1; K2.ntp = ntp; K2.n_tiles = (uint32_t)n_tiles;
+		K2.F1 = F1; K2.G1 = G1; K2.NG = NG; K2.f2_log2 = G.f2_log2;
+		K2.cnt1 = b->d_cnt1; K2.base2 = b->d_base2; K2.cbase = b->d_cbase; K2.cfirst = b->d_cfirst;
+		K2.rec2 = b->d_rec2; K2.offs2 = b->d_offs2;
+		regroup_kernel<<<(unsigned)n_pairs, PT_THREADS, regroup_smem_bytes(), b->stream>>>(K2);
+		b->timers.end(b->stream);
+		KWG_LAUNCHED();
+
+		K3.rec = b->d_rec2;
+		K3.offs = b->d_offs2;
+		K3.cfirst = b->d_cfirst;
+		K3.single_nci = 0;
+		K3.chunk_rec = b->d_chunk_rec;
+		K3.chunk_stride = 0;
+		K3.row_pitch = 0;
+		K3.f2_log2 = G.f2_log2;
+	}
+	const unsigned rgrid = (unsigned)std::min<uint64_t>(K3.n_buckets, (uint64_t)sm_count(b->device));
+	b->timers.begin(KWG_T_RESOLVE, b->stream);
+	resolve_kernel<<<rgrid, RS_THREADS, resolve_smem_bytes(), b->stream>>>(K3);
+	b->timers.end(b->stream);
+	KWG_LAUNCHED();
+
+	ScanParams P = S;
+	P.pos0 = pos0;
+	P.n_pos = n_pos;
+	P.loss = b->d_loss;
+	P.list_chunks = b->d_chunk_table;
+	return launch_scan<MODE_PASS_B>(b, P);
 }
 
 // All inputs on the device: d_bases (16-byte aligned), d_offsets[n_reads+1] with offsets relative
@@ -363,6 +445,8 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	P.start_mask = b->d_start;
 	P.k = b->k;
 	P.counter = b->d_counter;
+	P.pos0 = 0;
+	P.n_pos = n_bases;
 
 	if (b->raw) {
 		P.filter = b->d_filter;
@@ -370,34 +454,12 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 		return launch_scan<MODE_RAW>(b, P);
 	}
 
-	// counting mode
-	if (b->epoch_pos + n_bases >= (uint64_t)T_EMPTY) {
-		flatten_epoch_kernel<<<sm_count(b->device) * 8, 256, 0, b->stream>>>(b->T, 2ull << b->lc);
-		KWG_LAUNCHED();
-		b->epoch_pos = 1;
+	// counting mode: sub-batches of at most 2^28 start positions (a record carries a 28-bit position)
+	for (uint64_t pos0 = 0; pos0 < n_bases; pos0 += MAX_COUNT_POS) {
+		const uint64_t n_pos = std::min<uint64_t>(MAX_COUNT_POS, n_bases - pos0);
+		rc = count_sub_batch(b, P, pos0, n_pos);
+		if (rc) return rc;
 	}
-	uint64_t n_valid = 0;
-	rc = read_counter(b, &n_valid);
-	if (rc) return rc;
-	rc = ensure_list_capacity(b, n_valid + n_bases);
-	if (rc) return rc;
-
-	const size_t bitmap_words = (size_t)(ceil_div(n_bases, TILE_BASES) * (TILE_BASES / 32));
-	if ((rc = grow((void**)&b->d_won, &b->won_cap, bitmap_words * sizeof(uint32_t)))) return rc;
-	if ((rc = grow((void**)&b->d_recheck, &b->recheck_cap, bitmap_words * sizeof(uint32_t)))) return rc;
-	KWG_CUDA(cudaMemsetAsync(b->d_recheck, 0, bitmap_words * sizeof(uint32_t), b->stream));
-	P.won = b->d_won;
-	P.recheck = b->d_recheck;
-	P.T = b->T;
-	P.count_len = 1ull << b->lc;
-	P.count_mask = (b->lc >= 32) ? 0xFFFFFFFFu : ((1u << b->lc) - 1u);
-	P.epoch_base = (uint32_t)b->epoch_pos;
-	P.list_chunks = b->d_chunk_table;
-	rc = launch_scan<MODE_PASS_A>(b, P);
-	if (rc) return rc;
-	rc = launch_scan<MODE_PASS_B>(b, P);
-	if (rc) return rc;
-	b->epoch_pos += n_bases;
 	return KWG_OK;
 }
 
@@ -423,7 +485,10 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->T);
+	cudaFree(b->d_touched);
+	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
+	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec);
+	cudaFree(b->d_cfirst); cudaFree(b->d_loss);
 	for (uint64_t* c : b->chunks) cudaFree(c);
 	cudaFree(b->d_chunk_table);
 	cudaFree(b->d_counter);
@@ -432,8 +497,6 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_bases);
 	cudaFree(b->d_offsets);
 	cudaFree(b->d_start);
-	cudaFree(b->d_won);
-	cudaFree(b->d_recheck);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	delete b;
 }
@@ -457,10 +520,14 @@ int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t 
 	b->lc = log2_count_len; b->lmax = log2_max_len;
 	rc = bloom_alloc_common(b);
 	if (rc == KWG_OK) {
-		const size_t bytes = (size_t)(2ull << b->lc) * sizeof(uint32_t);
-		cudaError_t e = cudaMalloc(&b->T, bytes);
-		if (e != cudaSuccess) rc = fail(KWG_ERR_NO_MEMORY, std::string("first-touch table: ") + cudaGetErrorString(e));
-		else if (cudaMemsetAsync(b->T, 0xFF, bytes, b->stream) != cudaSuccess) rc = fail(KWG_ERR_CUDA, "memset of first-touch table failed");
+		b->geom = count_geometry(b->lc);
+		rc = count_kernels_init();
+		if (rc == KWG_OK) {
+			const size_t bytes = (size_t)1 << (b->lc + 1 - 3);       // two tables of 2^lc slots, one bit each
+			cudaError_t e = cudaMalloc(&b->d_touched, bytes);
+			if (e != cudaSuccess) rc = fail(KWG_ERR_NO_MEMORY, std::string("touched bitmap: ") + cudaGetErrorString(e));
+			else if (cudaMemsetAsync(b->d_touched, 0, bytes, b->stream) != cudaSuccess) rc = fail(KWG_ERR_CUDA, "memset of touched bitmap failed");
+		}
 	}
 	if (rc) { kwg_bloom_destroy(b); return rc; }
 	*out = b;
@@ -498,8 +565,7 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 	if (b->raw) {
 		KWG_CUDA(cudaMemsetAsync(b->d_filter, 0, (size_t)1 << (b->raw_L - 3), b->stream));
 	} else {
-		KWG_CUDA(cudaMemsetAsync(b->T, 0xFF, (size_t)(2ull << b->lc) * sizeof(uint32_t), b->stream));
-		b->epoch_pos = 1;
+		KWG_CUDA(cudaMemsetAsync(b->d_touched, 0, (size_t)1 << (b->lc + 1 - 3), b->stream));
 	}
 	return KWG_OK;
 }

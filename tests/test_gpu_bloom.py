@@ -117,6 +117,56 @@ def test_counting_mode_finalize_any_parameters_equals_fold():
     ob.close()
 
 
+def skewed_case(seed, n_reads=6000, poly=1500):
+    """Random ragged reads + a block of identical poly-A reads + repeats of the first reads: heavy
+    duplication puts hundreds of thousands of records into the same few partition buckets."""
+    bases, offsets = ragged_case(seed, n_reads=n_reads)
+    poly_a = np.full(poly * 150, ord("A"), np.uint8)
+    rep = bases[: int(offsets[n_reads // 4])]
+    flat = np.concatenate([bases, poly_a, rep, poly_a[: 150 * 7]])
+    offs = np.concatenate([offsets,
+                           offsets[-1] + np.arange(1, poly + 1, dtype=np.uint64) * np.uint64(150),
+                           offsets[-1] + np.uint64(poly * 150) + offsets[1: n_reads // 4 + 1],
+                           offsets[-1] + np.uint64(poly * 150) + offsets[n_reads // 4] + np.arange(1, 8, dtype=np.uint64) * np.uint64(150)])
+    return flat, offs.astype(np.uint64)
+
+
+@pytest.mark.parametrize("lc,split", [(18, 1), (23, 2), (24, 1), (25, 3), (27, 1), (30, 2), (32, 1)])
+def test_counting_mode_every_partition_geometry(lc, split):
+    # log2_count_len decides the partition geometry (single level up to 23, two levels above); the
+    # result must equal the oracle's sequential counting filters for every one of them
+    k, lmax = 31, 24
+    bases, offsets = skewed_case(50 + lc)
+    ob = O.Builder(k, 1, lc, lmax)
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(k, min_kmer_count=1, log2_count_len=lc, log2_max_len=lmax) as b:
+        n = len(offsets) - 1
+        cuts = [0] + [n * i // split for i in range(1, split)] + [n]
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            b.add_reads(bases, offsets[a: z + 1])
+        assert b.num_valid() == ob.num_valid()
+        for L, h in [(22, 3), (24, 5)]:
+            assert np.array_equal(b.finalize(L, h), ob.finalize(L, h)), (L, h)
+    ob.close()
+
+
+def test_counting_mode_small_filter_heavy_shadowing():
+    # many more k-mers than counting slots: most first occurrences are shadowed by earlier k-mers, so
+    # the stream-order rule (minimum position per slot, displacement of later occurrences) decides almost
+    # every k-mer
+    k, lc, lmax = 21, 18, 22
+    bases, offsets = S.uniform_reads(77, 0, 20000, 100)
+    ob = O.Builder(k, 1, lc, lmax)
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(k, min_kmer_count=1, log2_count_len=lc, log2_max_len=lmax) as b:
+        b.add_reads(bases, offsets[:7001])
+        b.add_reads(bases, offsets[7000:])
+        assert b.num_valid() == ob.num_valid()
+        assert b.num_valid() < 20000 * 80 // 2
+        assert np.array_equal(b.finalize(22, 2), ob.finalize(22, 2))
+    ob.close()
+
+
 def test_counting_mode_reset_and_invalid_statuses():
     case = dict(S.MAKE_BLOOM_CASES["no_kmers"])
     bases, offsets = S.make_bloom_reads(case)
