@@ -244,7 +244,8 @@ def stage_construct(D, args, windows):
     achieved = kmers * bytes_per_kmer_a / t_a / 1e9 if t_a > 0 else 0.0
     step_ms = sec / args.steps * 1e3
     kernels = {name: round(float(ms[idx]) / args.steps, 4) for name, idx in
-               (("scan_pass_a", capi.T_SCAN_A), ("scan_pass_b", capi.T_SCAN_B), ("insert_words", capi.T_INSERT), ("mark_read_starts", capi.T_AUX))}
+               (("partition_scan", capi.T_SCAN_A), ("regroup", capi.T_REGROUP), ("resolve", capi.T_RESOLVE), ("scan_pass_b", capi.T_SCAN_B),
+                ("insert_words", capi.T_INSERT), ("mark_read_starts", capi.T_AUX))}
     return {
         "value": n * kmers * args.steps / sec,
         "ms_per_step": step_ms,

@@ -204,6 +204,7 @@ struct kwg_bloom {
 	// counting mode
 	CountGeom geom{};
 	uint32_t* d_touched = nullptr;       // 2^(lc+1) bits: slot touched by an earlier batch of this accession
+	bool touched_dirty = false;          // false: nothing added since create/reset (the bitmap need not be read)
 	std::vector<uint64_t*> chunks;
 	uint64_t** d_chunk_table = nullptr;
 	size_t table_cap = 0;
@@ -301,7 +302,7 @@ static int launch_scan(kwg_bloom* b, const ScanParams& P)
 
 static size_t partition_smem_bytes()
 {
-	return (size_t)PT_REC * 8 + (size_t)(4 * PT_POS + PT_VEC + 2 + 2 * (PT_LOAD / 32 + 2) + PT_POS / 32 + MAX_FAN + 1 + MAX_FAN + 8) * 4;
+	return (size_t)PT_REC * 8 + (size_t)(4 * PT_POS + PT_VEC + 2 + 2 * (PT_LOAD / 32 + 2) + PT_POS / 32 + MAX_FAN + 1 + MAX_FAN + PT_THREADS / 32) * 4;
 }
 static size_t regroup_smem_bytes()
 {
@@ -361,6 +362,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	ResolveParams K3{};
 	K3.n_buckets = 1u << G.nb_log2;
 	K3.touched = b->d_touched;
+	K3.have_prior = b->touched_dirty ? 1u : 0u;
 	K3.loss = b->d_loss;
 	if (!two_level) {
 		K3.rec = b->d_rec1;
@@ -394,7 +396,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		K2.F1 = F1; K2.G1 = G1; K2.NG = NG; K2.f2_log2 = G.f2_log2;
 		K2.cnt1 = b->d_cnt1; K2.base2 = b->d_base2; K2.cbase = b->d_cbase; K2.cfirst = b->d_cfirst;
 		K2.rec2 = b->d_rec2; K2.offs2 = b->d_offs2;
-		regroup_kernel<<<(unsigned)n_pairs, PT_THREADS, regroup_smem_bytes(), b->stream>>>(K2);
+		regroup_kernel<<<(unsigned)n_pairs, RG_THREADS, regroup_smem_bytes(), b->stream>>>(K2);
 		b->timers.end(b->stream);
 		KWG_LAUNCHED();
 
@@ -412,6 +414,8 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	resolve_kernel<<<rgrid, RS_THREADS, resolve_smem_bytes(), b->stream>>>(K3);
 	b->timers.end(b->stream);
 	KWG_LAUNCHED();
+
+	b->touched_dirty = true;
 
 	ScanParams P = S;
 	P.pos0 = pos0;
@@ -565,7 +569,7 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 	if (b->raw) {
 		KWG_CUDA(cudaMemsetAsync(b->d_filter, 0, (size_t)1 << (b->raw_L - 3), b->stream));
 	} else {
-		KWG_CUDA(cudaMemsetAsync(b->d_touched, 0, (size_t)1 << (b->lc + 1 - 3), b->stream));
+		b->touched_dirty = false;            // the next batch rewrites every word of the touched bitmap
 	}
 	return KWG_OK;
 }

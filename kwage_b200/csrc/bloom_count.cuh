@@ -31,7 +31,8 @@
 
 namespace kwg {
 
-constexpr int PT_THREADS = 256;
+constexpr int PT_THREADS = 512;                   // partition_scan_kernel block size
+constexpr int RG_THREADS = 256;                   // regroup_kernel block size
 constexpr int PT_POS = 2048;                      // k-mer start positions per partition tile
 constexpr int PT_REC = 4 * PT_POS;                // record slots per tile
 constexpr int PT_LOAD = PT_POS + 32;              // bases staged per tile (halo >= k-1, 16-byte granular)
@@ -80,13 +81,16 @@ struct PartParams {
 	uint16_t* offs1;             // [(F1+1)][ntp]: start of bucket b inside the sorted tile; row F1 = record count
 };
 
-// exclusive prefix sum of n <= 2*PT_THREADS counters in shared memory (in place) by 256 threads;
-// returns the total.  s_warp: 8 words of scratch.
+// exclusive prefix sum of n <= MAX_FAN counters in shared memory (in place) by a block of THREADS
+// threads (256: two counters per thread, 512: one); returns the total.  s_warp: THREADS/32 words of scratch.
+template <int THREADS>
 __device__ __forceinline__ uint32_t block_exclusive_scan_512(uint32_t* v, uint32_t n, uint32_t* s_warp)
 {
+	constexpr int ITEMS = MAX_FAN / THREADS;
+	static_assert(ITEMS == 1 || ITEMS == 2, "block size must be 256 or 512");
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t a = (2 * tid < n) ? v[2 * tid] : 0u;
-	const uint32_t b = (2 * tid + 1 < n) ? v[2 * tid + 1] : 0u;
+	const uint32_t a = (ITEMS * tid < n) ? v[ITEMS * tid] : 0u;
+	const uint32_t b = (ITEMS == 2 && 2 * tid + 1 < n) ? v[2 * tid + 1] : 0u;
 	uint32_t x = a + b;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
@@ -97,14 +101,14 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_512(uint32_t* v, uint32
 	__syncthreads();
 	uint32_t base = 0, total = 0;
 #pragma unroll
-	for (int w = 0; w < PT_THREADS / 32; ++w) {
+	for (int w = 0; w < THREADS / 32; ++w) {
 		const uint32_t s = s_warp[w];
 		if ((uint32_t)w < warp) base += s;
 		total += s;
 	}
 	const uint32_t excl = base + x - (a + b);
-	if (2 * tid < n) v[2 * tid] = excl;
-	if (2 * tid + 1 < n) v[2 * tid + 1] = excl + a;
+	if (ITEMS * tid < n) v[ITEMS * tid] = excl;
+	if (ITEMS == 2 && 2 * tid + 1 < n) v[2 * tid + 1] = excl + a;
 	__syncthreads();
 	return total;
 }
@@ -122,7 +126,7 @@ partition_scan_kernel(const PartParams P)
 	uint32_t* s_ok = s_start + PT_LOAD / 32 + 2;                                       // PT_POS/32
 	uint32_t* s_hist = s_ok + PT_POS / 32;                                             // MAX_FAN + 1
 	uint32_t* s_cursor = s_hist + MAX_FAN + 1;                                         // MAX_FAN
-	uint32_t* s_warp = s_cursor + MAX_FAN;                                             // 8
+	uint32_t* s_warp = s_cursor + MAX_FAN;                                             // 16
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t k = P.k;
@@ -181,7 +185,7 @@ partition_scan_kernel(const PartParams P)
 	}
 	__syncthreads();
 
-	const uint32_t total = block_exclusive_scan_512(s_hist, F1, s_warp);
+	const uint32_t total = block_exclusive_scan_512<PT_THREADS>(s_hist, F1, s_warp);
 	for (uint32_t b = tid; b < F1; b += PT_THREADS) {
 		const uint32_t s = s_hist[b];
 		s_cursor[b] = s;
@@ -290,7 +294,43 @@ struct RegroupParams {
 	uint16_t* offs2;             // bucket i: rows at cfirst[i]*(F2+1); entry (j, local chunk c) at + j*nci + c
 };
 
-__global__ void __launch_bounds__(PT_THREADS, 3)
+// Visits the records of virtual range [cv0, cv1) of the gathered runs; RG_U runs are loaded before any
+// is consumed so that every warp keeps RG_U x 256 bytes in flight (the kernel is latency bound otherwise).
+constexpr int RG_U = 8;
+template <typename F>
+__device__ __forceinline__ void regroup_visit(const RegroupParams& P, const uint32_t* s_rs, const uint32_t* s_vs, uint32_t t0,
+	uint32_t nt, uint32_t cv0, uint32_t cv1, F f)
+{
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	constexpr uint32_t NW = RG_THREADS / 32;
+	for (uint32_t rb = warp; rb < nt; rb += NW * RG_U) {
+		uint64_t rec[RG_U];
+		const uint64_t* run[RG_U];
+		uint32_t n[RG_U];
+#pragma unroll
+		for (int u = 0; u < RG_U; ++u) {
+			const uint32_t r = rb + u * NW;
+			n[u] = 0; run[u] = P.rec1;
+			if (r < nt) {
+				const uint32_t vs = s_vs[r], ve = s_vs[r + 1];
+				const uint32_t lo = max(vs, cv0), hi = min(ve, cv1);
+				if (lo < hi) {
+					n[u] = hi - lo;
+					run[u] = P.rec1 + (uint64_t)(t0 + r) * PT_REC + s_rs[r] + (lo - vs);
+				}
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < RG_U; ++u) rec[u] = (lane < n[u]) ? run[u][lane] : 0ull;
+#pragma unroll
+		for (int u = 0; u < RG_U; ++u) {
+			if (lane < n[u]) f(rec[u]);
+			for (uint32_t x = 32 + lane; x < n[u]; x += 32) f(run[u][x]);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(RG_THREADS, 3)
 regroup_kernel(const RegroupParams P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -301,7 +341,7 @@ regroup_kernel(const RegroupParams P)
 	uint32_t* s_cursor = s_hist + MAX_FAN + 1;                              // MAX_FAN
 	uint32_t* s_warp = s_cursor + MAX_FAN;                                  // 8
 
-	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t tid = threadIdx.x;
 	const uint32_t i = blockIdx.x % P.F1, g = blockIdx.x / P.F1;
 	const uint32_t pair = i * P.NG + g;
 	const uint32_t cnt = P.cnt1[pair];
@@ -310,7 +350,7 @@ regroup_kernel(const RegroupParams P)
 	const uint32_t nt = min(P.G1, P.n_tiles - t0);
 	const uint32_t F2 = 1u << P.f2_log2;
 
-	for (uint32_t r = tid; r < (uint32_t)MAX_FAN; r += PT_THREADS) {
+	for (uint32_t r = tid; r < (uint32_t)MAX_FAN; r += RG_THREADS) {
 		uint32_t s = 0, len = 0;
 		if (r < nt) {
 			s = P.offs1[(uint64_t)i * P.ntp + t0 + r];
@@ -320,7 +360,7 @@ regroup_kernel(const RegroupParams P)
 		s_vs[r] = len;
 	}
 	__syncthreads();
-	block_exclusive_scan_512(s_vs, MAX_FAN, s_warp);
+	block_exclusive_scan_512<RG_THREADS>(s_vs, MAX_FAN, s_warp);
 	if (tid == 0) s_vs[MAX_FAN] = cnt;
 	__syncthreads();
 
@@ -330,47 +370,40 @@ regroup_kernel(const RegroupParams P)
 	const uint32_t cl0 = P.cbase[pair] - c0;
 	uint16_t* rows = P.offs2 + (uint64_t)c0 * (F2 + 1);
 	const uint64_t out0 = P.base2[pair];
-	const uint32_t sub_shift = FINAL_LOG2;
 
 	for (uint32_t c = 0; c < nchunk; ++c) {
 		const uint32_t cv0 = c * CHUNK_REC, cv1 = min(cnt, cv0 + CHUNK_REC);
-		for (uint32_t v = tid; v <= F2; v += PT_THREADS) s_hist[v] = 0;
+		for (uint32_t v = tid; v <= F2; v += RG_THREADS) s_hist[v] = 0;
 		__syncthreads();
 		// pass A: level-2 histogram of the records of this chunk
-		for (uint32_t r = warp; r < nt; r += PT_THREADS / 32) {
-			const uint32_t vs = s_vs[r], ve = s_vs[r + 1];
-			const uint32_t lo = max(vs, cv0), hi = min(ve, cv1);
-			if (lo >= hi) continue;
-			const uint64_t* run = P.rec1 + (uint64_t)(t0 + r) * PT_REC + s_rs[r];
-			for (uint32_t v = lo + lane; v < hi; v += 32) {
-				const uint64_t rec = run[v - vs];
-				atomicAdd(&s_hist[(uint32_t)(rec >> 32) >> sub_shift], 1u);
-			}
-		}
+		regroup_visit(P, s_rs, s_vs, t0, nt, cv0, cv1, [&](uint64_t rec) {
+			atomicAdd(&s_hist[(uint32_t)(rec >> 32) >> FINAL_LOG2], 1u);
+		});
 		__syncthreads();
-		block_exclusive_scan_512(s_hist, F2, s_warp);
-		for (uint32_t j = tid; j < F2; j += PT_THREADS) {
+		block_exclusive_scan_512<RG_THREADS>(s_hist, F2, s_warp);
+		for (uint32_t j = tid; j < F2; j += RG_THREADS) {
 			const uint32_t s = s_hist[j];
 			s_cursor[j] = s;
 			rows[(uint64_t)j * nci + cl0 + c] = (uint16_t)s;
 		}
 		if (tid == 0) rows[(uint64_t)F2 * nci + cl0 + c] = (uint16_t)(cv1 - cv0);
 		__syncthreads();
-		// pass B: scatter (second read of the runs comes from L1/L2)
-		for (uint32_t r = warp; r < nt; r += PT_THREADS / 32) {
-			const uint32_t vs = s_vs[r], ve = s_vs[r + 1];
-			const uint32_t lo = max(vs, cv0), hi = min(ve, cv1);
-			if (lo >= hi) continue;
-			const uint64_t* run = P.rec1 + (uint64_t)(t0 + r) * PT_REC + s_rs[r];
-			for (uint32_t v = lo + lane; v < hi; v += 32) {
-				const uint64_t rec = run[v - vs];
-				const uint32_t idx = atomicAdd(&s_cursor[(uint32_t)(rec >> 32) >> sub_shift], 1u);
-				s_sorted[idx] = rec;
-			}
-		}
+		// pass B: scatter into the staging chunk (the second read of the runs comes from L1/L2)
+		regroup_visit(P, s_rs, s_vs, t0, nt, cv0, cv1, [&](uint64_t rec) {
+			const uint32_t idx = atomicAdd(&s_cursor[(uint32_t)(rec >> 32) >> FINAL_LOG2], 1u);
+			s_sorted[idx] = rec;
+		});
 		__syncthreads();
-		uint64_t* dst = P.rec2 + out0 + cv0;
-		for (uint32_t x = tid; x < cv1 - cv0; x += PT_THREADS) dst[x] = s_sorted[x];
+		uint4* dst = reinterpret_cast<uint4*>(P.rec2 + out0 + cv0);
+		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+			const uint4* src = reinterpret_cast<const uint4*>(s_sorted);
+			const uint32_t n2 = (cv1 - cv0) / 2;
+			for (uint32_t x = tid; x < n2; x += RG_THREADS) st_na_v4(dst + x, src[x]);
+			if (tid == 0 && ((cv1 - cv0) & 1u)) P.rec2[out0 + cv1 - 1] = s_sorted[cv1 - cv0 - 1];
+		} else {
+			uint64_t* d8 = P.rec2 + out0 + cv0;
+			for (uint32_t x = tid; x < cv1 - cv0; x += RG_THREADS) d8[x] = s_sorted[x];
+		}
 		__syncthreads();
 	}
 }
@@ -387,6 +420,7 @@ struct ResolveParams {
 	uint32_t f2_log2;            // sub-buckets per group (single level: all final buckets are one group)
 	uint32_t n_buckets;          // final buckets
 	uint32_t* touched;           // persistent bitmap, FINAL_SLOTS bits per final bucket
+	uint32_t have_prior;         // 0: first batch after create/reset, the bitmap is known to be all zero
 	uint32_t* loss;              // 4-bit loss counters, 8 positions per word
 };
 
@@ -397,7 +431,7 @@ __device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
 	return r;
 }
 
-__device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* loss, uint64_t rec)
+__device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* loss, uint64_t rec)
 {
 	const uint32_t slot = (uint32_t)(rec >> 32) & (FINAL_SLOTS - 1);
 	const uint32_t pos = (uint32_t)rec;
@@ -411,7 +445,33 @@ __device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* loss,
 		// a later occurrence had been processed first and has just been displaced
 		const uint32_t q = old - 1u;
 		atomicAdd(&loss[q >> 3], 1u << ((q & 7u) << 2));
+	} else {
+		atomicOr(&s_bm[slot >> 5], 1u << (slot & 31u));      // first touch of the slot in this accession
 	}
+}
+
+// what a thread needs of a bucket before it can start: its word of the touched bitmap and run tid
+struct BucketPrefetch { uint32_t bmw, len; uint64_t off; };
+
+__device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P, uint32_t b)
+{
+	const uint32_t tid = threadIdx.x;
+	const uint32_t F2 = 1u << P.f2_log2;
+	const uint32_t i = b >> P.f2_log2, j = b & (F2 - 1);
+	const uint32_t c0 = P.cfirst ? P.cfirst[i] : 0u;
+	const uint32_t nci = P.cfirst ? P.cfirst[i + 1] - c0 : P.single_nci;
+	const uint64_t pitch = P.row_pitch ? P.row_pitch : (uint64_t)nci;
+	const uint16_t* row_s = P.offs + (uint64_t)c0 * (F2 + 1) + (uint64_t)j * pitch;
+	BucketPrefetch r;
+	r.bmw = P.have_prior ? P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] : 0u;
+	r.len = 0; r.off = 0;
+	if (tid < nci) {
+		const uint32_t s = row_s[tid], e = row_s[pitch + tid];
+		const uint64_t base = P.chunk_stride ? (uint64_t)(c0 + tid) * P.chunk_stride : P.chunk_rec[c0 + tid];
+		r.off = base + s;
+		r.len = e - s;
+	}
+	return r;
 }
 
 __global__ void __launch_bounds__(RS_THREADS, 1)
@@ -426,41 +486,57 @@ resolve_kernel(const ResolveParams P)
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t F2 = 1u << P.f2_log2;
 
-	for (uint32_t b = blockIdx.x; b < P.n_buckets; b += gridDim.x) {
+	uint32_t b = blockIdx.x;
+	BucketPrefetch pf{0u, 0u, 0ull};
+	if (b < P.n_buckets) pf = prefetch_bucket(P, b);
+
+	for (; b < P.n_buckets; b += gridDim.x) {
 		const uint32_t i = b >> P.f2_log2, j = b & (F2 - 1);
 		const uint32_t c0 = P.cfirst ? P.cfirst[i] : 0u;
 		const uint32_t nci = P.cfirst ? P.cfirst[i + 1] - c0 : P.single_nci;
 		const uint64_t pitch = P.row_pitch ? P.row_pitch : (uint64_t)nci;
 		const uint16_t* row_s = P.offs + (uint64_t)c0 * (F2 + 1) + (uint64_t)j * pitch;
-		const uint16_t* row_e = row_s + pitch;
 
-		// tile <- touched bitmap of this bucket (1024 words, one per thread)
-		uint32_t* bm = P.touched + (uint64_t)b * (FINAL_SLOTS / 32);
-		s_bm[tid] = bm[tid];
+		s_bm[tid] = pf.bmw;
+		s_off[tid] = pf.off;
+		s_len[tid] = pf.len;
 		__syncthreads();
+		// tables of the next bucket travel while this one is resolved
+		if (b + gridDim.x < P.n_buckets) pf = prefetch_bucket(P, b + gridDim.x);
+
+		// tile <- touched bitmap of this bucket
+		if (P.have_prior) {
 #pragma unroll
-		for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
-			const uint32_t s4 = (q * RS_THREADS + tid) * 4;
-			const uint32_t bits = s_bm[s4 >> 5] >> (s4 & 31);
-			uint4 v;
-			v.x = (bits & 1u) ? 0u : SLOT_EMPTY;
-			v.y = (bits & 2u) ? 0u : SLOT_EMPTY;
-			v.z = (bits & 4u) ? 0u : SLOT_EMPTY;
-			v.w = (bits & 8u) ? 0u : SLOT_EMPTY;
-			reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = v;
+			for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
+				const uint32_t s4 = (q * RS_THREADS + tid) * 4;
+				const uint32_t bits = s_bm[s4 >> 5] >> (s4 & 31);
+				uint4 v;
+				v.x = (bits & 1u) ? 0u : SLOT_EMPTY;
+				v.y = (bits & 2u) ? 0u : SLOT_EMPTY;
+				v.z = (bits & 4u) ? 0u : SLOT_EMPTY;
+				v.w = (bits & 8u) ? 0u : SLOT_EMPTY;
+				reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = v;
+			}
+		} else {
+			const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY);
+#pragma unroll
+			for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q)
+				reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = e4;
 		}
 		__syncthreads();
 
 		for (uint32_t cb = 0; cb < nci; cb += RS_THREADS) {
 			const uint32_t nrt = min((uint32_t)RS_THREADS, nci - cb);
-			if (tid < nrt) {
-				const uint32_t c = cb + tid;
-				const uint32_t s = row_s[c], e = row_e[c];
-				const uint64_t base = P.chunk_stride ? (uint64_t)(c0 + c) * P.chunk_stride : P.chunk_rec[c0 + c];
-				s_off[tid] = base + s;
-				s_len[tid] = e - s;
+			if (cb) {          // run tables beyond the prefetched first RS_THREADS runs
+				if (tid < nrt) {
+					const uint32_t c = cb + tid;
+					const uint32_t s = row_s[c], e = row_s[pitch + c];
+					const uint64_t base = P.chunk_stride ? (uint64_t)(c0 + c) * P.chunk_stride : P.chunk_rec[c0 + c];
+					s_off[tid] = base + s;
+					s_len[tid] = e - s;
+				}
+				__syncthreads();
 			}
-			__syncthreads();
 			// one warp per run, four runs in flight
 			for (uint32_t r0 = warp; r0 < nrt; r0 += 4 * (RS_THREADS / 32)) {
 				uint64_t rec[4];
@@ -476,22 +552,15 @@ resolve_kernel(const ResolveParams P)
 				for (int u = 0; u < 4; ++u) rec[u] = (lane < len[u]) ? ld_nc_u64(run[u] + lane) : 0ull;
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
-					if (lane < len[u]) resolve_record(s_tile, P.loss, rec[u]);
-					for (uint32_t x = 32 + lane; x < len[u]; x += 32) resolve_record(s_tile, P.loss, ld_nc_u64(run[u] + x));
+					if (lane < len[u]) resolve_record(s_tile, s_bm, P.loss, rec[u]);
+					for (uint32_t x = 32 + lane; x < len[u]; x += 32) resolve_record(s_tile, s_bm, P.loss, ld_nc_u64(run[u] + x));
 				}
 			}
 			__syncthreads();
 		}
 
-		// touched bitmap <- every slot that holds anything
-#pragma unroll 4
-		for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / RS_THREADS); ++q) {
-			const uint32_t s = q * RS_THREADS + tid;
-			const uint32_t m = __ballot_sync(0xFFFFFFFFu, s_tile[s] != SLOT_EMPTY);
-			if (lane == 0) s_bm[s >> 5] = m;
-		}
-		__syncthreads();
-		bm[tid] = s_bm[tid];
+		// the bitmap now holds the earlier batches' bits plus every slot first touched here
+		P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] = s_bm[tid];
 		__syncthreads();
 	}
 }
