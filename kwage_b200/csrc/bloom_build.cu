@@ -306,11 +306,11 @@ static size_t partition_smem_bytes()
 }
 static size_t regroup_smem_bytes()
 {
-	return (size_t)CHUNK_REC * 8 + (size_t)(MAX_FAN + (MAX_FAN + 1) + (MAX_FAN + 1) + MAX_FAN + 8) * 4;
+	return (size_t)CHUNK_REC * 8 + (size_t)((MAX_FAN + 1) + MAX_FAN + (MAX_FAN + 1) + MAX_FAN + RG_THREADS / 32) * 4 + 4 + (size_t)(3 * MAX_FAN) * 2;
 }
 static size_t resolve_smem_bytes()
 {
-	return (size_t)FINAL_SLOTS * 4 + (size_t)(FINAL_SLOTS / 32) * 4 + (size_t)RS_THREADS * 8 + (size_t)RS_THREADS * 4;
+	return (size_t)FINAL_SLOTS * 4 + (size_t)(FINAL_SLOTS / 32) * 4 + (size_t)RS_THREADS * 4 + (size_t)RS_THREADS * 4 + 4 + (size_t)RS_THREADS * 2;
 }
 
 static int count_kernels_init()

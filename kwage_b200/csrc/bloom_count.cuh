@@ -32,7 +32,7 @@
 namespace kwg {
 
 constexpr int PT_THREADS = 512;                   // partition_scan_kernel block size
-constexpr int RG_THREADS = 256;                   // regroup_kernel block size
+constexpr int RG_THREADS = 512;                   // regroup_kernel block size
 constexpr int PT_POS = 2048;                      // k-mer start positions per partition tile
 constexpr int PT_REC = 4 * PT_POS;                // record slots per tile
 constexpr int PT_LOAD = PT_POS + 32;              // bases staged per tile (halo >= k-1, 16-byte granular)
@@ -43,6 +43,7 @@ constexpr int MAX_FAN_LOG2 = 9;                   // at most 512 buckets per par
 constexpr int MAX_FAN = 1 << MAX_FAN_LOG2;
 constexpr int CHUNK_REC = 8192;                   // records per level-2 chunk
 constexpr int RS_THREADS = 1024;                  // resolve kernel block size
+constexpr int RS_U = 8;                           // runs in flight per warp in the resolve kernel
 constexpr uint32_t SLOT_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t MAX_COUNT_POS = 1ull << 28;    // positions per counting sub-batch (record: 28-bit position)
 
@@ -294,54 +295,32 @@ struct RegroupParams {
 	uint16_t* offs2;             // bucket i: rows at cfirst[i]*(F2+1); entry (j, local chunk c) at + j*nci + c
 };
 
-// Visits the records of virtual range [cv0, cv1) of the gathered runs; RG_U runs are loaded before any
-// is consumed so that every warp keeps RG_U x 256 bytes in flight (the kernel is latency bound otherwise).
-constexpr int RG_U = 8;
-template <typename F>
-__device__ __forceinline__ void regroup_visit(const RegroupParams& P, const uint32_t* s_rs, const uint32_t* s_vs, uint32_t t0,
-	uint32_t nt, uint32_t cv0, uint32_t cv1, F f)
-{
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	constexpr uint32_t NW = RG_THREADS / 32;
-	for (uint32_t rb = warp; rb < nt; rb += NW * RG_U) {
-		uint64_t rec[RG_U];
-		const uint64_t* run[RG_U];
-		uint32_t n[RG_U];
-#pragma unroll
-		for (int u = 0; u < RG_U; ++u) {
-			const uint32_t r = rb + u * NW;
-			n[u] = 0; run[u] = P.rec1;
-			if (r < nt) {
-				const uint32_t vs = s_vs[r], ve = s_vs[r + 1];
-				const uint32_t lo = max(vs, cv0), hi = min(ve, cv1);
-				if (lo < hi) {
-					n[u] = hi - lo;
-					run[u] = P.rec1 + (uint64_t)(t0 + r) * PT_REC + s_rs[r] + (lo - vs);
-				}
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < RG_U; ++u) rec[u] = (lane < n[u]) ? run[u][lane] : 0ull;
-#pragma unroll
-		for (int u = 0; u < RG_U; ++u) {
-			if (lane < n[u]) f(rec[u]);
-			for (uint32_t x = 32 + lane; x < n[u]; x += 32) f(run[u][x]);
-		}
-	}
-}
+// One block regroups the runs of level-1 bucket i coming from a group of G1 <= 512 tiles.  Every warp
+// owns RG_R runs per round and keeps their first 32 records in registers: all RG_R loads (256 bytes
+// each) are issued back to back, so one DRAM round trip covers the block's whole input, and the
+// scatter pass re-uses the registers instead of reading the runs again.  Runs longer than a warp
+// (~9 % at the usual 26 records per run) and the first round of 512-tile groups are re-read (L2).
+constexpr int RG_R = 16;                                     // runs per warp per round
+constexpr int RG_RPR = (RG_THREADS / 32) * RG_R;             // runs per block per round (256)
+static_assert(2 * RG_RPR >= MAX_FAN, "two rounds must cover the largest tile group");
 
-__global__ void __launch_bounds__(RG_THREADS, 3)
+__global__ void __launch_bounds__(RG_THREADS, 2)
 regroup_kernel(const RegroupParams P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint64_t* s_sorted = reinterpret_cast<uint64_t*>(smem_raw);             // CHUNK_REC records
-	uint32_t* s_rs = reinterpret_cast<uint32_t*>(smem_raw + CHUNK_REC * 8); // MAX_FAN: run start inside its tile
-	uint32_t* s_vs = s_rs + MAX_FAN;                                        // MAX_FAN + 1: virtual start of each run
-	uint32_t* s_hist = s_vs + MAX_FAN + 1;                                  // MAX_FAN + 1
+	uint32_t* s_vs = reinterpret_cast<uint32_t*>(smem_raw + CHUNK_REC * 8); // MAX_FAN + 1: virtual start of each run
+	uint32_t* s_roff = s_vs + MAX_FAN + 1;                                  // MAX_FAN: record offset of the run's part in this chunk
+	uint32_t* s_hist = s_roff + MAX_FAN;                                    // MAX_FAN + 1
 	uint32_t* s_cursor = s_hist + MAX_FAN + 1;                              // MAX_FAN
-	uint32_t* s_warp = s_cursor + MAX_FAN;                                  // 8
+	uint32_t* s_warp = s_cursor + MAX_FAN;                                  // RG_THREADS / 32
+	uint32_t* s_nlong = s_warp + RG_THREADS / 32;                           // 1: runs with more than 32 records in this chunk
+	uint16_t* s_rs = reinterpret_cast<uint16_t*>(s_nlong + 1);              // MAX_FAN: run start inside its tile
+	uint16_t* s_rn = s_rs + MAX_FAN;                                        // MAX_FAN: records of the run in this chunk
+	uint16_t* s_long = s_rn + MAX_FAN;                                      // MAX_FAN: the long runs
 
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr uint32_t NW = RG_THREADS / 32;
 	const uint32_t i = blockIdx.x % P.F1, g = blockIdx.x / P.F1;
 	const uint32_t pair = i * P.NG + g;
 	const uint32_t cnt = P.cnt1[pair];
@@ -349,6 +328,7 @@ regroup_kernel(const RegroupParams P)
 	const uint32_t t0 = g * P.G1;
 	const uint32_t nt = min(P.G1, P.n_tiles - t0);
 	const uint32_t F2 = 1u << P.f2_log2;
+	const uint64_t* __restrict__ base = P.rec1 + (uint64_t)t0 * PT_REC;
 
 	for (uint32_t r = tid; r < (uint32_t)MAX_FAN; r += RG_THREADS) {
 		uint32_t s = 0, len = 0;
@@ -356,7 +336,7 @@ regroup_kernel(const RegroupParams P)
 			s = P.offs1[(uint64_t)i * P.ntp + t0 + r];
 			len = (uint32_t)P.offs1[(uint64_t)(i + 1) * P.ntp + t0 + r] - s;
 		}
-		s_rs[r] = s;
+		s_rs[r] = (uint16_t)s;
 		s_vs[r] = len;
 	}
 	__syncthreads();
@@ -370,15 +350,42 @@ regroup_kernel(const RegroupParams P)
 	const uint32_t cl0 = P.cbase[pair] - c0;
 	uint16_t* rows = P.offs2 + (uint64_t)c0 * (F2 + 1);
 	const uint64_t out0 = P.base2[pair];
+	const uint32_t n_rounds = (nt + RG_RPR - 1) / RG_RPR;       // 1 or 2
 
 	for (uint32_t c = 0; c < nchunk; ++c) {
 		const uint32_t cv0 = c * CHUNK_REC, cv1 = min(cnt, cv0 + CHUNK_REC);
 		for (uint32_t v = tid; v <= F2; v += RG_THREADS) s_hist[v] = 0;
+		if (tid == 0) *s_nlong = 0;
 		__syncthreads();
-		// pass A: level-2 histogram of the records of this chunk
-		regroup_visit(P, s_rs, s_vs, t0, nt, cv0, cv1, [&](uint64_t rec) {
-			atomicAdd(&s_hist[(uint32_t)(rec >> 32) >> FINAL_LOG2], 1u);
-		});
+		for (uint32_t r = tid; r < (uint32_t)MAX_FAN; r += RG_THREADS) {
+			const uint32_t vs = s_vs[r], ve = s_vs[r + 1];
+			const uint32_t lo = max(vs, cv0), hi = min(ve, cv1);
+			const uint32_t n = (lo < hi) ? hi - lo : 0u;
+			s_rn[r] = (uint16_t)n;
+			s_roff[r] = r * PT_REC + s_rs[r] + (lo - vs);
+			if (n > 32) s_long[atomicAdd(s_nlong, 1u)] = (uint16_t)r;
+		}
+		__syncthreads();
+		const uint32_t nlong = *s_nlong;
+
+		// pass A: level-2 histogram; the records of the last round stay in registers
+		uint64_t rec[RG_R];
+		for (uint32_t round = 0; round < n_rounds; ++round) {
+			const uint32_t rb = round * RG_RPR + warp;
+#pragma unroll
+			for (int u = 0; u < RG_R; ++u) {
+				const uint32_t r = rb + u * NW;
+				rec[u] = (lane < s_rn[r]) ? base[s_roff[r] + lane] : 0ull;
+			}
+#pragma unroll
+			for (int u = 0; u < RG_R; ++u)
+				if (lane < s_rn[rb + u * NW]) atomicAdd(&s_hist[(uint32_t)(rec[u] >> 32) >> FINAL_LOG2], 1u);
+		}
+		for (uint32_t q = warp; q < nlong; q += NW) {
+			const uint32_t r = s_long[q], n = s_rn[r];
+			const uint64_t* run = base + s_roff[r];
+			for (uint32_t x = 32 + lane; x < n; x += 32) atomicAdd(&s_hist[(uint32_t)(run[x] >> 32) >> FINAL_LOG2], 1u);
+		}
 		__syncthreads();
 		block_exclusive_scan_512<RG_THREADS>(s_hist, F2, s_warp);
 		for (uint32_t j = tid; j < F2; j += RG_THREADS) {
@@ -388,11 +395,34 @@ regroup_kernel(const RegroupParams P)
 		}
 		if (tid == 0) rows[(uint64_t)F2 * nci + cl0 + c] = (uint16_t)(cv1 - cv0);
 		__syncthreads();
-		// pass B: scatter into the staging chunk (the second read of the runs comes from L1/L2)
-		regroup_visit(P, s_rs, s_vs, t0, nt, cv0, cv1, [&](uint64_t rec) {
-			const uint32_t idx = atomicAdd(&s_cursor[(uint32_t)(rec >> 32) >> FINAL_LOG2], 1u);
-			s_sorted[idx] = rec;
-		});
+
+		// pass B: scatter into the staging chunk
+		for (uint32_t round = 0; round + 1 < n_rounds; ++round) {          // earlier rounds: re-read (L2)
+			const uint32_t rb = round * RG_RPR + warp;
+			uint64_t tmp[RG_R];
+#pragma unroll
+			for (int u = 0; u < RG_R; ++u) {
+				const uint32_t r = rb + u * NW;
+				tmp[u] = (lane < s_rn[r]) ? base[s_roff[r] + lane] : 0ull;
+			}
+#pragma unroll
+			for (int u = 0; u < RG_R; ++u)
+				if (lane < s_rn[rb + u * NW]) s_sorted[atomicAdd(&s_cursor[(uint32_t)(tmp[u] >> 32) >> FINAL_LOG2], 1u)] = tmp[u];
+		}
+		{
+			const uint32_t rb = (n_rounds - 1) * RG_RPR + warp;
+#pragma unroll
+			for (int u = 0; u < RG_R; ++u)
+				if (lane < s_rn[rb + u * NW]) s_sorted[atomicAdd(&s_cursor[(uint32_t)(rec[u] >> 32) >> FINAL_LOG2], 1u)] = rec[u];
+		}
+		for (uint32_t q = warp; q < nlong; q += NW) {
+			const uint32_t r = s_long[q], n = s_rn[r];
+			const uint64_t* run = base + s_roff[r];
+			for (uint32_t x = 32 + lane; x < n; x += 32) {
+				const uint64_t v = run[x];
+				s_sorted[atomicAdd(&s_cursor[(uint32_t)(v >> 32) >> FINAL_LOG2], 1u)] = v;
+			}
+		}
 		__syncthreads();
 		uint4* dst = reinterpret_cast<uint4*>(P.rec2 + out0 + cv0);
 		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
@@ -451,7 +481,7 @@ __device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm,
 }
 
 // what a thread needs of a bucket before it can start: its word of the touched bitmap and run tid
-struct BucketPrefetch { uint32_t bmw, len; uint64_t off; };
+struct BucketPrefetch { uint32_t bmw, len, off; };    // off: record index (< 2^30)
 
 __device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P, uint32_t b)
 {
@@ -468,7 +498,7 @@ __device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P
 	if (tid < nci) {
 		const uint32_t s = row_s[tid], e = row_s[pitch + tid];
 		const uint64_t base = P.chunk_stride ? (uint64_t)(c0 + tid) * P.chunk_stride : P.chunk_rec[c0 + tid];
-		r.off = base + s;
+		r.off = (uint32_t)(base + s);
 		r.len = e - s;
 	}
 	return r;
@@ -480,14 +510,16 @@ resolve_kernel(const ResolveParams P)
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);                           // FINAL_SLOTS
 	uint32_t* s_bm = s_tile + FINAL_SLOTS;                                              // FINAL_SLOTS / 32
-	unsigned long long* s_off = reinterpret_cast<unsigned long long*>(s_bm + FINAL_SLOTS / 32);   // RS_THREADS
-	uint32_t* s_len = reinterpret_cast<uint32_t*>(s_off + RS_THREADS);                  // RS_THREADS
+	uint32_t* s_off = s_bm + FINAL_SLOTS / 32;                                          // RS_THREADS: record index of every run
+	uint32_t* s_len = s_off + RS_THREADS;                                               // RS_THREADS
+	uint32_t* s_nlong = s_len + RS_THREADS;                                             // 1: runs with more than 32 records
+	uint16_t* s_long = reinterpret_cast<uint16_t*>(s_nlong + 1);                        // RS_THREADS: their indices
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t F2 = 1u << P.f2_log2;
 
 	uint32_t b = blockIdx.x;
-	BucketPrefetch pf{0u, 0u, 0ull};
+	BucketPrefetch pf{0u, 0u, 0u};
 	if (b < P.n_buckets) pf = prefetch_bucket(P, b);
 
 	for (; b < P.n_buckets; b += gridDim.x) {
@@ -500,9 +532,19 @@ resolve_kernel(const ResolveParams P)
 		s_bm[tid] = pf.bmw;
 		s_off[tid] = pf.off;
 		s_len[tid] = pf.len;
+		if (tid == 0) *s_nlong = 0;
 		__syncthreads();
-		// tables of the next bucket travel while this one is resolved
-		if (b + gridDim.x < P.n_buckets) pf = prefetch_bucket(P, b + gridDim.x);
+		if (pf.len > 32) s_long[atomicAdd(s_nlong, 1u)] = (uint16_t)tid;
+		// tables of the next bucket travel while this one is resolved, and its runs are pulled into L2
+		if (b + gridDim.x < P.n_buckets) {
+			pf = prefetch_bucket(P, b + gridDim.x);
+			if (pf.len) {
+				const char* p0 = reinterpret_cast<const char*>(P.rec + pf.off);
+				const char* p1 = p0 + (size_t)min(pf.len, 64u) * 8 - 1;
+				for (const char* q = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127); q <= p1; q += 128)
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+			}
+		}
 
 		// tile <- touched bitmap of this bucket
 		if (P.have_prior) {
@@ -528,33 +570,40 @@ resolve_kernel(const ResolveParams P)
 		for (uint32_t cb = 0; cb < nci; cb += RS_THREADS) {
 			const uint32_t nrt = min((uint32_t)RS_THREADS, nci - cb);
 			if (cb) {          // run tables beyond the prefetched first RS_THREADS runs
+				uint32_t off = 0, len = 0;
 				if (tid < nrt) {
 					const uint32_t c = cb + tid;
 					const uint32_t s = row_s[c], e = row_s[pitch + c];
 					const uint64_t base = P.chunk_stride ? (uint64_t)(c0 + c) * P.chunk_stride : P.chunk_rec[c0 + c];
-					s_off[tid] = base + s;
-					s_len[tid] = e - s;
+					off = (uint32_t)(base + s);
+					len = e - s;
 				}
+				s_off[tid] = off;
+				s_len[tid] = len;
+				if (tid == 0) *s_nlong = 0;
+				__syncthreads();
+				if (len > 32) s_long[atomicAdd(s_nlong, 1u)] = (uint16_t)tid;
 				__syncthreads();
 			}
-			// one warp per run, four runs in flight
-			for (uint32_t r0 = warp; r0 < nrt; r0 += 4 * (RS_THREADS / 32)) {
-				uint64_t rec[4];
-				uint32_t len[4];
-				const uint64_t* run[4];
+			// one warp per run, the first 32 records of RS_U runs in flight (s_len is zero beyond nrt)
+			for (uint32_t r0 = warp; r0 < nrt; r0 += RS_U * (RS_THREADS / 32)) {
+				uint64_t rec[RS_U];
+				uint32_t len[RS_U];
 #pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					const uint32_t r = r0 + u * (RS_THREADS / 32);
-					len[u] = (r < nrt) ? s_len[r] : 0u;
-					run[u] = P.rec + ((r < nrt) ? s_off[r] : 0ull);
+				for (int u = 0; u < RS_U; ++u) {
+					const uint32_t r = (r0 + u * (RS_THREADS / 32)) & (RS_THREADS - 1);
+					len[u] = (r >= r0) ? s_len[r] : 0u;
+					rec[u] = (lane < len[u]) ? ld_nc_u64(P.rec + s_off[r] + lane) : 0ull;
 				}
 #pragma unroll
-				for (int u = 0; u < 4; ++u) rec[u] = (lane < len[u]) ? ld_nc_u64(run[u] + lane) : 0ull;
-#pragma unroll
-				for (int u = 0; u < 4; ++u) {
+				for (int u = 0; u < RS_U; ++u)
 					if (lane < len[u]) resolve_record(s_tile, s_bm, P.loss, rec[u]);
-					for (uint32_t x = 32 + lane; x < len[u]; x += 32) resolve_record(s_tile, s_bm, P.loss, ld_nc_u64(run[u] + x));
-				}
+			}
+			const uint32_t nlong = *s_nlong;
+			for (uint32_t q = warp; q < nlong; q += RS_THREADS / 32) {
+				const uint32_t r = s_long[q], len = s_len[r];
+				const uint64_t* run = P.rec + s_off[r];
+				for (uint32_t x = 32 + lane; x < len; x += 32) resolve_record(s_tile, s_bm, P.loss, ld_nc_u64(run + x));
 			}
 			__syncthreads();
 		}
