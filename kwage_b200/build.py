@@ -11,7 +11,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libkwage_cuda.so")
 SOURCES = ["api.cu", "bloom_build.cu", "transpose.cu", "search.cu", "synth.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "kwage_cuda.h")]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+    [os.path.join(ROOT, "include", "kwage_cuda.h"), os.path.abspath(__file__)]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

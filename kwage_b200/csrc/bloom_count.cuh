@@ -28,11 +28,14 @@
 // duplication (poly-G reads, adapters) only makes one bucket longer, never overflows anything.
 #pragma once
 #include "common.cuh"
+#ifdef KWG_DEBUG_RESOLVE
+#include <cstdio>
+#endif
 
 namespace kwg {
 
 constexpr int PT_THREADS = 512;                   // partition_scan_kernel block size
-constexpr int RG_THREADS = 512;                   // regroup_kernel block size
+constexpr int RG_THREADS = 1024;                  // regroup_kernel block size
 constexpr int PT_POS = 2048;                      // k-mer start positions per partition tile
 constexpr int PT_REC = 4 * PT_POS;                // record slots per tile
 constexpr int PT_LOAD = PT_POS + 32;              // bases staged per tile (halo >= k-1, 16-byte granular)
@@ -43,7 +46,6 @@ constexpr int MAX_FAN_LOG2 = 9;                   // at most 512 buckets per par
 constexpr int MAX_FAN = 1 << MAX_FAN_LOG2;
 constexpr int CHUNK_REC = 8192;                   // records per level-2 chunk
 constexpr int RS_THREADS = 1024;                  // resolve kernel block size
-constexpr int RS_U = 8;                           // runs in flight per warp in the resolve kernel
 constexpr uint32_t SLOT_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t MAX_COUNT_POS = 1ull << 28;    // positions per counting sub-batch (record: 28-bit position)
 
@@ -83,12 +85,12 @@ struct PartParams {
 };
 
 // exclusive prefix sum of n <= MAX_FAN counters in shared memory (in place) by a block of THREADS
-// threads (256: two counters per thread, 512: one); returns the total.  s_warp: THREADS/32 words of scratch.
+// threads (256: two counters per thread, 512/1024: one); returns the total.  s_warp: THREADS/32 words of scratch.
 template <int THREADS>
 __device__ __forceinline__ uint32_t block_exclusive_scan_512(uint32_t* v, uint32_t n, uint32_t* s_warp)
 {
-	constexpr int ITEMS = MAX_FAN / THREADS;
-	static_assert(ITEMS == 1 || ITEMS == 2, "block size must be 256 or 512");
+	constexpr int ITEMS = (MAX_FAN + THREADS - 1) / THREADS;
+	static_assert(ITEMS == 1 || ITEMS == 2, "block size must be 256, 512 or 1024");
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t a = (ITEMS * tid < n) ? v[ITEMS * tid] : 0u;
 	const uint32_t b = (ITEMS == 2 && 2 * tid + 1 < n) ? v[2 * tid + 1] : 0u;
@@ -237,11 +239,13 @@ group_count_kernel(const uint16_t* __restrict__ offs1, uint32_t ntp, uint32_t n_
 	if (lane == 0) cnt1[idx] = sum;
 }
 
-// Exclusive prefix sums over the F1*NG (bucket-major) group counts: record base of every group, id of
-// its first chunk, record base of every chunk, first chunk of every level-1 bucket.  One block.
+// Exclusive prefix sums over the F1*NG (bucket-major) group counts: record base of every group (kept
+// even so that every chunk starts 16-byte aligned for the bulk stores), id of its first chunk, record
+// base and owning pair of every chunk, first chunk of every level-1 bucket.  One block.
 __global__ void __launch_bounds__(1024)
 group_prefix_kernel(const uint32_t* __restrict__ cnt1, uint32_t n, uint32_t NG, uint32_t F1,
-	uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase, uint64_t* __restrict__ chunk_rec, uint32_t* __restrict__ cfirst)
+	uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase, uint64_t* __restrict__ chunk_rec, uint32_t* __restrict__ chunk_pair,
+	uint32_t* __restrict__ cfirst)
 {
 	__shared__ unsigned long long s_rec[32];
 	__shared__ uint32_t s_chk[32];
@@ -250,7 +254,7 @@ group_prefix_kernel(const uint32_t* __restrict__ cnt1, uint32_t n, uint32_t NG, 
 	const uint32_t a = min(tid * per, n), b = min(a + per, n);
 	unsigned long long rsum = 0;
 	uint32_t csum = 0;
-	for (uint32_t x = a; x < b; ++x) { const uint32_t c = cnt1[x]; rsum += c; csum += (c + CHUNK_REC - 1) / CHUNK_REC; }
+	for (uint32_t x = a; x < b; ++x) { const uint32_t c = cnt1[x]; rsum += (c + 1u) & ~1u; csum += (c + CHUNK_REC - 1) / CHUNK_REC; }
 	unsigned long long rinc = rsum;
 	uint32_t cinc = csum;
 	for (int o = 1; o < 32; o <<= 1) {
@@ -274,10 +278,91 @@ group_prefix_kernel(const uint32_t* __restrict__ cnt1, uint32_t n, uint32_t NG, 
 		cbase[x] = c;
 		if (x % NG == 0) cfirst[x / NG] = c;
 		const uint32_t nc = (cnt + CHUNK_REC - 1) / CHUNK_REC;
-		for (uint32_t q = 0; q < nc; ++q) chunk_rec[c + q] = r + (unsigned long long)q * CHUNK_REC;
-		r += cnt; c += nc;
+		for (uint32_t q = 0; q < nc; ++q) { chunk_rec[c + q] = r + (unsigned long long)q * CHUNK_REC; chunk_pair[c + q] = x; }
+		r += (cnt + 1u) & ~1u; c += nc;
 	}
 	if (tid == 0) cfirst[F1] = ctotal;
+}
+
+// ------------------------------------------------------------------------------------------ async-copy plumbing
+// The runs a block gathers are short (~26 records = 208 bytes) and scattered.  Loading them with LDG costs
+// ~40 instructions per run and leaves every warp waiting on its own few loads; instead one thread per run
+// issues one bulk asynchronous copy (cp.async.bulk, the TMA engine's linear mode) into shared memory: all
+// the runs of a block are in flight at once, no registers are held, and completion is one mbarrier wait.
+// Bulk copies need 16-byte aligned addresses and sizes; runs are 8-byte aligned, so a copy is widened by
+// up to one record on either side and the owner thread overwrites those strangers with REC_NULL.
+constexpr int STAGE_REC = CHUNK_REC + 2 * MAX_FAN;           // staging capacity in records (72 KiB)
+constexpr uint32_t REC_NULL_HI = 0xFFFFFFFFu;                // slot field of a padding record (real ones use < 2^24)
+constexpr unsigned long long REC_NULL = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must trap, not hang the device.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+	const uint32_t addr = smem_u32(bar);
+	for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+		uint32_t done;
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+		if (done) return;
+	}
+	__trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+	             :: "l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy accesses to shared memory before this fence are ordered before later async-proxy accesses
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// exclusive prefix sum of one value per thread over a block of 1024 threads; returns the total
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t x, uint32_t& total, uint32_t* s_warp)
+{
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = x;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+		if (lane >= (uint32_t)o) inc += y;
+	}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	uint32_t w = (lane < 32) ? s_warp[lane] : 0u;          // every warp scans the 32 warp totals
+	uint32_t winc = w;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+		if (lane >= (uint32_t)o) winc += y;
+	}
+	total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+	const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, winc - w, warp);
+	__syncthreads();
+	return wbase + inc - x;
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -288,154 +373,141 @@ struct RegroupParams {
 	uint32_t F1, G1, NG;
 	uint32_t f2_log2;
 	const uint32_t* cnt1;
-	const uint64_t* base2;
 	const uint32_t* cbase;
-	const uint32_t* cfirst;
+	const uint32_t* cfirst;      // [F1 + 1]; cfirst[F1] = number of chunks = work units of this kernel
+	const uint64_t* chunk_rec;
+	const uint32_t* chunk_pair;
 	uint64_t* rec2;
 	uint16_t* offs2;             // bucket i: rows at cfirst[i]*(F2+1); entry (j, local chunk c) at + j*nci + c
 };
 
-// One block regroups the runs of level-1 bucket i coming from a group of G1 <= 512 tiles.  Every warp
-// owns RG_R runs per round and keeps their first 32 records in registers: all RG_R loads (256 bytes
-// each) are issued back to back, so one DRAM round trip covers the block's whole input, and the
-// scatter pass re-uses the registers instead of reading the runs again.  Runs longer than a warp
-// (~9 % at the usual 26 records per run) and the first round of 512-tile groups are re-read (L2).
-constexpr int RG_R = 16;                                     // runs per warp per round
-constexpr int RG_RPR = (RG_THREADS / 32) * RG_R;             // runs per block per round (256)
-static_assert(2 * RG_RPR >= MAX_FAN, "two rounds must cover the largest tile group");
+struct RegroupUnit {             // what process() needs to know about a staged chunk
+	uint32_t staged;             // records in the staging buffer (including padding)
+	uint32_t count;              // real records of the chunk
+	uint32_t nci, cl;            // chunks of the level-1 bucket, index of this chunk among them
+	unsigned long long rows;     // offs2 element index of the bucket's rows
+	unsigned long long out;      // rec2 record index of the chunk
+};
 
-__global__ void __launch_bounds__(RG_THREADS, 2)
+// Persistent blocks, one work unit = one chunk (<= CHUNK_REC records of level-1 bucket i from one group of
+// tiles).  Two staging buffers: the runs of the next unit are gathered while this one is sorted.
+__global__ void __launch_bounds__(RG_THREADS, 1)
 regroup_kernel(const RegroupParams P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	uint64_t* s_sorted = reinterpret_cast<uint64_t*>(smem_raw);             // CHUNK_REC records
-	uint32_t* s_vs = reinterpret_cast<uint32_t*>(smem_raw + CHUNK_REC * 8); // MAX_FAN + 1: virtual start of each run
-	uint32_t* s_roff = s_vs + MAX_FAN + 1;                                  // MAX_FAN: record offset of the run's part in this chunk
-	uint32_t* s_hist = s_roff + MAX_FAN;                                    // MAX_FAN + 1
-	uint32_t* s_cursor = s_hist + MAX_FAN + 1;                              // MAX_FAN
-	uint32_t* s_warp = s_cursor + MAX_FAN;                                  // RG_THREADS / 32
-	uint32_t* s_nlong = s_warp + RG_THREADS / 32;                           // 1: runs with more than 32 records in this chunk
-	uint16_t* s_rs = reinterpret_cast<uint16_t*>(s_nlong + 1);              // MAX_FAN: run start inside its tile
-	uint16_t* s_rn = s_rs + MAX_FAN;                                        // MAX_FAN: records of the run in this chunk
-	uint16_t* s_long = s_rn + MAX_FAN;                                      // MAX_FAN: the long runs
+	uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem_raw);                          // [2][STAGE_REC]
+	uint64_t* s_sorted = s_stage + 2 * STAGE_REC;                                       // CHUNK_REC (+2 spare)
+	unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_sorted + CHUNK_REC + 2);   // [2]
+	RegroupUnit* s_unit = reinterpret_cast<RegroupUnit*>(s_bar + 2);                    // [2]
+	uint32_t* s_own = reinterpret_cast<uint32_t*>(s_unit + 2);                          // [2][MAX_FAN]: so | n << 14 | lead << 28
+	uint32_t* s_hist = s_own + 2 * MAX_FAN;                                             // MAX_FAN + 1
+	uint32_t* s_cursor = s_hist + MAX_FAN + 1;                                          // MAX_FAN
+	uint32_t* s_warp = s_cursor + MAX_FAN;                                              // 32
 
-	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	constexpr uint32_t NW = RG_THREADS / 32;
-	const uint32_t i = blockIdx.x % P.F1, g = blockIdx.x / P.F1;
-	const uint32_t pair = i * P.NG + g;
-	const uint32_t cnt = P.cnt1[pair];
-	if (cnt == 0) return;
-	const uint32_t t0 = g * P.G1;
-	const uint32_t nt = min(P.G1, P.n_tiles - t0);
+	const uint32_t tid = threadIdx.x;
 	const uint32_t F2 = 1u << P.f2_log2;
-	const uint64_t* __restrict__ base = P.rec1 + (uint64_t)t0 * PT_REC;
+	const uint32_t n_units = P.cfirst[P.F1];
 
-	for (uint32_t r = tid; r < (uint32_t)MAX_FAN; r += RG_THREADS) {
-		uint32_t s = 0, len = 0;
-		if (r < nt) {
-			s = P.offs1[(uint64_t)i * P.ntp + t0 + r];
-			len = (uint32_t)P.offs1[(uint64_t)(i + 1) * P.ntp + t0 + r] - s;
-		}
-		s_rs[r] = (uint16_t)s;
-		s_vs[r] = len;
-	}
-	__syncthreads();
-	block_exclusive_scan_512<RG_THREADS>(s_vs, MAX_FAN, s_warp);
-	if (tid == 0) s_vs[MAX_FAN] = cnt;
+	if (tid == 0) { mbar_init(&s_bar[0], RG_THREADS); mbar_init(&s_bar[1], RG_THREADS); mbar_init_fence(); }
 	__syncthreads();
 
-	const uint32_t nchunk = (cnt + CHUNK_REC - 1) / CHUNK_REC;
-	const uint32_t c0 = P.cfirst[i];
-	const uint32_t nci = P.cfirst[i + 1] - c0;
-	const uint32_t cl0 = P.cbase[pair] - c0;
-	uint16_t* rows = P.offs2 + (uint64_t)c0 * (F2 + 1);
-	const uint64_t out0 = P.base2[pair];
-	const uint32_t n_rounds = (nt + RG_RPR - 1) / RG_RPR;       // 1 or 2
-
-	for (uint32_t c = 0; c < nchunk; ++c) {
-		const uint32_t cv0 = c * CHUNK_REC, cv1 = min(cnt, cv0 + CHUNK_REC);
-		for (uint32_t v = tid; v <= F2; v += RG_THREADS) s_hist[v] = 0;
-		if (tid == 0) *s_nlong = 0;
-		__syncthreads();
-		for (uint32_t r = tid; r < (uint32_t)MAX_FAN; r += RG_THREADS) {
-			const uint32_t vs = s_vs[r], ve = s_vs[r + 1];
-			const uint32_t lo = max(vs, cv0), hi = min(ve, cv1);
-			const uint32_t n = (lo < hi) ? hi - lo : 0u;
-			s_rn[r] = (uint16_t)n;
-			s_roff[r] = r * PT_REC + s_rs[r] + (lo - vs);
-			if (n > 32) s_long[atomicAdd(s_nlong, 1u)] = (uint16_t)r;
+	// gather the runs of unit u into staging buffer `buf`
+	auto prepare = [&](uint32_t u, uint32_t buf) {
+		const uint32_t pair = P.chunk_pair[u];
+		const uint32_t i = pair / P.NG, g = pair % P.NG;
+		const uint32_t cnt = P.cnt1[pair];
+		const uint32_t clocal = u - P.cbase[pair];
+		const uint32_t cv0 = clocal * CHUNK_REC, cv1 = min(cnt, cv0 + CHUNK_REC);
+		const uint32_t t0 = g * P.G1;
+		const uint32_t nt = min(P.G1, P.n_tiles - t0);
+		uint32_t s0 = 0, n = 0;
+		if (tid < nt) {
+			s0 = P.offs1[(uint64_t)i * P.ntp + t0 + tid];
+			n = (uint32_t)P.offs1[(uint64_t)(i + 1) * P.ntp + t0 + tid] - s0;
 		}
+		if (cnt > CHUNK_REC) {           // (block-uniform) a skewed group spans several chunks: clip the runs to this one
+			uint32_t tot;
+			const uint32_t vs = block_exclusive_scan_1024(n, tot, s_warp);
+			const uint32_t lo = max(vs, cv0), hi = min(vs + n, cv1);
+			s0 += lo - vs;
+			n = (lo < hi) ? hi - lo : 0u;
+		}
+		const uint32_t lead = s0 & 1u;
+		const uint32_t span = n ? ((lead + n + 1u) & ~1u) : 0u;
+		uint32_t staged;
+		const uint32_t so = block_exclusive_scan_1024(span, staged, s_warp);
+		if (tid < (uint32_t)MAX_FAN) s_own[buf * MAX_FAN + tid] = so | (n << 14) | (lead << 28);
+		if (tid == 0) {
+			const uint32_t c0 = P.cfirst[i];
+			RegroupUnit U;
+			U.staged = staged; U.count = cv1 - cv0;
+			U.nci = P.cfirst[i + 1] - c0; U.cl = u - c0;
+			U.rows = (unsigned long long)c0 * (F2 + 1);
+			U.out = P.chunk_rec[u];
+			s_unit[buf] = U;
+		}
+		// every thread arrives; those with a run announce its bytes and start the copy.  Earlier generic
+		// accesses to this staging buffer (previous unit's reads and padding stores) are fenced first.
+		fence_async_smem();
 		__syncthreads();
-		const uint32_t nlong = *s_nlong;
+		if (n) {
+			mbar_arrive_expect_tx(&s_bar[buf], span * 8u);
+			bulk_g2s(s_stage + (size_t)buf * STAGE_REC + so, P.rec1 + (uint64_t)(t0 + tid) * PT_REC + (s0 - lead), span * 8u, &s_bar[buf]);
+		} else {
+			mbar_arrive(&s_bar[buf]);
+		}
+	};
 
-		// pass A: level-2 histogram; the records of the last round stay in registers
-		uint64_t rec[RG_R];
-		for (uint32_t round = 0; round < n_rounds; ++round) {
-			const uint32_t rb = round * RG_RPR + warp;
-#pragma unroll
-			for (int u = 0; u < RG_R; ++u) {
-				const uint32_t r = rb + u * NW;
-				rec[u] = (lane < s_rn[r]) ? base[s_roff[r] + lane] : 0ull;
+	uint32_t phase = 0;                   // bit b: parity to wait for on barrier b
+	uint32_t u = blockIdx.x, k = 0;
+	if (u < n_units) prepare(u, 0);
+	for (; u < n_units; u += gridDim.x, k ^= 1u) {
+		if (u + gridDim.x < n_units) prepare(u + gridDim.x, k ^ 1u);
+
+		uint64_t* stage = s_stage + (size_t)k * STAGE_REC;
+		mbar_wait(&s_bar[k], (phase >> k) & 1u);
+		phase ^= 1u << k;
+		if (tid < (uint32_t)MAX_FAN) {
+			const uint32_t own = s_own[k * MAX_FAN + tid];
+			const uint32_t so = own & 0x3FFFu, n = (own >> 14) & 0x3FFFu, lead = own >> 28;
+			if (n) {
+				if (lead) stage[so] = REC_NULL;
+				if ((lead + n) & 1u) stage[so + lead + n] = REC_NULL;
 			}
-#pragma unroll
-			for (int u = 0; u < RG_R; ++u)
-				if (lane < s_rn[rb + u * NW]) atomicAdd(&s_hist[(uint32_t)(rec[u] >> 32) >> FINAL_LOG2], 1u);
 		}
-		for (uint32_t q = warp; q < nlong; q += NW) {
-			const uint32_t r = s_long[q], n = s_rn[r];
-			const uint64_t* run = base + s_roff[r];
-			for (uint32_t x = 32 + lane; x < n; x += 32) atomicAdd(&s_hist[(uint32_t)(run[x] >> 32) >> FINAL_LOG2], 1u);
+		for (uint32_t v = tid; v <= F2; v += RG_THREADS) s_hist[v] = 0;
+		__syncthreads();
+		const RegroupUnit U = s_unit[k];
+
+		// pass A: level-2 histogram, one record per lane
+		for (uint32_t e = tid; e < U.staged; e += RG_THREADS) {
+			const uint32_t hi = (uint32_t)(stage[e] >> 32);
+			if (hi != REC_NULL_HI) atomicAdd(&s_hist[hi >> FINAL_LOG2], 1u);
 		}
 		__syncthreads();
 		block_exclusive_scan_512<RG_THREADS>(s_hist, F2, s_warp);
+		uint16_t* rows = P.offs2 + U.rows;
 		for (uint32_t j = tid; j < F2; j += RG_THREADS) {
 			const uint32_t s = s_hist[j];
 			s_cursor[j] = s;
-			rows[(uint64_t)j * nci + cl0 + c] = (uint16_t)s;
+			rows[(uint64_t)j * U.nci + U.cl] = (uint16_t)s;
 		}
-		if (tid == 0) rows[(uint64_t)F2 * nci + cl0 + c] = (uint16_t)(cv1 - cv0);
-		__syncthreads();
-
-		// pass B: scatter into the staging chunk
-		for (uint32_t round = 0; round + 1 < n_rounds; ++round) {          // earlier rounds: re-read (L2)
-			const uint32_t rb = round * RG_RPR + warp;
-			uint64_t tmp[RG_R];
-#pragma unroll
-			for (int u = 0; u < RG_R; ++u) {
-				const uint32_t r = rb + u * NW;
-				tmp[u] = (lane < s_rn[r]) ? base[s_roff[r] + lane] : 0ull;
-			}
-#pragma unroll
-			for (int u = 0; u < RG_R; ++u)
-				if (lane < s_rn[rb + u * NW]) s_sorted[atomicAdd(&s_cursor[(uint32_t)(tmp[u] >> 32) >> FINAL_LOG2], 1u)] = tmp[u];
-		}
-		{
-			const uint32_t rb = (n_rounds - 1) * RG_RPR + warp;
-#pragma unroll
-			for (int u = 0; u < RG_R; ++u)
-				if (lane < s_rn[rb + u * NW]) s_sorted[atomicAdd(&s_cursor[(uint32_t)(rec[u] >> 32) >> FINAL_LOG2], 1u)] = rec[u];
-		}
-		for (uint32_t q = warp; q < nlong; q += NW) {
-			const uint32_t r = s_long[q], n = s_rn[r];
-			const uint64_t* run = base + s_roff[r];
-			for (uint32_t x = 32 + lane; x < n; x += 32) {
-				const uint64_t v = run[x];
-				s_sorted[atomicAdd(&s_cursor[(uint32_t)(v >> 32) >> FINAL_LOG2], 1u)] = v;
-			}
+		if (tid == 0) {
+			rows[(uint64_t)F2 * U.nci + U.cl] = (uint16_t)U.count;
+			bulk_wait_read();             // the previous chunk has left s_sorted
 		}
 		__syncthreads();
-		uint4* dst = reinterpret_cast<uint4*>(P.rec2 + out0 + cv0);
-		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-			const uint4* src = reinterpret_cast<const uint4*>(s_sorted);
-			const uint32_t n2 = (cv1 - cv0) / 2;
-			for (uint32_t x = tid; x < n2; x += RG_THREADS) st_na_v4(dst + x, src[x]);
-			if (tid == 0 && ((cv1 - cv0) & 1u)) P.rec2[out0 + cv1 - 1] = s_sorted[cv1 - cv0 - 1];
-		} else {
-			uint64_t* d8 = P.rec2 + out0 + cv0;
-			for (uint32_t x = tid; x < cv1 - cv0; x += RG_THREADS) d8[x] = s_sorted[x];
+		// pass B: counting-sort scatter
+		for (uint32_t e = tid; e < U.staged; e += RG_THREADS) {
+			const uint64_t rec = stage[e];
+			const uint32_t hi = (uint32_t)(rec >> 32);
+			if (hi != REC_NULL_HI) s_sorted[atomicAdd(&s_cursor[hi >> FINAL_LOG2], 1u)] = rec;
 		}
+		fence_async_smem();
 		__syncthreads();
+		if (tid == 0) bulk_s2g(P.rec2 + U.out, s_sorted, ((U.count + 1u) & ~1u) * 8u);
 	}
+	if (tid == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------ K3
@@ -453,6 +525,9 @@ struct ResolveParams {
 	uint32_t have_prior;         // 0: first batch after create/reset, the bitmap is known to be all zero
 	uint32_t* loss;              // 4-bit loss counters, 8 positions per word
 };
+
+constexpr uint32_t RS_LONG = 64;                             // runs longer than this are read directly, not staged
+constexpr uint32_t RS_ROUND = STAGE_REC - (RS_LONG + 2);     // staging window per round (one run may overhang)
 
 __device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
 {
@@ -504,19 +579,32 @@ __device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P
 	return r;
 }
 
+// One final bucket at a time per (persistent) block: 2^15 slots as a 128 KiB tile of u32 "smallest
+// position that touched the slot".  The bucket's runs (one per chunk, ~26 records) are gathered into the
+// staging buffer by bulk async copies while the tile is initialised, then resolved one record per lane.
 __global__ void __launch_bounds__(RS_THREADS, 1)
 resolve_kernel(const ResolveParams P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);                           // FINAL_SLOTS
-	uint32_t* s_bm = s_tile + FINAL_SLOTS;                                              // FINAL_SLOTS / 32
+	uint64_t* s_stage = reinterpret_cast<uint64_t*>(s_tile + FINAL_SLOTS);              // STAGE_REC
+	unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_stage + STAGE_REC);        // 1 (+1 pad)
+	uint32_t* s_bm = reinterpret_cast<uint32_t*>(s_bar + 2);                            // FINAL_SLOTS / 32
 	uint32_t* s_off = s_bm + FINAL_SLOTS / 32;                                          // RS_THREADS: record index of every run
 	uint32_t* s_len = s_off + RS_THREADS;                                               // RS_THREADS
-	uint32_t* s_nlong = s_len + RS_THREADS;                                             // 1: runs with more than 32 records
-	uint16_t* s_long = reinterpret_cast<uint16_t*>(s_nlong + 1);                        // RS_THREADS: their indices
+	uint32_t* s_warp = s_len + RS_THREADS;                                              // 32
+	uint32_t* s_misc = s_warp + 32;                                                     // [0] long runs, [1] staged extent of the round
+	uint16_t* s_long = reinterpret_cast<uint16_t*>(s_misc + 2);                         // RS_THREADS: indices of the long runs
+#ifdef KWG_DEBUG_RESOLVE
+	__shared__ uint32_t s_dbg[2];
+#endif
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t F2 = 1u << P.f2_log2;
+
+	if (tid == 0) { mbar_init(&s_bar[0], RS_THREADS); mbar_init_fence(); }
+	__syncthreads();
+	uint32_t parity = 0;
 
 	uint32_t b = blockIdx.x;
 	BucketPrefetch pf{0u, 0u, 0u};
@@ -529,81 +617,116 @@ resolve_kernel(const ResolveParams P)
 		const uint64_t pitch = P.row_pitch ? P.row_pitch : (uint64_t)nci;
 		const uint16_t* row_s = P.offs + (uint64_t)c0 * (F2 + 1) + (uint64_t)j * pitch;
 
+		uint32_t my_off = pf.off, my_len = pf.len;
 		s_bm[tid] = pf.bmw;
-		s_off[tid] = pf.off;
-		s_len[tid] = pf.len;
-		if (tid == 0) *s_nlong = 0;
-		__syncthreads();
-		if (pf.len > 32) s_long[atomicAdd(s_nlong, 1u)] = (uint16_t)tid;
 		// tables of the next bucket travel while this one is resolved, and its runs are pulled into L2
 		if (b + gridDim.x < P.n_buckets) {
 			pf = prefetch_bucket(P, b + gridDim.x);
 			if (pf.len) {
 				const char* p0 = reinterpret_cast<const char*>(P.rec + pf.off);
-				const char* p1 = p0 + (size_t)min(pf.len, 64u) * 8 - 1;
+				const char* p1 = p0 + (size_t)min(pf.len, RS_LONG) * 8 - 1;
 				for (const char* q = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127); q <= p1; q += 128)
 					asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
 			}
 		}
 
-		// tile <- touched bitmap of this bucket
-		if (P.have_prior) {
-#pragma unroll
-			for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
-				const uint32_t s4 = (q * RS_THREADS + tid) * 4;
-				const uint32_t bits = s_bm[s4 >> 5] >> (s4 & 31);
-				uint4 v;
-				v.x = (bits & 1u) ? 0u : SLOT_EMPTY;
-				v.y = (bits & 2u) ? 0u : SLOT_EMPTY;
-				v.z = (bits & 4u) ? 0u : SLOT_EMPTY;
-				v.w = (bits & 8u) ? 0u : SLOT_EMPTY;
-				reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = v;
-			}
-		} else {
-			const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY);
-#pragma unroll
-			for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q)
-				reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = e4;
-		}
-		__syncthreads();
-
+		bool tile_ready = false;
 		for (uint32_t cb = 0; cb < nci; cb += RS_THREADS) {
 			const uint32_t nrt = min((uint32_t)RS_THREADS, nci - cb);
 			if (cb) {          // run tables beyond the prefetched first RS_THREADS runs
-				uint32_t off = 0, len = 0;
+				my_off = 0; my_len = 0;
 				if (tid < nrt) {
 					const uint32_t c = cb + tid;
 					const uint32_t s = row_s[c], e = row_s[pitch + c];
 					const uint64_t base = P.chunk_stride ? (uint64_t)(c0 + c) * P.chunk_stride : P.chunk_rec[c0 + c];
-					off = (uint32_t)(base + s);
-					len = e - s;
+					my_off = (uint32_t)(base + s);
+					my_len = e - s;
 				}
-				s_off[tid] = off;
-				s_len[tid] = len;
-				if (tid == 0) *s_nlong = 0;
-				__syncthreads();
-				if (len > 32) s_long[atomicAdd(s_nlong, 1u)] = (uint16_t)tid;
-				__syncthreads();
 			}
-			// one warp per run, the first 32 records of RS_U runs in flight (s_len is zero beyond nrt)
-			for (uint32_t r0 = warp; r0 < nrt; r0 += RS_U * (RS_THREADS / 32)) {
-				uint64_t rec[RS_U];
-				uint32_t len[RS_U];
-#pragma unroll
-				for (int u = 0; u < RS_U; ++u) {
-					const uint32_t r = (r0 + u * (RS_THREADS / 32)) & (RS_THREADS - 1);
-					len[u] = (r >= r0) ? s_len[r] : 0u;
-					rec[u] = (lane < len[u]) ? ld_nc_u64(P.rec + s_off[r] + lane) : 0ull;
+			if (tid == 0) s_misc[0] = 0;
+			// staging layout of the short runs: prefix sum of their 16-byte aligned spans
+			const bool is_long = my_len > RS_LONG;
+			const uint32_t lead = my_off & 1u;
+			const uint32_t span = (my_len && !is_long) ? ((lead + my_len + 1u) & ~1u) : 0u;
+			uint32_t staged;
+			const uint32_t so = block_exclusive_scan_1024(span, staged, s_warp);      // (two block barriers inside)
+			if (is_long) {
+				const uint32_t q = atomicAdd(&s_misc[0], 1u);
+				s_long[q] = (uint16_t)tid; s_off[q] = my_off; s_len[q] = my_len;
+			}
+
+			for (uint32_t r0 = 0; r0 < staged || r0 == 0; r0 += RS_ROUND) {
+				const bool mine = span && so >= r0 && so < r0 + RS_ROUND;
+				if (mine && (so + span >= r0 + RS_ROUND || so + span == staged)) s_misc[1] = so + span - r0;
+				if (staged == 0 && tid == 0) s_misc[1] = 0;
+				// the last run of the previous round may overhang the window: the first run of this one then
+				// starts a few records in, and what lies before it must not be resolved a second time
+				if (r0 && tid < RS_LONG + 2) s_stage[tid] = REC_NULL;
+				fence_async_smem();
+				__syncthreads();
+				if (mine) {
+					mbar_arrive_expect_tx(&s_bar[0], span * 8u);
+					bulk_g2s(s_stage + (so - r0), P.rec + (my_off - lead), span * 8u, &s_bar[0]);
+				} else {
+					mbar_arrive(&s_bar[0]);
 				}
+				if (!tile_ready) {
+					// tile <- touched bitmap of this bucket, while the copies are in flight
+					if (P.have_prior) {
 #pragma unroll
-				for (int u = 0; u < RS_U; ++u)
-					if (lane < len[u]) resolve_record(s_tile, s_bm, P.loss, rec[u]);
+						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
+							const uint32_t s4 = (q * RS_THREADS + tid) * 4;
+							const uint32_t bits = s_bm[s4 >> 5] >> (s4 & 31);
+							uint4 v;
+							v.x = (bits & 1u) ? 0u : SLOT_EMPTY;
+							v.y = (bits & 2u) ? 0u : SLOT_EMPTY;
+							v.z = (bits & 4u) ? 0u : SLOT_EMPTY;
+							v.w = (bits & 8u) ? 0u : SLOT_EMPTY;
+							reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = v;
+						}
+					} else {
+						const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY);
+#pragma unroll
+						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q)
+							reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = e4;
+					}
+					tile_ready = true;
+				}
+				mbar_wait(&s_bar[0], parity);
+				parity ^= 1u;
+				if (mine) {
+					if (lead) s_stage[so - r0] = REC_NULL;
+					if ((lead + my_len) & 1u) s_stage[so - r0 + lead + my_len] = REC_NULL;
+				}
+				__syncthreads();
+				const uint32_t extent = s_misc[1];
+#ifdef KWG_DEBUG_RESOLVE
+				if (tid == 0) { s_dbg[0] = 0; s_dbg[1] = 0; }
+				__syncthreads();
+				if (mine) atomicAdd(&s_dbg[1], my_len);
+#endif
+				for (uint32_t e = tid; e < extent; e += RS_THREADS) {
+					const uint64_t rec = s_stage[e];
+					if ((uint32_t)(rec >> 32) != REC_NULL_HI) {
+						resolve_record(s_tile, s_bm, P.loss, rec);
+#ifdef KWG_DEBUG_RESOLVE
+						atomicAdd(&s_dbg[0], 1u);
+#endif
+					}
+				}
+				__syncthreads();
+#ifdef KWG_DEBUG_RESOLVE
+				if (tid == 0 && s_dbg[0] != s_dbg[1])
+					printf("resolve mismatch: bucket %u cb %u r0 %u staged %u extent %u processed %u expected %u\n", b, cb, r0, staged, extent, s_dbg[0], s_dbg[1]);
+				__syncthreads();
+#endif
 			}
-			const uint32_t nlong = *s_nlong;
+			// long runs (heavy duplication): one warp per run straight from global memory
+			const uint32_t nlong = s_misc[0];
 			for (uint32_t q = warp; q < nlong; q += RS_THREADS / 32) {
-				const uint32_t r = s_long[q], len = s_len[r];
-				const uint64_t* run = P.rec + s_off[r];
-				for (uint32_t x = 32 + lane; x < len; x += 32) resolve_record(s_tile, s_bm, P.loss, ld_nc_u64(run + x));
+				const uint64_t* run = P.rec + s_off[q];
+				const uint32_t len = s_len[q];
+				for (uint32_t x = lane; x < len; x += 32) resolve_record(s_tile, s_bm, P.loss, ld_nc_u64(run + x));
 			}
 			__syncthreads();
 		}

@@ -150,6 +150,20 @@ def test_counting_mode_every_partition_geometry(lc, split):
     ob.close()
 
 
+@pytest.mark.parametrize("k,lc,n_reads", [(32, 22, 5000), (31, 23, 20000), (31, 21, 20000), (31, 20, 30000)])
+def test_counting_mode_many_tiles_per_bucket(k, lc, n_reads):
+    # single-level geometries with more tiles than one staging window holds: the resolve kernel gathers a
+    # bucket's runs in several rounds (and, beyond 1024 tiles, several run-table passes)
+    bases, offsets = S.uniform_reads(13, 0, n_reads, 150)
+    ob = O.Builder(k, 1, lc, 24)
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(k, min_kmer_count=1, log2_count_len=lc, log2_max_len=24) as b:
+        b.add_reads(bases, offsets)
+        assert b.num_valid() == ob.num_valid()
+        assert np.array_equal(b.finalize(24, 3), ob.finalize(24, 3))
+    ob.close()
+
+
 def test_counting_mode_small_filter_heavy_shadowing():
     # many more k-mers than counting slots: most first occurrences are shadowed by earlier k-mers, so
     # the stream-order rule (minimum position per slot, displacement of later occurrences) decides almost
