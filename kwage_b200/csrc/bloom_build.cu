@@ -217,7 +217,7 @@ struct kwg_bloom {
 	uint64_t* d_base2 = nullptr; size_t base2_cap = 0;
 	uint32_t* d_cbase = nullptr; size_t cbase_cap = 0;
 	uint64_t* d_chunk_rec = nullptr; size_t chunk_rec_cap = 0;
-	uint32_t* d_chunk_pair = nullptr; size_t chunk_pair_cap = 0;
+	uint4* d_chunk_meta = nullptr; size_t chunk_meta_cap = 0;
 	uint32_t* d_cfirst = nullptr; size_t cfirst_cap = 0;
 	uint32_t* d_loss = nullptr;  size_t loss_cap = 0;
 	// both modes
@@ -307,8 +307,8 @@ static size_t partition_smem_bytes()
 }
 static size_t regroup_smem_bytes()
 {
-	return (size_t)2 * STAGE_REC * 8 + (size_t)(CHUNK_REC + 2) * 8 + 16 + 2 * sizeof(RegroupUnit) +
-	       (size_t)(2 * MAX_FAN + (MAX_FAN + 1) + MAX_FAN + 32) * 4;
+	return (size_t)2 * STAGE_REC * 8 + (size_t)(CHUNK_REC + 2) * 8 + 32 + 2 * sizeof(RegroupUnit) +
+	       (size_t)(2 * MAX_FAN + 2 + (MAX_FAN + 1) + MAX_FAN + 16 + 4) * 4;
 }
 static size_t resolve_smem_bytes()
 {
@@ -386,23 +386,23 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		if ((rc = grow((void**)&b->d_cbase, &b->cbase_cap, n_pairs * sizeof(uint32_t)))) return rc;
 		if ((rc = grow((void**)&b->d_cfirst, &b->cfirst_cap, (size_t)(F1 + 1) * sizeof(uint32_t)))) return rc;
 		if ((rc = grow((void**)&b->d_chunk_rec, &b->chunk_rec_cap, max_chunks * sizeof(uint64_t)))) return rc;
-		if ((rc = grow((void**)&b->d_chunk_pair, &b->chunk_pair_cap, max_chunks * sizeof(uint32_t)))) return rc;
+		if ((rc = grow((void**)&b->d_chunk_meta, &b->chunk_meta_cap, max_chunks * sizeof(uint4)))) return rc;
 		if ((rc = grow((void**)&b->d_offs2, &b->offs2_cap, max_chunks * (F2 + 1) * sizeof(uint16_t)))) return rc;
 		if ((rc = grow((void**)&b->d_rec2, &b->rec2_cap, ((size_t)n_tiles * PT_REC + n_pairs + 2) * sizeof(uint64_t)))) return rc;
 
 		b->timers.begin(KWG_T_REGROUP, b->stream);
 		group_count_kernel<<<(unsigned)ceil_div(n_pairs, 8), 256, 0, b->stream>>>(b->d_offs1, ntp, (uint32_t)n_tiles, F1, G1, NG, b->d_cnt1);
 		KWG_LAUNCHED();
-		group_prefix_kernel<<<1, 1024, 0, b->stream>>>(b->d_cnt1, (uint32_t)n_pairs, NG, F1, b->d_base2, b->d_cbase, b->d_chunk_rec, b->d_chunk_pair, b->d_cfirst);
+		group_prefix_kernel<<<1, 1024, 0, b->stream>>>(b->d_cnt1, (uint32_t)n_pairs, NG, F1, b->d_base2, b->d_cbase, b->d_chunk_rec, b->d_chunk_meta, b->d_cfirst);
 		KWG_LAUNCHED();
 		RegroupParams K2{};
 		K2.rec1 = b->d_rec1; K2.offs1 = b->d_offs1; K2.ntp = ntp; K2.n_tiles = (uint32_t)n_tiles;
-		K2.F1 = F1; K2.G1 = G1; K2.NG = NG; K2.f2_log2 = G.f2_log2;
-		K2.cnt1 = b->d_cnt1; K2.cbase = b->d_cbase; K2.cfirst = b->d_cfirst;
-		K2.chunk_rec = b->d_chunk_rec; K2.chunk_pair = b->d_chunk_pair;
+		K2.F1 = F1; K2.G1 = G1; K2.f2_log2 = G.f2_log2;
+		K2.cfirst = b->d_cfirst;
+		K2.chunk_rec = b->d_chunk_rec; K2.chunk_meta = b->d_chunk_meta;
 		K2.rec2 = b->d_rec2; K2.offs2 = b->d_offs2;
 		const unsigned ggrid = (unsigned)std::min<uint64_t>(max_chunks, (uint64_t)sm_count(b->device));
-		regroup_kernel<<<ggrid, RG_THREADS, regroup_smem_bytes(), b->stream>>>(K2);
+		regroup_kernel<<<ggrid, RG_BLOCK, regroup_smem_bytes(), b->stream>>>(K2);
 		b->timers.end(b->stream);
 		KWG_LAUNCHED();
 
@@ -497,7 +497,7 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	cudaFree(b->d_touched);
 	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
-	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_pair);
+	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_meta);
 	cudaFree(b->d_cfirst); cudaFree(b->d_loss);
 	for (uint64_t* c : b->chunks) cudaFree(c);
 	cudaFree(b->d_chunk_table);

@@ -35,7 +35,6 @@
 namespace kwg {
 
 constexpr int PT_THREADS = 512;                   // partition_scan_kernel block size
-constexpr int RG_THREADS = 1024;                  // regroup_kernel block size
 constexpr int PT_POS = 2048;                      // k-mer start positions per partition tile
 constexpr int PT_REC = 4 * PT_POS;                // record slots per tile
 constexpr int PT_LOAD = PT_POS + 32;              // bases staged per tile (halo >= k-1, 16-byte granular)
@@ -241,10 +240,10 @@ group_count_kernel(const uint16_t* __restrict__ offs1, uint32_t ntp, uint32_t n_
 
 // Exclusive prefix sums over the F1*NG (bucket-major) group counts: record base of every group (kept
 // even so that every chunk starts 16-byte aligned for the bulk stores), id of its first chunk, record
-// base and owning pair of every chunk, first chunk of every level-1 bucket.  One block.
+// base and description of every chunk, first chunk of every level-1 bucket.  One block.
 __global__ void __launch_bounds__(1024)
 group_prefix_kernel(const uint32_t* __restrict__ cnt1, uint32_t n, uint32_t NG, uint32_t F1,
-	uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase, uint64_t* __restrict__ chunk_rec, uint32_t* __restrict__ chunk_pair,
+	uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase, uint64_t* __restrict__ chunk_rec, uint4* __restrict__ chunk_meta,
 	uint32_t* __restrict__ cfirst)
 {
 	__shared__ unsigned long long s_rec[32];
@@ -278,7 +277,10 @@ group_prefix_kernel(const uint32_t* __restrict__ cnt1, uint32_t n, uint32_t NG, 
 		cbase[x] = c;
 		if (x % NG == 0) cfirst[x / NG] = c;
 		const uint32_t nc = (cnt + CHUNK_REC - 1) / CHUNK_REC;
-		for (uint32_t q = 0; q < nc; ++q) { chunk_rec[c + q] = r + (unsigned long long)q * CHUNK_REC; chunk_pair[c + q] = x; }
+		for (uint32_t q = 0; q < nc; ++q) {
+			chunk_rec[c + q] = r + (unsigned long long)q * CHUNK_REC;
+			chunk_meta[c + q] = make_uint4(((x / NG) << 16) | (x % NG), cnt, q, 0u);     // (bucket i, group g), records of the pair, chunk within the pair
+		}
 		r += (cnt + 1u) & ~1u; c += nc;
 	}
 	if (tid == 0) cfirst[F1] = ctotal;
@@ -370,144 +372,246 @@ struct RegroupParams {
 	const uint64_t* rec1;
 	const uint16_t* offs1;
 	uint32_t ntp, n_tiles;
-	uint32_t F1, G1, NG;
+	uint32_t F1, G1;
 	uint32_t f2_log2;
-	const uint32_t* cnt1;
-	const uint32_t* cbase;
 	const uint32_t* cfirst;      // [F1 + 1]; cfirst[F1] = number of chunks = work units of this kernel
 	const uint64_t* chunk_rec;
-	const uint32_t* chunk_pair;
+	const uint4* chunk_meta;     // x: i << 16 | g, y: records of the (i, g) pair, z: chunk index within the pair
 	uint64_t* rec2;
 	uint16_t* offs2;             // bucket i: rows at cfirst[i]*(F2+1); entry (j, local chunk c) at + j*nci + c
 };
 
-struct RegroupUnit {             // what process() needs to know about a staged chunk
-	uint32_t staged;             // records in the staging buffer (including padding)
+struct RegroupUnit {             // what the consumers need to know about a staged chunk
 	uint32_t count;              // real records of the chunk
 	uint32_t nci, cl;            // chunks of the level-1 bucket, index of this chunk among them
+	uint32_t pad;
 	unsigned long long rows;     // offs2 element index of the bucket's rows
 	unsigned long long out;      // rec2 record index of the chunk
 };
 
-// Persistent blocks, one work unit = one chunk (<= CHUNK_REC records of level-1 bucket i from one group of
-// tiles).  Two staging buffers: the runs of the next unit are gathered while this one is sorted.
-__global__ void __launch_bounds__(RG_THREADS, 1)
+constexpr int RG_PRODUCERS = 128;                            // producer threads: each owns 4 consecutive runs
+constexpr int RG_CONSUMERS = 512;                            // consumer threads: one record per lane
+constexpr int RG_BLOCK = RG_PRODUCERS + RG_CONSUMERS;
+static_assert(RG_PRODUCERS * 4 == MAX_FAN, "a producer thread owns four runs");
+
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 2, %0;" :: "n"(RG_PRODUCERS) : "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(RG_CONSUMERS) : "memory"); }
+
+// exclusive prefix of one value per producer thread; *total receives the sum.  s_pw: RG_PRODUCERS/32 words.
+__device__ __forceinline__ uint32_t producer_exclusive_scan(uint32_t x, uint32_t* total, uint32_t* s_pw, uint32_t pt)
+{
+	const uint32_t lane = pt & 31, warp = pt >> 5;
+	uint32_t inc = x;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+		if (lane >= (uint32_t)o) inc += y;
+	}
+	producer_sync();                              // previous use of s_pw is over
+	if (lane == 31) s_pw[warp] = inc;
+	producer_sync();
+	uint32_t base = 0, tot = 0;
+#pragma unroll
+	for (int w = 0; w < RG_PRODUCERS / 32; ++w) {
+		const uint32_t v = s_pw[w];
+		if ((uint32_t)w < warp) base += v;
+		tot += v;
+	}
+	*total = tot;
+	return base + inc - x;
+}
+
+// exclusive prefix sum of n <= RG_CONSUMERS counters in shared memory (in place) by the consumer threads
+__device__ __forceinline__ void consumer_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* s_warp, uint32_t ct)
+{
+	const uint32_t lane = ct & 31, warp = ct >> 5;
+	const uint32_t a = (ct < n) ? v[ct] : 0u;
+	uint32_t x = a;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+		if (lane >= (uint32_t)o) x += y;
+	}
+	if (lane == 31) s_warp[warp] = x;
+	consumer_sync();
+	uint32_t base = 0;
+#pragma unroll
+	for (int w = 0; w < RG_CONSUMERS / 32; ++w)
+		if ((uint32_t)w < warp) base += s_warp[w];
+	if (ct < n) v[ct] = base + x - a;
+	consumer_sync();
+}
+
+// Persistent, warp-specialised blocks; one work unit = one chunk (<= CHUNK_REC records of level-1 bucket i
+// coming from one group of G1 <= 512 tiles).
+//   producer warps: each thread owns four consecutive runs of the unit (its slice of the run table is one
+//                   64-bit load per row, prefetched one unit ahead), the group prefix-sums the 16-byte aligned
+//                   spans into a staging layout and every thread issues its bulk async copies; completion is
+//                   tracked by the buffer's "full" mbarrier (complete_tx)
+//   consumer warps: wait for "full", blank the stranger records the 16-byte widening dragged in, histogram
+//                   the level-2 buckets, prefix-sum, scatter into the sorted chunk, bulk-store it, and hand
+//                   the staging buffer back through the "empty" mbarrier
+// Two staging buffers: the runs of the next unit travel while this one is sorted.
+__global__ void __launch_bounds__(RG_BLOCK, 1)
 regroup_kernel(const RegroupParams P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem_raw);                          // [2][STAGE_REC]
 	uint64_t* s_sorted = s_stage + 2 * STAGE_REC;                                       // CHUNK_REC (+2 spare)
-	unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_sorted + CHUNK_REC + 2);   // [2]
-	RegroupUnit* s_unit = reinterpret_cast<RegroupUnit*>(s_bar + 2);                    // [2]
+	unsigned long long* s_full = reinterpret_cast<unsigned long long*>(s_sorted + CHUNK_REC + 2);  // [2]
+	unsigned long long* s_empty = s_full + 2;                                           // [2]
+	RegroupUnit* s_unit = reinterpret_cast<RegroupUnit*>(s_empty + 2);                  // [2]
 	uint32_t* s_own = reinterpret_cast<uint32_t*>(s_unit + 2);                          // [2][MAX_FAN]: so | n << 14 | lead << 28
-	uint32_t* s_hist = s_own + 2 * MAX_FAN;                                             // MAX_FAN + 1
+	uint32_t* s_staged = s_own + 2 * MAX_FAN;                                           // [2] records staged (incl. padding)
+	uint32_t* s_hist = s_staged + 2;                                                    // MAX_FAN + 1
 	uint32_t* s_cursor = s_hist + MAX_FAN + 1;                                          // MAX_FAN
-	uint32_t* s_warp = s_cursor + MAX_FAN;                                              // 32
+	uint32_t* s_warp = s_cursor + MAX_FAN;                                              // 16 (consumer scans)
+	uint32_t* s_pw = s_warp + 16;                                                       // 4 (producer scans)
 
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
 	const uint32_t F2 = 1u << P.f2_log2;
 	const uint32_t n_units = P.cfirst[P.F1];
 
-	if (tid == 0) { mbar_init(&s_bar[0], RG_THREADS); mbar_init(&s_bar[1], RG_THREADS); mbar_init_fence(); }
+	if (tid == 0) {
+		mbar_init(&s_full[0], RG_PRODUCERS); mbar_init(&s_full[1], RG_PRODUCERS);
+		mbar_init(&s_empty[0], RG_CONSUMERS / 32); mbar_init(&s_empty[1], RG_CONSUMERS / 32);
+		mbar_init_fence();
+	}
 	__syncthreads();
 
-	// gather the runs of unit u into staging buffer `buf`
-	auto prepare = [&](uint32_t u, uint32_t buf) {
-		const uint32_t pair = P.chunk_pair[u];
-		const uint32_t i = pair / P.NG, g = pair % P.NG;
-		const uint32_t cnt = P.cnt1[pair];
-		const uint32_t clocal = u - P.cbase[pair];
-		const uint32_t cv0 = clocal * CHUNK_REC, cv1 = min(cnt, cv0 + CHUNK_REC);
-		const uint32_t t0 = g * P.G1;
-		const uint32_t nt = min(P.G1, P.n_tiles - t0);
-		uint32_t s0 = 0, n = 0;
-		if (tid < nt) {
-			s0 = P.offs1[(uint64_t)i * P.ntp + t0 + tid];
-			n = (uint32_t)P.offs1[(uint64_t)(i + 1) * P.ntp + t0 + tid] - s0;
-		}
-		if (cnt > CHUNK_REC) {           // (block-uniform) a skewed group spans several chunks: clip the runs to this one
-			uint32_t tot;
-			const uint32_t vs = block_exclusive_scan_1024(n, tot, s_warp);
-			const uint32_t lo = max(vs, cv0), hi = min(vs + n, cv1);
-			s0 += lo - vs;
-			n = (lo < hi) ? hi - lo : 0u;
-		}
-		const uint32_t lead = s0 & 1u;
-		const uint32_t span = n ? ((lead + n + 1u) & ~1u) : 0u;
-		uint32_t staged;
-		const uint32_t so = block_exclusive_scan_1024(span, staged, s_warp);
-		if (tid < (uint32_t)MAX_FAN) s_own[buf * MAX_FAN + tid] = so | (n << 14) | (lead << 28);
-		if (tid == 0) {
-			const uint32_t c0 = P.cfirst[i];
-			RegroupUnit U;
-			U.staged = staged; U.count = cv1 - cv0;
-			U.nci = P.cfirst[i + 1] - c0; U.cl = u - c0;
-			U.rows = (unsigned long long)c0 * (F2 + 1);
-			U.out = P.chunk_rec[u];
-			s_unit[buf] = U;
-		}
-		// every thread arrives; those with a run announce its bytes and start the copy.  Earlier generic
-		// accesses to this staging buffer (previous unit's reads and padding stores) are fenced first.
-		fence_async_smem();
-		__syncthreads();
-		if (n) {
-			mbar_arrive_expect_tx(&s_bar[buf], span * 8u);
-			bulk_g2s(s_stage + (size_t)buf * STAGE_REC + so, P.rec1 + (uint64_t)(t0 + tid) * PT_REC + (s0 - lead), span * 8u, &s_bar[buf]);
-		} else {
-			mbar_arrive(&s_bar[buf]);
-		}
-	};
-
-	uint32_t phase = 0;                   // bit b: parity to wait for on barrier b
-	uint32_t u = blockIdx.x, k = 0;
-	if (u < n_units) prepare(u, 0);
-	for (; u < n_units; u += gridDim.x, k ^= 1u) {
-		if (u + gridDim.x < n_units) prepare(u + gridDim.x, k ^ 1u);
-
-		uint64_t* stage = s_stage + (size_t)k * STAGE_REC;
-		mbar_wait(&s_bar[k], (phase >> k) & 1u);
-		phase ^= 1u << k;
-		if (tid < (uint32_t)MAX_FAN) {
-			const uint32_t own = s_own[k * MAX_FAN + tid];
-			const uint32_t so = own & 0x3FFFu, n = (own >> 14) & 0x3FFFu, lead = own >> 28;
-			if (n) {
-				if (lead) stage[so] = REC_NULL;
-				if ((lead + n) & 1u) stage[so + lead + n] = REC_NULL;
+	if (tid < (uint32_t)RG_PRODUCERS) {
+		// ================================================================= producer group
+		const uint32_t pt = tid;
+		// run table slice of a unit: runs 4pt .. 4pt+3, starts and ends as 4 x u16 each
+		uint2 ts = make_uint2(0, 0), te = make_uint2(0, 0);
+		uint4 meta = make_uint4(0, 0, 0, 0);
+		auto load_table = [&](uint32_t u) {
+			meta = P.chunk_meta[u];
+			const uint32_t i = meta.x >> 16, t0 = (meta.x & 0xFFFFu) * P.G1;
+			const uint32_t nt = min(P.G1, P.n_tiles - t0);
+			ts = make_uint2(0, 0); te = make_uint2(0, 0);
+			if (4 * pt < nt) {             // rows are 8-byte aligned (ntp % 64 == 0, t0 % 4 == 0); slack past nt is never used
+				const uint16_t* r0 = P.offs1 + (uint64_t)i * P.ntp + t0 + 4 * pt;
+				ts = *reinterpret_cast<const uint2*>(r0);
+				te = *reinterpret_cast<const uint2*>(r0 + P.ntp);
 			}
-		}
-		for (uint32_t v = tid; v <= F2; v += RG_THREADS) s_hist[v] = 0;
-		__syncthreads();
-		const RegroupUnit U = s_unit[k];
+		};
+		uint32_t u = blockIdx.x;
+		if (u < n_units) load_table(u);
+		for (uint32_t it = 0; u < n_units; u += gridDim.x, ++it) {
+			const uint32_t buf = it & 1u;
+			const uint32_t i = meta.x >> 16, t0 = (meta.x & 0xFFFFu) * P.G1;
+			const uint32_t nt = min(P.G1, P.n_tiles - t0);
+			const uint32_t cnt = meta.y, clocal = meta.z;
+			const uint32_t cv0 = clocal * CHUNK_REC, cv1 = min(cnt, cv0 + CHUNK_REC);
+			uint32_t s0[4], n[4];
+			s0[0] = ts.x & 0xFFFFu; s0[1] = ts.x >> 16; s0[2] = ts.y & 0xFFFFu; s0[3] = ts.y >> 16;
+			n[0] = (te.x & 0xFFFFu) - s0[0]; n[1] = (te.x >> 16) - s0[1]; n[2] = (te.y & 0xFFFFu) - s0[2]; n[3] = (te.y >> 16) - s0[3];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) if (4 * pt + q >= nt) { s0[q] = 0; n[q] = 0; }
+			// unit header (one thread; its loads overlap the layout computation)
+			unsigned long long out = 0;
+			uint32_t c0 = 0, c1 = 0;
+			if (pt == 0) { out = P.chunk_rec[u]; c0 = P.cfirst[i]; c1 = P.cfirst[i + 1]; }
+			if (u + gridDim.x < n_units) load_table(u + gridDim.x);     // next unit's table travels meanwhile
 
-		// pass A: level-2 histogram, one record per lane
-		for (uint32_t e = tid; e < U.staged; e += RG_THREADS) {
-			const uint32_t hi = (uint32_t)(stage[e] >> 32);
-			if (hi != REC_NULL_HI) atomicAdd(&s_hist[hi >> FINAL_LOG2], 1u);
+			if (cnt > CHUNK_REC) {
+				// a skewed group spans several chunks: clip the runs to the virtual range [cv0, cv1) of this one
+				uint32_t tot;
+				uint32_t vs = producer_exclusive_scan(n[0] + n[1] + n[2] + n[3], &tot, s_pw, pt);
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					const uint32_t lo = max(vs, cv0), hi = min(vs + n[q], cv1);
+					vs += n[q];
+					s0[q] += lo - (vs - n[q]);
+					n[q] = (lo < hi) ? hi - lo : 0u;
+				}
+			}
+			uint32_t span[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) span[q] = n[q] ? (((s0[q] & 1u) + n[q] + 1u) & ~1u) : 0u;
+			const uint32_t mine = span[0] + span[1] + span[2] + span[3];
+			uint32_t staged;
+			uint32_t so = producer_exclusive_scan(mine, &staged, s_pw, pt);
+			// the consumers must have left this buffer (they used it two units ago)
+			if (it >= 2) mbar_wait(&s_empty[buf], ((it >> 1) - 1u) & 1u);
+			uint4 own;
+			uint32_t sos[4];
+			sos[0] = so; sos[1] = sos[0] + span[0]; sos[2] = sos[1] + span[1]; sos[3] = sos[2] + span[2];
+			own.x = sos[0] | (n[0] << 14) | ((s0[0] & 1u) << 28);
+			own.y = sos[1] | (n[1] << 14) | ((s0[1] & 1u) << 28);
+			own.z = sos[2] | (n[2] << 14) | ((s0[2] & 1u) << 28);
+			own.w = sos[3] | (n[3] << 14) | ((s0[3] & 1u) << 28);
+			reinterpret_cast<uint4*>(s_own + buf * MAX_FAN)[pt] = own;
+			if (pt == 0) {
+				RegroupUnit U;
+				U.count = cv1 - cv0;
+				U.nci = c1 - c0; U.cl = u - c0; U.pad = 0;
+				U.rows = (unsigned long long)c0 * (F2 + 1);
+				U.out = out;
+				s_unit[buf] = U;
+				s_staged[buf] = staged;
+			}
+			// arrive (releases the stores above) and announce this thread's bytes, then start its copies
+			if (mine) mbar_arrive_expect_tx(&s_full[buf], mine * 8u); else mbar_arrive(&s_full[buf]);
+			uint64_t* stage = s_stage + (size_t)buf * STAGE_REC;
+			const uint64_t* src = P.rec1 + (uint64_t)(t0 + 4 * pt) * PT_REC;
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (n[q]) bulk_g2s(stage + sos[q], src + (uint64_t)q * PT_REC + (s0[q] - (s0[q] & 1u)), span[q] * 8u, &s_full[buf]);
 		}
-		__syncthreads();
-		block_exclusive_scan_512<RG_THREADS>(s_hist, F2, s_warp);
-		uint16_t* rows = P.offs2 + U.rows;
-		for (uint32_t j = tid; j < F2; j += RG_THREADS) {
-			const uint32_t s = s_hist[j];
-			s_cursor[j] = s;
-			rows[(uint64_t)j * U.nci + U.cl] = (uint16_t)s;
+	} else {
+		// ================================================================= consumer warps
+		const uint32_t ct = tid - RG_PRODUCERS;
+		uint32_t it = 0;
+		for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+			const uint32_t buf = it & 1u;
+			uint64_t* stage = s_stage + (size_t)buf * STAGE_REC;
+			mbar_wait(&s_full[buf], (it >> 1) & 1u);
+			{
+				const uint32_t own = s_own[buf * MAX_FAN + ct];
+				const uint32_t so = own & 0x3FFFu, n = (own >> 14) & 0x3FFFu, lead = own >> 28;
+				if (n) {
+					if (lead) stage[so] = REC_NULL;
+					if ((lead + n) & 1u) stage[so + lead + n] = REC_NULL;
+				}
+			}
+			for (uint32_t v = ct; v <= F2; v += RG_CONSUMERS) s_hist[v] = 0;
+			consumer_sync();
+			const RegroupUnit U = s_unit[buf];
+			const uint32_t staged = s_staged[buf];
+
+			// pass A: level-2 histogram, one record per lane
+			for (uint32_t e = ct; e < staged; e += RG_CONSUMERS) {
+				const uint32_t hi = (uint32_t)(stage[e] >> 32);
+				if (hi != REC_NULL_HI) atomicAdd(&s_hist[hi >> FINAL_LOG2], 1u);
+			}
+			consumer_sync();
+			consumer_exclusive_scan(s_hist, F2, s_warp, ct);
+			uint16_t* rows = P.offs2 + U.rows;
+			for (uint32_t j = ct; j < F2; j += RG_CONSUMERS) {
+				const uint32_t s = s_hist[j];
+				s_cursor[j] = s;
+				rows[(uint64_t)j * U.nci + U.cl] = (uint16_t)s;
+			}
+			if (ct == 0) {
+				rows[(uint64_t)F2 * U.nci + U.cl] = (uint16_t)U.count;
+				bulk_wait_read();             // the previous chunk has left s_sorted
+			}
+			consumer_sync();
+			// pass B: counting-sort scatter
+			for (uint32_t e = ct; e < staged; e += RG_CONSUMERS) {
+				const uint64_t rec = stage[e];
+				const uint32_t hi = (uint32_t)(rec >> 32);
+				if (hi != REC_NULL_HI) s_sorted[atomicAdd(&s_cursor[hi >> FINAL_LOG2], 1u)] = rec;
+			}
+			fence_async_smem();               // staging reads/stores and s_sorted stores before the async proxy touches either
+			consumer_sync();
+			if (lane == 0) mbar_arrive(&s_empty[buf]);
+			if (ct == 0) bulk_s2g(P.rec2 + U.out, s_sorted, ((U.count + 1u) & ~1u) * 8u);
 		}
-		if (tid == 0) {
-			rows[(uint64_t)F2 * U.nci + U.cl] = (uint16_t)U.count;
-			bulk_wait_read();             // the previous chunk has left s_sorted
-		}
-		__syncthreads();
-		// pass B: counting-sort scatter
-		for (uint32_t e = tid; e < U.staged; e += RG_THREADS) {
-			const uint64_t rec = stage[e];
-			const uint32_t hi = (uint32_t)(rec >> 32);
-			if (hi != REC_NULL_HI) s_sorted[atomicAdd(&s_cursor[hi >> FINAL_LOG2], 1u)] = rec;
-		}
-		fence_async_smem();
-		__syncthreads();
-		if (tid == 0) bulk_s2g(P.rec2 + U.out, s_sorted, ((U.count + 1u) & ~1u) * 8u);
+		if (ct == 0) bulk_wait_all();
 	}
-	if (tid == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------ K3
