@@ -219,6 +219,11 @@ struct kwg_bloom {
 	uint64_t* d_chunk_rec = nullptr; size_t chunk_rec_cap = 0;
 	uint4* d_chunk_meta = nullptr; size_t chunk_meta_cap = 0;
 	uint32_t* d_cfirst = nullptr; size_t cfirst_cap = 0;
+	unsigned long long* d_tot_rec = nullptr; size_t tot_rec_cap = 0;
+	uint32_t* d_tot_chk = nullptr; size_t tot_chk_cap = 0;
+	// host feed: bases stream in on a copy stream while the partition scan already runs on what has arrived
+	cudaStream_t copy_stream = nullptr;
+	std::vector<cudaEvent_t> feed_events;
 	uint32_t* d_loss = nullptr;  size_t loss_cap = 0;
 	// both modes
 	unsigned long long* d_counter = nullptr;
@@ -326,7 +331,11 @@ static int count_kernels_init()
 
 // One sub-batch of the counting construction: start positions [pos0, pos0 + n_pos) of the batch in S.
 // partition (K1) -> [regroup (K2)] -> resolve (K3) -> pass B (valid-word list).
-static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos)
+// h_feed != NULL: the bases of this (single) sub-batch are still on the host at h_feed; they are copied in
+// FEED_CHUNK pieces on the copy stream and the partition scan is launched piece by piece behind them.
+constexpr size_t FEED_CHUNK = 16u << 20;
+
+static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const char* h_feed)
 {
 	const CountGeom& G = b->geom;
 	const uint32_t F1 = 1u << G.f1_log2, F2 = 1u << G.f2_log2;
@@ -357,10 +366,39 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	K1.ntp = ntp;
 	K1.rec1 = b->d_rec1;
 	K1.offs1 = b->d_offs1;
+	K1.tile0 = 0;
 	b->timers.begin(KWG_T_SCAN_A, b->stream);
-	partition_scan_kernel<<<(unsigned)n_tiles, PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
+	if (!h_feed) {
+		partition_scan_kernel<<<(unsigned)n_tiles, PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
+		KWG_LAUNCHED();
+	} else {
+		if (!b->copy_stream) KWG_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+		const size_t n_chunks = (size_t)ceil_div(S.n_bases, FEED_CHUNK);
+		while (b->feed_events.size() < n_chunks + 1) {
+			cudaEvent_t e;
+			KWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			b->feed_events.push_back(e);
+		}
+		// the staging buffer may still be read by work queued earlier on the compute stream
+		KWG_CUDA(cudaEventRecord(b->feed_events[n_chunks], b->stream));
+		KWG_CUDA(cudaStreamWaitEvent(b->copy_stream, b->feed_events[n_chunks], 0));
+		uint64_t t_done = 0;
+		for (size_t c = 0; c < n_chunks; ++c) {
+			const size_t off = c * FEED_CHUNK, len = std::min<size_t>(FEED_CHUNK, (size_t)S.n_bases - off);
+			KWG_CUDA(cudaMemcpyAsync(const_cast<char*>(S.bases) + off, h_feed + off, len, cudaMemcpyHostToDevice, b->copy_stream));
+			KWG_CUDA(cudaEventRecord(b->feed_events[c], b->copy_stream));
+			KWG_CUDA(cudaStreamWaitEvent(b->stream, b->feed_events[c], 0));
+			// a tile reads PT_LOAD bases from its first position
+			const uint64_t t_end = (c + 1 == n_chunks) ? n_tiles : std::min<uint64_t>(n_tiles, (off + len >= (size_t)PT_LOAD) ? (off + len - PT_LOAD) / PT_POS + 1 : 0);
+			if (t_end > t_done) {
+				K1.tile0 = (uint32_t)t_done;
+				partition_scan_kernel<<<(unsigned)(t_end - t_done), PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
+				KWG_LAUNCHED();
+				t_done = t_end;
+			}
+		}
+	}
 	b->timers.end(b->stream);
-	KWG_LAUNCHED();
 
 	ResolveParams K3{};
 	K3.n_buckets = 1u << G.nb_log2;
@@ -385,6 +423,8 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		if ((rc = grow((void**)&b->d_base2, &b->base2_cap, n_pairs * sizeof(uint64_t)))) return rc;
 		if ((rc = grow((void**)&b->d_cbase, &b->cbase_cap, n_pairs * sizeof(uint32_t)))) return rc;
 		if ((rc = grow((void**)&b->d_cfirst, &b->cfirst_cap, (size_t)(F1 + 1) * sizeof(uint32_t)))) return rc;
+		if ((rc = grow((void**)&b->d_tot_rec, &b->tot_rec_cap, (size_t)F1 * sizeof(unsigned long long)))) return rc;
+		if ((rc = grow((void**)&b->d_tot_chk, &b->tot_chk_cap, (size_t)F1 * sizeof(uint32_t)))) return rc;
 		if ((rc = grow((void**)&b->d_chunk_rec, &b->chunk_rec_cap, max_chunks * sizeof(uint64_t)))) return rc;
 		if ((rc = grow((void**)&b->d_chunk_meta, &b->chunk_meta_cap, max_chunks * sizeof(uint4)))) return rc;
 		if ((rc = grow((void**)&b->d_offs2, &b->offs2_cap, max_chunks * (F2 + 1) * sizeof(uint16_t)))) return rc;
@@ -393,7 +433,10 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		b->timers.begin(KWG_T_REGROUP, b->stream);
 		group_count_kernel<<<(unsigned)ceil_div(n_pairs, 8), 256, 0, b->stream>>>(b->d_offs1, ntp, (uint32_t)n_tiles, F1, G1, NG, b->d_cnt1);
 		KWG_LAUNCHED();
-		group_prefix_kernel<<<1, 1024, 0, b->stream>>>(b->d_cnt1, (uint32_t)n_pairs, NG, F1, b->d_base2, b->d_cbase, b->d_chunk_rec, b->d_chunk_meta, b->d_cfirst);
+		group_scan_kernel<<<F1, GS_THREADS, 0, b->stream>>>(b->d_cnt1, NG, b->d_base2, b->d_cbase, b->d_tot_rec, b->d_tot_chk);
+		KWG_LAUNCHED();
+		group_finish_kernel<<<F1, GS_THREADS, 0, b->stream>>>(b->d_cnt1, NG, F1, b->d_tot_rec, b->d_tot_chk, b->d_base2, b->d_cbase,
+			b->d_chunk_rec, b->d_chunk_meta, b->d_cfirst);
 		KWG_LAUNCHED();
 		RegroupParams K2{};
 		K2.rec1 = b->d_rec1; K2.offs1 = b->d_offs1; K2.ntp = ntp; K2.n_tiles = (uint32_t)n_tiles;
@@ -434,7 +477,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 // All inputs on the device: d_bases (16-byte aligned), d_offsets[n_reads+1] with offsets relative
 // to off0.  n_bases < 2^32 - 2.
 static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
-	uint64_t off0, uint64_t n_bases)
+	uint64_t off0, uint64_t n_bases, const char* h_feed = nullptr)
 {
 	if (n_bases == 0 || n_reads == 0) return KWG_OK;
 	if (n_bases >= 0xFFFFFFF0ull) return fail(KWG_ERR_INVALID_ARG, "a device batch must hold fewer than 2^32-16 bases");
@@ -467,7 +510,7 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	// counting mode: sub-batches of at most 2^28 start positions (a record carries a 28-bit position)
 	for (uint64_t pos0 = 0; pos0 < n_bases; pos0 += MAX_COUNT_POS) {
 		const uint64_t n_pos = std::min<uint64_t>(MAX_COUNT_POS, n_bases - pos0);
-		rc = count_sub_batch(b, P, pos0, n_pos);
+		rc = count_sub_batch(b, P, pos0, n_pos, (n_bases <= MAX_COUNT_POS) ? h_feed : nullptr);
 		if (rc) return rc;
 	}
 	return KWG_OK;
@@ -498,7 +541,9 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_touched);
 	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
 	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_meta);
-	cudaFree(b->d_cfirst); cudaFree(b->d_loss);
+	cudaFree(b->d_cfirst); cudaFree(b->d_loss); cudaFree(b->d_tot_rec); cudaFree(b->d_tot_chk);
+	for (cudaEvent_t e : b->feed_events) cudaEventDestroy(e);
+	if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
 	for (uint64_t* c : b->chunks) cudaFree(c);
 	cudaFree(b->d_chunk_table);
 	cudaFree(b->d_counter);
@@ -597,14 +642,22 @@ int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offse
 	if (!bases || !offsets) return fail(KWG_ERR_INVALID_ARG, "NULL input");
 	int rc = select_device(b->device);
 	if (rc) return rc;
-	for (uint64_t r = 0; r < n_reads; ++r)
-		if (offsets[r + 1] < offsets[r]) return fail(KWG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+	{
+		uint64_t bad = 0;                      // branch-free so that the compiler vectorises the scan
+		for (uint64_t r = 0; r < n_reads; ++r) bad |= (uint64_t)(offsets[r + 1] < offsets[r]);
+		if (bad) return fail(KWG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+	}
 
 	uint64_t r0 = 0;
 	while (r0 < n_reads) {
 		// cut a batch of whole reads of at most MAX_BATCH_BASES bases (at least one read)
-		uint64_t r1 = r0 + 1;
-		while (r1 < n_reads && offsets[r1 + 1] - offsets[r0] <= MAX_BATCH_BASES) ++r1;
+		uint64_t r1;
+		if (offsets[n_reads] - offsets[r0] <= MAX_BATCH_BASES) {
+			r1 = n_reads;
+		} else {
+			r1 = (uint64_t)(std::upper_bound(offsets + r0 + 1, offsets + n_reads + 1, offsets[r0] + MAX_BATCH_BASES) - offsets) - 1;
+			if (r1 <= r0) r1 = r0 + 1;
+		}
 		const uint64_t off0 = offsets[r0];
 		const uint64_t nb = offsets[r1] - off0;
 		if (nb >= 0xFFFFFFF0ull) return fail(KWG_ERR_INVALID_ARG, "a single read of 2^32 bases or more is not supported");
@@ -613,9 +666,10 @@ int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offse
 			if (rc) return rc;
 			rc = grow((void**)&b->d_offsets, &b->offsets_cap, (r1 - r0 + 1) * sizeof(uint64_t));
 			if (rc) return rc;
-			KWG_CUDA(cudaMemcpyAsync(b->d_bases, bases + off0, nb, cudaMemcpyHostToDevice, b->stream));
 			KWG_CUDA(cudaMemcpyAsync(b->d_offsets, offsets + r0, (r1 - r0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
-			rc = add_batch_dev(b, b->d_bases, b->d_offsets, r1 - r0, off0, nb);
+			const bool feed = !b->raw && nb <= MAX_COUNT_POS && nb > FEED_CHUNK;
+			if (!feed) KWG_CUDA(cudaMemcpyAsync(b->d_bases, bases + off0, nb, cudaMemcpyHostToDevice, b->stream));
+			rc = add_batch_dev(b, b->d_bases, b->d_offsets, r1 - r0, off0, nb, feed ? bases + off0 : nullptr);
 			if (rc) return rc;
 		}
 		r0 = r1;

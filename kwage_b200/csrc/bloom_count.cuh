@@ -79,6 +79,7 @@ struct PartParams {
 	uint32_t shift1;             // FINAL_LOG2 + f2_log2: record keeps the slot bits below this
 	uint32_t table_shift;        // f1_log2 - 1: where the table index (0: first, 1: second) lands in the level-1 bucket
 	uint32_t ntp;                // row pitch of offs1 (tiles, padded)
+	uint32_t tile0;              // first tile of this launch (the scan may be launched in pieces while the bases stream in)
 	uint64_t* rec1;              // [n_tiles][PT_REC]
 	uint16_t* offs1;             // [(F1+1)][ntp]: start of bucket b inside the sorted tile; row F1 = record count
 };
@@ -132,7 +133,7 @@ partition_scan_kernel(const PartParams P)
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t k = P.k;
-	const uint64_t tile = blockIdx.x;
+	const uint64_t tile = (uint64_t)blockIdx.x + P.tile0;
 	const uint64_t rel0 = tile * PT_POS;               // sub-batch relative position of the tile
 	const uint64_t t0 = P.pos0 + rel0;                 // absolute base index
 	const uint32_t F1 = 1u << P.f1_log2;
@@ -238,52 +239,86 @@ group_count_kernel(const uint16_t* __restrict__ offs1, uint32_t ntp, uint32_t n_
 	if (lane == 0) cnt1[idx] = sum;
 }
 
-// Exclusive prefix sums over the F1*NG (bucket-major) group counts: record base of every group (kept
-// even so that every chunk starts 16-byte aligned for the bulk stores), id of its first chunk, record
-// base and description of every chunk, first chunk of every level-1 bucket.  One block.
-__global__ void __launch_bounds__(1024)
-group_prefix_kernel(const uint32_t* __restrict__ cnt1, uint32_t n, uint32_t NG, uint32_t F1,
-	uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase, uint64_t* __restrict__ chunk_rec, uint4* __restrict__ chunk_meta,
-	uint32_t* __restrict__ cfirst)
+// Exclusive prefix sums over the F1*NG (bucket-major) group counts, in two small kernels of F1 blocks:
+//   group_scan_kernel   block i: prefix over the groups of bucket i (records rounded up to even so that every
+//                       chunk starts 16-byte aligned for the bulk stores; chunks = ceil(records / CHUNK_REC))
+//                       -> local prefixes in base2/cbase, bucket totals in tot_rec/tot_chk
+//   group_finish_kernel block i: adds the totals of the buckets before it, writes the record base and the
+//                       description of every chunk and the first chunk of every level-1 bucket
+constexpr int GS_THREADS = 256;
+
+__global__ void __launch_bounds__(GS_THREADS)
+group_scan_kernel(const uint32_t* __restrict__ cnt1, uint32_t NG, uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase,
+	unsigned long long* __restrict__ tot_rec, uint32_t* __restrict__ tot_chk)
 {
-	__shared__ unsigned long long s_rec[32];
-	__shared__ uint32_t s_chk[32];
-	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t per = (n + 1023) / 1024;
-	const uint32_t a = min(tid * per, n), b = min(a + per, n);
-	unsigned long long rsum = 0;
-	uint32_t csum = 0;
-	for (uint32_t x = a; x < b; ++x) { const uint32_t c = cnt1[x]; rsum += (c + 1u) & ~1u; csum += (c + CHUNK_REC - 1) / CHUNK_REC; }
-	unsigned long long rinc = rsum;
-	uint32_t cinc = csum;
-	for (int o = 1; o < 32; o <<= 1) {
-		const unsigned long long ry = __shfl_up_sync(0xFFFFFFFFu, rinc, o);
-		const uint32_t cy = __shfl_up_sync(0xFFFFFFFFu, cinc, o);
-		if (lane >= (uint32_t)o) { rinc += ry; cinc += cy; }
+	__shared__ uint32_t s_r[GS_THREADS / 32], s_c[GS_THREADS / 32];
+	const uint32_t i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned long long rcarry = 0;
+	uint32_t ccarry = 0;
+	for (uint32_t g0 = 0; g0 < NG; g0 += GS_THREADS) {
+		const uint32_t g = g0 + tid;
+		const uint32_t c = (g < NG) ? cnt1[(uint64_t)i * NG + g] : 0u;
+		const uint32_t r = (c + 1u) & ~1u, k = (c + CHUNK_REC - 1) / CHUNK_REC;
+		uint32_t rinc = r, cinc = k;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t ry = __shfl_up_sync(0xFFFFFFFFu, rinc, o), cy = __shfl_up_sync(0xFFFFFFFFu, cinc, o);
+			if (lane >= (uint32_t)o) { rinc += ry; cinc += cy; }
+		}
+		__syncthreads();
+		if (lane == 31) { s_r[warp] = rinc; s_c[warp] = cinc; }
+		__syncthreads();
+		uint32_t rb = 0, cb = 0, rt = 0, ctot = 0;
+#pragma unroll
+		for (int w = 0; w < GS_THREADS / 32; ++w) {
+			if ((uint32_t)w < warp) { rb += s_r[w]; cb += s_c[w]; }
+			rt += s_r[w]; ctot += s_c[w];
+		}
+		if (g < NG) {
+			base2[(uint64_t)i * NG + g] = rcarry + rb + rinc - r;
+			cbase[(uint64_t)i * NG + g] = ccarry + cb + cinc - k;
+		}
+		rcarry += rt; ccarry += ctot;
 	}
-	if (lane == 31) { s_rec[warp] = rinc; s_chk[warp] = cinc; }
+	if (tid == 0) { tot_rec[i] = rcarry; tot_chk[i] = ccarry; }
+}
+
+__global__ void __launch_bounds__(GS_THREADS)
+group_finish_kernel(const uint32_t* __restrict__ cnt1, uint32_t NG, uint32_t F1, const unsigned long long* __restrict__ tot_rec,
+	const uint32_t* __restrict__ tot_chk, uint64_t* __restrict__ base2, uint32_t* __restrict__ cbase, uint64_t* __restrict__ chunk_rec,
+	uint4* __restrict__ chunk_meta, uint32_t* __restrict__ cfirst)
+{
+	__shared__ unsigned long long s_r[GS_THREADS / 32];
+	__shared__ uint32_t s_c[GS_THREADS / 32];
+	const uint32_t i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned long long r = 0;
+	uint32_t c = 0;
+	for (uint32_t x = tid; x < i; x += GS_THREADS) { r += tot_rec[x]; c += tot_chk[x]; }
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, o); c += __shfl_xor_sync(0xFFFFFFFFu, c, o); }
+	if (lane == 0) { s_r[warp] = r; s_c[warp] = c; }
 	__syncthreads();
-	unsigned long long rbase = 0;
-	uint32_t cb = 0, ctotal = 0;
-	for (uint32_t w = 0; w < 32; ++w) {
-		if (w < warp) { rbase += s_rec[w]; cb += s_chk[w]; }
-		ctotal += s_chk[w];
+	unsigned long long roff = 0;
+	uint32_t coff = 0;
+#pragma unroll
+	for (int w = 0; w < GS_THREADS / 32; ++w) { roff += s_r[w]; coff += s_c[w]; }
+	if (tid == 0) {
+		cfirst[i] = coff;
+		if (i + 1 == F1) cfirst[F1] = coff + tot_chk[i];
 	}
-	unsigned long long r = rbase + rinc - rsum;
-	uint32_t c = cb + cinc - csum;
-	for (uint32_t x = a; x < b; ++x) {
+	for (uint32_t g = tid; g < NG; g += GS_THREADS) {
+		const uint64_t x = (uint64_t)i * NG + g;
 		const uint32_t cnt = cnt1[x];
-		base2[x] = r;
-		cbase[x] = c;
-		if (x % NG == 0) cfirst[x / NG] = c;
+		const unsigned long long rb = roff + base2[x];
+		const uint32_t cb = coff + cbase[x];
+		base2[x] = rb;
+		cbase[x] = cb;
 		const uint32_t nc = (cnt + CHUNK_REC - 1) / CHUNK_REC;
 		for (uint32_t q = 0; q < nc; ++q) {
-			chunk_rec[c + q] = r + (unsigned long long)q * CHUNK_REC;
-			chunk_meta[c + q] = make_uint4(((x / NG) << 16) | (x % NG), cnt, q, 0u);     // (bucket i, group g), records of the pair, chunk within the pair
+			chunk_rec[cb + q] = rb + (unsigned long long)q * CHUNK_REC;
+			chunk_meta[cb + q] = make_uint4((i << 16) | g, cnt, q, 0u);     // (bucket i, group g), records of the pair, chunk within the pair
 		}
-		r += (cnt + 1u) & ~1u; c += nc;
 	}
-	if (tid == 0) cfirst[F1] = ctotal;
 }
 
 // ------------------------------------------------------------------------------------------ async-copy plumbing
