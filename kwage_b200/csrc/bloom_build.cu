@@ -221,6 +221,8 @@ struct kwg_bloom {
 	uint32_t* d_cfirst = nullptr; size_t cfirst_cap = 0;
 	unsigned long long* d_tot_rec = nullptr; size_t tot_rec_cap = 0;
 	uint32_t* d_tot_chk = nullptr; size_t tot_chk_cap = 0;
+	uint64_t n_valid_host = 0;           // last value read from d_counter (saves a device round trip in finalize)
+	bool n_valid_known = false;
 	// host feed: bases stream in on a copy stream while the partition scan already runs on what has arrived
 	cudaStream_t copy_stream = nullptr;
 	std::vector<cudaEvent_t> feed_events;
@@ -253,9 +255,12 @@ static int grow(void** p, size_t* cap, size_t need)
 
 static int read_counter(kwg_bloom* b, uint64_t* out)
 {
+	if (b->n_valid_known) { *out = b->n_valid_host; return KWG_OK; }
 	KWG_CUDA(cudaMemcpyAsync(b->h_counter, b->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
 	KWG_CUDA(cudaStreamSynchronize(b->stream));
 	*out = *b->h_counter;
+	b->n_valid_host = *out;
+	b->n_valid_known = true;
 	return KWG_OK;
 }
 
@@ -465,6 +470,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	KWG_LAUNCHED();
 
 	b->touched_dirty = true;
+	b->n_valid_known = false;
 
 	ScanParams P = S;
 	P.pos0 = pos0;
@@ -481,6 +487,7 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 {
 	if (n_bases == 0 || n_reads == 0) return KWG_OK;
 	if (n_bases >= 0xFFFFFFF0ull) return fail(KWG_ERR_INVALID_ARG, "a device batch must hold fewer than 2^32-16 bases");
+	if (b->raw) b->n_valid_known = false;      // (counting mode invalidates after it has read the counter, below)
 	if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) != 0) return fail(KWG_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
 
 	const size_t start_words = (size_t)(n_bases / 32 + 2);
@@ -617,6 +624,8 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 	int rc = select_device(b->device);
 	if (rc) return rc;
 	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(unsigned long long), b->stream));
+	b->n_valid_host = 0;
+	b->n_valid_known = true;
 	if (b->raw) {
 		KWG_CUDA(cudaMemsetAsync(b->d_filter, 0, (size_t)1 << (b->raw_L - 3), b->stream));
 	} else {
