@@ -28,9 +28,6 @@
 // duplication (poly-G reads, adapters) only makes one bucket longer, never overflows anything.
 #pragma once
 #include "common.cuh"
-#ifdef KWG_DEBUG_RESOLVE
-#include <cstdio>
-#endif
 
 namespace kwg {
 
@@ -353,11 +350,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
 {
 	const uint32_t addr = smem_u32(bar);
-	for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+	for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
 		uint32_t done;
 		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 		             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
 		if (done) return;
+		__nanosleep(spin < 8 ? 32 : 256);       // waiting warps must not crowd the issue slots of the working ones
 	}
 	__trap();
 }
@@ -734,9 +732,6 @@ resolve_kernel(const ResolveParams P)
 	uint32_t* s_warp = s_len + RS_THREADS;                                              // 32
 	uint32_t* s_misc = s_warp + 32;                                                     // [0] long runs, [1] staged extent of the round
 	uint16_t* s_long = reinterpret_cast<uint16_t*>(s_misc + 2);                         // RS_THREADS: indices of the long runs
-#ifdef KWG_DEBUG_RESOLVE
-	__shared__ uint32_t s_dbg[2];
-#endif
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t F2 = 1u << P.f2_log2;
@@ -839,26 +834,13 @@ resolve_kernel(const ResolveParams P)
 				}
 				__syncthreads();
 				const uint32_t extent = s_misc[1];
-#ifdef KWG_DEBUG_RESOLVE
-				if (tid == 0) { s_dbg[0] = 0; s_dbg[1] = 0; }
-				__syncthreads();
-				if (mine) atomicAdd(&s_dbg[1], my_len);
-#endif
 				for (uint32_t e = tid; e < extent; e += RS_THREADS) {
 					const uint64_t rec = s_stage[e];
 					if ((uint32_t)(rec >> 32) != REC_NULL_HI) {
 						resolve_record(s_tile, s_bm, P.loss, rec);
-#ifdef KWG_DEBUG_RESOLVE
-						atomicAdd(&s_dbg[0], 1u);
-#endif
 					}
 				}
 				__syncthreads();
-#ifdef KWG_DEBUG_RESOLVE
-				if (tid == 0 && s_dbg[0] != s_dbg[1])
-					printf("resolve mismatch: bucket %u cb %u r0 %u staged %u extent %u processed %u expected %u\n", b, cb, r0, staged, extent, s_dbg[0], s_dbg[1]);
-				__syncthreads();
-#endif
 			}
 			// long runs (heavy duplication): one warp per run straight from global memory
 			const uint32_t nlong = s_misc[0];
