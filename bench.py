@@ -42,6 +42,15 @@ def env_int(name, default):
         return default
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the
+# default workload (profiles/r1c_ncu_full_*.md); reported as roofline.traffic when the workload matches
+NCU_TRAFFIC = {
+    "partition_scan": 3.987e9, "regroup": 7.728e9, "resolve": 6.529e9, "scan_pass_b": 1.147e9, "insert_words": 4.995e9,
+    "transpose_kernel": 6.868e10, "search_count_kernel": 3.018e10,
+}
+NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_construct.md, profiles/r1c_ncu_full_transpose_search.md, profiles/r1a_ncu_full.md (search)"
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -268,7 +277,9 @@ def stage_construct(D, args, windows):
                 "d2h_bytes_per_step": (1 << state["L"]) // 8 + 8, "ms_per_step": sec_e2e / args.steps * 1e3},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC.get(dom) if n_reads == 1000000 else None, "traffic_source": NCU_TRAFFIC_SOURCE,
+                     "algorithmic_bytes": kmers * per_kernel[dom]["algorithmic_bytes_per_kmer"], "peak_source": peak_src,
                      "algorithmic_bytes_per_kmer": per_kernel[dom]["algorithmic_bytes_per_kmer"],
                      "kernel_ms": per_kernel[dom]["ms_per_step"], "share_of_step": per_kernel[dom]["ms_per_step"] / step_ms,
                      "pipeline_algorithmic_bytes_per_kmer": round(sum(v[2] for v in alg.values()), 2),
@@ -334,7 +345,8 @@ def stage_transpose(D, args, windows):
             "e2e": {"value": n * nf * cbits * 2 / sec_e2e, "unit": "bits/s", "h2d_bytes_per_step": nf * cbits // 8, "d2h_bytes_per_step": nf * cbits // 8,
                     "workload": "kwg_transpose, 2048 filters x 2^22 slices per call (the reference's chunk)"},
             "roofline": {"bound": "hbm", "kernel": "transpose_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src},
+                         "traffic": NCU_TRAFFIC["transpose_kernel"] if (n_filters, L) == (4096, 26) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "algorithmic_bytes": 2 * bits // 8, "peak_source": peak_src},
             "gpu_launches": int(capi.launch_count() - launches0)}
 
 
@@ -408,7 +420,8 @@ def stage_search(D, args, windows):
             "e2e": {"value": n * tests * steps / sec_e2e, "unit": "tests/s", "h2d_bytes_per_step": nq * qlen + 8 * (nq + 1), "d2h_bytes_per_step": 12 * n_hits[0] + 4 * nq,
                     "threshold": 0.5, "hits": n_hits[0]},
             "roofline": {"bound": "hbm", "kernel": "search_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": t_k * 1e3, "share_of_step": t_k * 1e3 / (sec / steps * 1e3),
+                         "traffic": NCU_TRAFFIC["search_count_kernel"] if (F, L, nq, qlen) == (8192, 26, 10000, 1000) else None,
+                         "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": t_k * 1e3, "share_of_step": t_k * 1e3 / (sec / steps * 1e3),
                          "algorithmic_bytes": alg_bytes},
             "kernel_ms_per_step": {"query_kmers": float(ms[capi.T_AUX]) / steps, "search_count": float(ms[capi.T_SEARCH]) / steps},
             "gpu_launches": int(launches)}
