@@ -26,13 +26,8 @@ constexpr int QK_THREADS = 128;
 // ------------------------------------------------------------------------------------------
 // query -> unique canonical k-mers -> row indices
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t base_code(uint32_t ch)   // 0..3, or 4 for anything else (word.h:80-101)
-{
-	const uint32_t u = ch & 0xDFu;
-	const uint32_t x = (ch >> 1) & 3u;
-	const uint32_t c = x ^ (x >> 1);
-	return (u == 'A' || u == 'C' || u == 'G' || u == 'T') ? c : 4u;
-}
+constexpr int QK_TILE = 2048;                       // k-mer start positions per staged tile
+constexpr int QK_LOAD = QK_TILE + 32;               // bytes staged per tile (halo >= k - 1)
 
 template <int NH>
 __global__ void __launch_bounds__(QK_THREADS)
@@ -42,7 +37,15 @@ query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ 
 	uint32_t* __restrict__ rows,        // row indices at rows[(o0 + i) * NH + h]
 	uint32_t* __restrict__ n_kmers)     // per query, zero-initialised
 {
-	const uint32_t q = blockIdx.x;
+	// same front end as the construction kernels: the tile is staged once, 16 bases at a time become 32 bits
+	// of 2-bit codes + 16 "not ACGT" flags (encode16), and every start position extracts its window from
+	// shared memory (no per-position byte loop)
+	__shared__ __align__(16) uint8_t s_bytes[QK_LOAD];
+	__shared__ uint32_t s_codes[QK_LOAD / 16 + 2];
+	__shared__ uint32_t s_bad[QK_LOAD / 32 + 2];
+	__shared__ uint32_t s_nostart[QK_LOAD / 32 + 2];
+
+	const uint32_t q = blockIdx.x, tid = threadIdx.x;
 	const uint64_t o0 = offsets[q] - offsets[0], o1 = offsets[q + 1] - offsets[0];
 	const uint64_t len = o1 - o0;
 	if (len < k) return;
@@ -50,31 +53,42 @@ query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ 
 	const uint64_t tsize = 2 * len;
 	uint64_t* tab = table + 2 * o0;
 	const char* s = bases + o0;
+	for (uint32_t v = tid; v < (uint32_t)(QK_LOAD / 32 + 2); v += QK_THREADS) s_nostart[v] = 0u;
 
-	for (uint64_t p = (uint64_t)blockIdx.y * QK_THREADS + threadIdx.x; p < n_pos; p += (uint64_t)gridDim.y * QK_THREADS) {
-		uint64_t sense = 0;
-		bool ok = true;
-		for (uint32_t j = 0; j < k; ++j) {
-			const uint32_t c = base_code((uint8_t)s[p + j]);
-			ok = ok && (c < 4u);
-			sense = (sense << 2) | (c & 3u);
+	for (uint64_t tile0 = (uint64_t)blockIdx.y * QK_TILE; tile0 < n_pos; tile0 += (uint64_t)gridDim.y * QK_TILE) {
+		__syncthreads();                                    // previous tile's readers are done
+		const uint64_t avail = len - tile0;
+		for (uint32_t i = tid; i < (uint32_t)QK_LOAD; i += QK_THREADS) s_bytes[i] = (i < avail) ? (uint8_t)s[tile0 + i] : (uint8_t)'N';
+		__syncthreads();
+		for (uint32_t v = tid; v < (uint32_t)(QK_LOAD / 16); v += QK_THREADS) {
+			uint32_t codes, bad16;
+			encode16(*reinterpret_cast<const uint4*>(s_bytes + 16 * v), codes, bad16);
+			s_codes[v] = codes;
+			reinterpret_cast<uint16_t*>(s_bad)[v] = (uint16_t)bad16;
 		}
-		if (!ok) continue;
-		const Canon c = canonical(sense, k);
-		uint64_t slot = mix64(c.word) % tsize;
-		for (;;) {
-			const unsigned long long old = atomicCAS((unsigned long long*)(tab + slot), (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
-			if (old == SET_EMPTY) {
-				const uint32_t i = atomicAdd(n_kmers + q, 1u);
-				kmers[o0 + i] = c.word;
-				uint32_t h[NH];
-				murmur3_multi<NH>(c.low, k, h);
+		if (tid == 0) {
+			s_codes[QK_LOAD / 16] = 0; s_codes[QK_LOAD / 16 + 1] = 0;
+			s_bad[QK_LOAD / 32] = 0xFFFFFFFFu; s_bad[QK_LOAD / 32 + 1] = 0xFFFFFFFFu;
+		}
+		__syncthreads();
+		for (uint32_t p = tid; p < (uint32_t)QK_TILE && tile0 + p < n_pos; p += QK_THREADS) {
+			if (!window_ok(s_bad, s_nostart, p, k)) continue;
+			const Canon c = canonical(window_sense(s_codes, p, k), k);
+			uint64_t slot = mix64(c.word) % tsize;
+			for (;;) {
+				const unsigned long long old = atomicCAS((unsigned long long*)(tab + slot), (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
+				if (old == SET_EMPTY) {
+					const uint32_t i = atomicAdd(n_kmers + q, 1u);
+					kmers[o0 + i] = c.word;
+					uint32_t h[NH];
+					murmur3_multi<NH>(c.low, k, h);
 #pragma unroll
-				for (int t = 0; t < NH; ++t) rows[(o0 + i) * NH + t] = h[t] & filter_mask;
-				break;
+					for (int t = 0; t < NH; ++t) rows[(o0 + i) * NH + t] = h[t] & filter_mask;
+					break;
+				}
+				if (old == c.word) break;
+				slot = (slot + 1 == tsize) ? 0 : slot + 1;
 			}
-			if (old == c.word) break;
-			slot = (slot + 1 == tsize) ? 0 : slot + 1;
 		}
 	}
 }
@@ -105,7 +119,7 @@ struct SearchParams {
 };
 
 template <int NH>
-__global__ void __launch_bounds__(SC_THREADS, 2)
+__global__ void __launch_bounds__(SC_THREADS, 4)
 search_count_kernel(const SearchParams P)
 {
 	extern __shared__ uint32_t sm_planes[];   // [substream][plane][lanes_per_row * 4]
@@ -327,7 +341,10 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	KWG_CUDA(cudaMemsetAsync(d_nk, 0, (size_t)n_queries * sizeof(uint32_t), db->stream));
 
 	const uint32_t filter_mask = (db->log2_len >= 32) ? 0xFFFFFFFFu : ((1u << db->log2_len) - 1u);
-	const uint32_t parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ceil_div(max_query_len, 8 * QK_THREADS), 1), 256);
+	// blockIdx.y strides over the tiles of a query: a performance knob only (any query length is covered by the
+	// kernel's loop).  The device entry point does not know the longest query: assume at most 4x the average.
+	const uint64_t len_bound = std::min<uint64_t>(max_query_len, 4 * ceil_div(std::max<uint64_t>(n_bases, 1), std::max<uint32_t>(n_queries, 1)));
+	const uint32_t parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ceil_div(len_bound, QK_TILE), 1), 256);
 	const dim3 qgrid(n_queries, parts);
 	db->timers.begin(KWG_T_AUX, db->stream);
 	switch (db->num_hash) {
