@@ -364,6 +364,12 @@ def stage_search(D, args, windows):
     d_q = torch.empty(nq * qlen + 16, dtype=torch.uint8, device="cuda")
     d_qo = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
     capi.synth_reads_dev(4242, 0, nq, qlen, d_q.data_ptr(), d_qo.data_ptr(), device=dev)     # same queries on every rank
+    # known positives: every 10th query carries PLANT bp whose k-mers are inserted into three columns of the slab
+    PLANT, plant_cols = 600, sorted({0, 4097 % F, F - 1})
+    n_planted = (nq + 9) // 10
+    torch.cuda.synchronize()
+    for c in plant_cols:
+        capi.synth_plant_dev(slab.data_ptr(), row_pitch, K, h, L, c, d_q.data_ptr(), d_qo.data_ptr(), 0, 10, n_planted, PLANT, device=dev)
     count_pitch = (F + 3) // 4 * 4
     d_counts = torch.empty(nq * count_pitch, dtype=torch.int32, device="cuda")
     d_nk = torch.empty(nq, dtype=torch.int32, device="cuda")
@@ -418,7 +424,8 @@ def stage_search(D, args, windows):
             "config": {"filters_per_gpu": F, "log2_filter_len": L, "num_hash": h, "queries": nq, "query_len": qlen, "slab_bytes": (1 << L) * row_pitch,
                        "unique_query_kmers": n_kmers},
             "e2e": {"value": n * tests * steps / sec_e2e, "unit": "tests/s", "h2d_bytes_per_step": nq * qlen + 8 * (nq + 1), "d2h_bytes_per_step": 12 * n_hits[0] + 4 * nq,
-                    "threshold": 0.5, "hits": n_hits[0]},
+                    "threshold": 0.5, "hits": n_hits[0], "hits_expected_at_least": n * n_planted * len(plant_cols),
+                    "planted": "%d of %d queries carry %d bp whose k-mers are inserted into columns %s of every slab" % (n_planted, nq, PLANT, plant_cols)},
             "roofline": {"bound": "hbm", "kernel": "search_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC["search_count_kernel"] if (F, L, nq, qlen) == (8192, 26, 10000, 1000) else None,
                          "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": t_k * 1e3, "share_of_step": t_k * 1e3 / (sec / steps * 1e3),

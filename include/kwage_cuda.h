@@ -176,6 +176,11 @@ int kwg_synth_reads_dev(int device, uint64_t seed, uint64_t first_read, uint64_t
 	char* d_bases, uint64_t* d_offsets /* n_reads+1, may be NULL */, void* stream);
 int kwg_synth_filter_bits_dev(int device, uint64_t seed, uint64_t first_filter, uint32_t n_filters,
 	uint64_t filter_bytes, uint64_t filter_pitch, uint8_t* d_filters, void* stream);
+/* Known positives for the search benchmark: sets bit `column` of the rows of every k-mer of the first plant_len
+ * bases of queries query_first, query_first + query_stride, ... (n_planted of them) in a device slice slab. */
+int kwg_synth_plant_dev(int device, uint8_t* d_slab, uint64_t row_pitch, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len,
+	uint32_t column, const char* d_bases, const uint64_t* d_offsets, uint32_t query_first, uint32_t query_stride, uint32_t n_planted,
+	uint32_t plant_len, void* stream);
 
 /* Per-kernel device timing (CUDA events on the handle's stream around every launch).  Enable, run,
  * then get: ms[i] / launches[i] accumulate since the last get.  Kernel ids: */

@@ -28,7 +28,7 @@ EXPORTS = [
     "kwg_transpose", "kwg_transpose_dev",
     "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
-    "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev",
+    "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev", "kwg_synth_plant_dev",
     "kwg_bloom_set_timing", "kwg_bloom_get_timing", "kwg_db_set_timing", "kwg_db_get_timing",
 ]
 T_SCAN_A, T_SCAN_B, T_INSERT, T_AUX, T_SEARCH, T_HITS, T_REGROUP, T_RESOLVE, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
@@ -97,6 +97,7 @@ def lib():
     L.kwg_db_get_timing.argtypes = [vp, vp, vp]
     L.kwg_synth_reads_dev.argtypes = [i32, u64, u64, u64, u32, vp, vp, vp]
     L.kwg_synth_filter_bits_dev.argtypes = [i32, u64, u64, u32, u64, u64, vp, vp]
+    L.kwg_synth_plant_dev.argtypes = [i32, vp, u64, u32, u32, u32, u32, vp, vp, u32, u32, u32, u32, vp]
     _lib = L
     return L
 
@@ -371,6 +372,12 @@ class Database:
 def synth_reads_dev(seed, first_read, n_reads, read_len, d_bases_ptr, d_offsets_ptr=0, *, device=0, stream=0):
     check(lib().kwg_synth_reads_dev(device, seed, first_read, n_reads, read_len, C.c_void_p(d_bases_ptr),
                                     C.c_void_p(d_offsets_ptr), C.c_void_p(stream)))
+
+
+def synth_plant_dev(d_slab_ptr, row_pitch, k, num_hash, log2_len, column, d_bases_ptr, d_offsets_ptr, query_first, query_stride,
+                    n_planted, plant_len, *, device=0, stream=0):
+    check(lib().kwg_synth_plant_dev(device, C.c_void_p(d_slab_ptr), row_pitch, k, num_hash, log2_len, column, C.c_void_p(d_bases_ptr),
+                                    C.c_void_p(d_offsets_ptr), query_first, query_stride, n_planted, plant_len, C.c_void_p(stream)))
 
 
 def synth_filter_bits_dev(seed, first_filter, n_filters, filter_bytes, filter_pitch, d_filters_ptr, *, device=0, stream=0):

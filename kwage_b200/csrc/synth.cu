@@ -31,6 +31,38 @@ __global__ void synth_filter_bits_kernel(uint64_t seed, uint64_t first_filter, u
 	}
 }
 
+// Plants the k-mers of the first plant_len bases of every query_stride-th query into one column of a slice
+// slab (sets bit `column` of row murmur3(kmer, h) & mask for h < NH): the benchmark's known positives.
+__global__ void plant_kmers_kernel(uint8_t* __restrict__ slab, uint64_t row_pitch, uint32_t k, uint32_t num_hash, uint32_t mask,
+	uint32_t column, const char* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t query_first, uint32_t query_stride,
+	uint32_t plant_len)
+{
+	const uint32_t q = query_first + blockIdx.x * query_stride;
+	const uint64_t o0 = offsets[q], o1 = offsets[q + 1];
+	const uint64_t len = min((uint64_t)plant_len, o1 - o0);
+	if (len < k) return;
+	const char* s = bases + o0;
+	for (uint64_t p = threadIdx.x; p + k <= len; p += blockDim.x) {
+		uint64_t sense = 0;
+		bool ok = true;
+		for (uint32_t j = 0; j < k; ++j) {
+			const uint32_t ch = (uint8_t)s[p + j], u = ch & 0xDFu;
+			const uint32_t x = (ch >> 1) & 3u;
+			ok = ok && (u == 'A' || u == 'C' || u == 'G' || u == 'T');
+			sense = (sense << 2) | ((x ^ (x >> 1)) & 3u);
+		}
+		if (!ok) continue;
+		const Canon c = canonical(sense, k);
+		uint32_t h[KWG_MAX_NUM_HASH];
+		murmur3_multi<KWG_MAX_NUM_HASH>(c.low, k, h);
+		for (uint32_t t = 0; t < num_hash; ++t) {
+			uint8_t* byte = slab + (uint64_t)(h[t] & mask) * row_pitch + column / 8;
+			uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(byte) & ~(uintptr_t)3);
+			atomicOr(word, (1u << (column & 7u)) << (8 * (uint32_t)(reinterpret_cast<uintptr_t>(byte) & 3)));
+		}
+	}
+}
+
 } // namespace kwg
 
 using namespace kwg;
@@ -60,6 +92,23 @@ int kwg_synth_filter_bits_dev(int device, uint64_t seed, uint64_t first_filter, 
 	int rc = select_device(device);
 	if (rc) return rc;
 	synth_filter_bits_kernel<<<sm_count(device) * 16, 256, 0, (cudaStream_t)stream>>>(seed, first_filter, n_filters, filter_bytes / 8, filter_pitch, d_filters);
+	KWG_LAUNCHED();
+	return KWG_OK;
+}
+
+int kwg_synth_plant_dev(int device, uint8_t* d_slab, uint64_t row_pitch, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len,
+	uint32_t column, const char* d_bases, const uint64_t* d_offsets, uint32_t query_first, uint32_t query_stride, uint32_t n_planted,
+	uint32_t plant_len, void* stream)
+{
+	if (!d_slab || !d_bases || !d_offsets) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	if (kmer_len < 1 || kmer_len > KWG_MAX_KMER_LEN || num_hash < 1 || num_hash > KWG_MAX_NUM_HASH || log2_len > 32 || row_pitch % 4)
+		return fail(KWG_ERR_INVALID_ARG, "bad planting parameters");
+	if (n_planted == 0) return KWG_OK;
+	int rc = select_device(device);
+	if (rc) return rc;
+	const uint32_t mask = (log2_len >= 32) ? 0xFFFFFFFFu : ((1u << log2_len) - 1u);
+	plant_kmers_kernel<<<n_planted, 128, 0, (cudaStream_t)stream>>>(d_slab, row_pitch, kmer_len, num_hash, mask, column, d_bases, d_offsets,
+		query_first, query_stride, plant_len);
 	KWG_LAUNCHED();
 	return KWG_OK;
 }

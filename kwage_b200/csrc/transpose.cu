@@ -54,20 +54,23 @@ transpose_kernel(const uint8_t* __restrict__ filters, uint64_t filter_pitch, uin
 	for (int b = 0; b < 32; ++b) tile[(b * 32 + lw) * TR_WARPS + (g ^ sw)] = a[b];
 	__syncthreads();
 
-	// 8 consecutive lanes write the 32 bytes (8 groups) of one row; a warp covers 4 rows.
-	const uint64_t col_byte0 = (uint64_t)by * TR_WARPS * 4;
-#pragma unroll 4
-	for (int it = 0; it < 32; ++it) {
-		const uint32_t flat = it * TR_THREADS + threadIdx.x;
-		const uint32_t wd = flat & 7;              // group within the block
-		const uint32_t q = (flat >> 3) & 3;        // low two bits of lw
-		const uint32_t R = flat >> 5;              // 0..255
-		const uint32_t b = R & 31, lwh = R >> 5;
-		const uint32_t rlw = lwh * 4 + q;
-		const uint32_t v = tile[(b * 32 + rlw) * TR_WARPS + (wd ^ lwh)];
-		const uint64_t rword = bx * TR_WORDS + rlw;
-		const uint64_t cbyte = col_byte0 + wd * 4;
-		if (rword < n_words && cbyte < dest_pitch) st_na_u32(dest + (rword * 32 + b) * dest_pitch + cbyte, v);
+	// 8 consecutive lanes write the 32 bytes (8 groups) of one row; a warp covers 4 rows.  Fully unrolled: with
+	// R = it*8 + (tid>>5), everything that depends on `it` is a compile-time constant (lwh = it>>2,
+	// b = (it&3)*8 + tid>>5), so an iteration is one LDS, one address add and one predicated store.
+	const uint32_t wd = threadIdx.x & 7;                 // group within the block
+	const uint32_t q = (threadIdx.x >> 3) & 3;           // low two bits of lw
+	const uint32_t r0 = threadIdx.x >> 5;                // 0..7
+	const uint64_t cbyte = (uint64_t)by * TR_WARPS * 4 + wd * 4;
+	if (cbyte < dest_pitch) {
+		uint8_t* out0 = dest + ((bx * TR_WORDS + q) * 32 + r0) * dest_pitch + cbyte;
+		const uint32_t* t0 = tile + (r0 * 32 + q) * TR_WARPS;
+#pragma unroll
+		for (int it = 0; it < 32; ++it) {
+			const int lwh = it >> 2, bb = (it & 3) * 8;      // rlw = lwh*4 + q, b = bb + r0
+			const uint32_t v = t0[(bb * 32 + lwh * 4) * TR_WARPS + (wd ^ lwh)];
+			if (bx * TR_WORDS + lwh * 4 + q < n_words)
+				st_na_u32(out0 + ((uint64_t)(lwh * 4) * 32 + bb) * dest_pitch, v);
+		}
 	}
 }
 
