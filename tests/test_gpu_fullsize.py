@@ -1,0 +1,72 @@
+"""GPU properties at the benchmark's full accession size (BASELINE.json configs[1]: 1e6 x 150 bp reads, 1.2e8 k-mer
+occurrences, lc = 30 -> 65,536 final buckets, two-level partition, chunked host feed).  The oracle needs minutes at
+this size, so these tests use properties that hold for any input:
+  * the result does not depend on how the stream is cut into add_reads calls (stream-order exactness);
+  * adding reads that were already added changes nothing (every one of their touches finds its slot taken);
+  * every bit of the counting-mode filter is a bit of the raw-mode filter (same L, h), and the k-mers the counting
+    filters dropped are exactly the difference between the number of distinct k-mers and num_valid;
+  * a smaller accession embedded at the start of the stream gives the oracle's exact num_valid for that prefix."""
+import numpy as np
+import pytest
+
+from kwage_b200 import capi, hostapi as H
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+K, N_READS, READ_LEN, LMAX = 31, 1_000_000, 150, 32
+
+
+@pytest.fixture(scope="module")
+def accession():
+    bases = O.gen_reads(20260101, 0, N_READS, READ_LEN)
+    offsets = np.arange(N_READS + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    return bases, offsets
+
+
+def test_full_size_accession_is_split_and_repeat_invariant(accession):
+    bases, offsets = accession
+    lc = H.counting_filter_log2_len(int(offsets[-1]))
+    assert lc == 30
+    with capi.BloomBuilder(K, min_kmer_count=1, log2_count_len=lc, log2_max_len=LMAX) as b:
+        b.add_reads(bases, offsets)
+        n_one = b.num_valid()
+        L, h = H.optimal_bloom_param(K, n_one, 0.25, 18, LMAX)
+        assert (L, h) == (29, 3)
+        bits_one = b.finalize(L, h)
+        # the same reads again: nothing may change
+        b.add_reads(bases, offsets[: N_READS // 3 + 1])
+        assert b.num_valid() == n_one
+        assert np.array_equal(b.finalize(L, h), bits_one)
+        # a fresh accession fed in five uneven calls
+        b.reset()
+        cuts = [0, 1, 99_999, 400_000, 400_001, N_READS]
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            b.add_reads(bases, offsets[a: z + 1])
+        assert b.num_valid() == n_one
+        assert np.array_equal(b.finalize(L, h), bits_one)
+    # uniform random 150-mers: practically every 31-mer is distinct, the counting filters shadow ~3e-4 of them
+    n_kmers = N_READS * (READ_LEN - K + 1)
+    assert 0.9990 * n_kmers < n_one < n_kmers
+
+    with capi.BloomBuilder(K, raw_num_hash=h, raw_log2_len=L) as r:
+        r.add_reads(bases, offsets)
+        assert r.num_valid() == n_kmers
+        raw = r.finalize()
+    assert not np.any(bits_one & ~raw), "counting-mode filter has a bit the raw filter lacks"
+    missing = int(np.unpackbits(raw & ~bits_one).sum())
+    assert 0 < missing <= h * (n_kmers - n_one)
+
+
+def test_full_geometry_prefix_matches_oracle(accession):
+    # the full-size geometry (lc = 30) on a prefix the oracle can do in seconds
+    bases, offsets = accession
+    n = 60_000
+    ob = O.Builder(K, 1, 30, 26)
+    ob.add_reads(bases, offsets[: n + 1])
+    with capi.BloomBuilder(K, min_kmer_count=1, log2_count_len=30, log2_max_len=26) as b:
+        b.add_reads(bases, offsets[: n // 2 + 1])
+        b.add_reads(bases, offsets[n // 2: n + 1])
+        assert b.num_valid() == ob.num_valid()
+        assert np.array_equal(b.finalize(26, 4), ob.finalize(26, 4))
+    ob.close()
