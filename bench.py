@@ -43,12 +43,13 @@ def env_int(name, default):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the
-# default workload (profiles/r1c_ncu_full_*.md); reported as roofline.traffic when the workload matches
+# default workload (profiles/r1c_ncu_full_construct.md, r1d_ncu_full_transpose_search.md); reported as roofline.traffic
+# when the workload matches
 NCU_TRAFFIC = {
     "partition_scan": 3.987e9, "regroup": 7.728e9, "resolve": 6.529e9, "scan_pass_b": 1.147e9, "insert_words": 4.995e9,
-    "transpose_kernel": 6.868e10, "search_count_kernel": 3.018e10,
+    "transpose_kernel": 6.868e10, "search_count_kernel": 3.026e10,
 }
-NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_construct.md, profiles/r1c_ncu_full_transpose_search.md, profiles/r1a_ncu_full.md (search)"
+NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_construct.md, profiles/r1d_ncu_full_transpose_search.md"
 
 
 def measured_peaks():
