@@ -12,15 +12,17 @@
 //                              counting sort of the <= 8192 records by level-1 bucket in shared memory,
 //                              coalesced copy-out of the sorted tile + one row of run offsets.
 //                              No global atomics: every tile owns a fixed 64 KiB output window.
-//   K2 regroup_kernel          (only when there are more than 512 final buckets) block (i, g) gathers
-//                              the runs of level-1 bucket i from a group of tiles, sorts them by
-//                              level-2 bucket in shared memory and writes one dense chunk at an exact
-//                              (prefix-summed) position.
+//   K2 regroup_kernel          (only when there are more than 512 final buckets) persistent, warp-specialised
+//                              blocks: a producer group gathers the ~256 runs of one chunk = (level-1 bucket i,
+//                              group of tiles) into a staging buffer with bulk async copies + mbarrier, consumer
+//                              warps counting-sort it by level-2 bucket in shared memory and bulk-store one
+//                              dense chunk at an exact (prefix-summed) position.
 //   K3 resolve_kernel          one final bucket = 2^15 slots = a 128 KiB shared-memory tile of
 //                              "smallest stream position that touched this slot": tile initialised from
-//                              the persistent touched-bitmap, records streamed through atomicMin,
-//                              every touch that is not (or stops being) the first toucher adds 1 to the
-//                              4-bit loss counter of its occurrence; the bitmap is written back.
+//                              the persistent touched-bitmap, the bucket's runs staged by bulk async copies and
+//                              streamed through atomicMin, every touch that is not (or stops being) the first
+//                              toucher adds 1 to the 4-bit loss counter of its occurrence; the bitmap is
+//                              written back.
 //   pass B (kmer_scan_kernel)  occurrence is valid <=> loss counter < 4  (it is the first toucher of at
 //                              least one of its four slots, i.e. the reference read a zero counter).
 //
