@@ -196,9 +196,22 @@ def stage_construct(D, args, windows):
     d_offsets = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
     for i in range(pool):      # accession seeds follow SURVEY 8d: 12345 + accession index (distinct per rank)
         capi.synth_reads_dev(12345 + D.rank * 100000 + i, 0, n_reads, READ_LEN, d_bases[i].data_ptr(), d_offsets.data_ptr(), device=dev)
+        if args.coverage > 0:
+            # reads sampled from a random genome so that k-mers recur (needed for min_kmer_count > 1); torch only
+            # prepares the synthetic input here
+            g = torch.Generator(device="cuda")
+            g.manual_seed(12345 + D.rank * 100000 + i)
+            glen = max(READ_LEN + 1, int(n_bases / args.coverage))
+            genome = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")[torch.randint(0, 4, (glen,), generator=g, device="cuda")]
+            starts = torch.randint(0, glen - READ_LEN, (n_reads,), generator=g, device="cuda")
+            for a in range(0, n_reads, 100000):
+                z = min(n_reads, a + 100000)
+                idx = starts[a:z, None] + torch.arange(READ_LEN, device="cuda")[None, :]
+                d_bases[i][a * READ_LEN: z * READ_LEN] = genome[idx].reshape(-1)
+            del genome, starts, idx
     torch.cuda.synchronize()
     d_out = torch.empty((1 << LMAX) // 8, dtype=torch.uint8, device="cuda")
-    b = capi.BloomBuilder(K, device=dev, min_kmer_count=1, log2_count_len=lc, log2_max_len=LMAX)
+    b = capi.BloomBuilder(K, device=dev, min_kmer_count=args.min_kmer_count, log2_count_len=lc, log2_max_len=LMAX)
     state = {}
 
     def step_dev(i):
@@ -227,7 +240,8 @@ def stage_construct(D, args, windows):
     n_workers = max(1, args.e2e_workers)
     h_offsets = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
     h_offsets.copy_(d_offsets)
-    builders = [b] + [capi.BloomBuilder(K, device=dev, min_kmer_count=1, log2_count_len=lc, log2_max_len=LMAX) for _ in range(n_workers - 1)]
+    builders = [b] + [capi.BloomBuilder(K, device=dev, min_kmer_count=args.min_kmer_count, log2_count_len=lc, log2_max_len=LMAX)
+                      for _ in range(n_workers - 1)]
     h_bases, h_out = [], []
     for w in range(n_workers):
         hb = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
@@ -550,6 +564,8 @@ def main():
     ap.add_argument("--stages", default="construct,transpose,search")
     ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (handles) per GPU in the construct e2e arm")
     ap.add_argument("--reads", type=int, default=1000000, help="reads per accession (step)")
+    ap.add_argument("--min-kmer-count", type=int, default=1, help="counting-filter threshold (reference default 5; needs --coverage)")
+    ap.add_argument("--coverage", type=float, default=0.0, help=">0: reads are sampled from a random genome at this coverage")
     ap.add_argument("--tr-filters", type=int, default=4096)
     ap.add_argument("--tr-log2", type=int, default=26)
     ap.add_argument("--se-filters", type=int, default=8192)
@@ -562,9 +578,10 @@ def main():
     stages = [s for s in args.stages.split(",") if s]
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     config = {"workload": "configs[1] Bloom construction: one accession per step = %d synthetic %d bp reads (%.3g k-mer occurrences), "
-                          "k=%d, counting filter with min_kmer_count=1, p=%.2f, L in [%d,%d]; accessions sharded across GPUs" % (
-                              args.reads, READ_LEN, args.reads * (READ_LEN - K + 1), K, P_FALSE, LMIN, LMAX),
-              "reads_per_accession": args.reads, "read_len": READ_LEN, "kmer_len": K, "min_kmer_count": 1,
+                          "k=%d, counting filter with min_kmer_count=%d, p=%.2f, L in [%d,%d]; accessions sharded across GPUs%s" % (
+                              args.reads, READ_LEN, args.reads * (READ_LEN - K + 1), K, args.min_kmer_count, P_FALSE, LMIN, LMAX,
+                              "; reads sampled from a random genome at coverage %g" % args.coverage if args.coverage > 0 else ""),
+              "reads_per_accession": args.reads, "read_len": READ_LEN, "kmer_len": K, "min_kmer_count": args.min_kmer_count,
               "parallelism": "accession-per-GPU x%d" % world,
               "l2_policy": "inputs (150 MB reads, 3.8 GB of touch records per accession, 64 GiB slabs) are larger than the 126 MB L2"}
 

@@ -58,8 +58,11 @@ uint64_t kwg_launch_count(void);
  *
  * Counting mode (kwg_bloom_create) reproduces the reference's pair of 4-bit counting Bloom
  * filters with conservative update (make_bloom.cpp:63-69,546-601) followed by the 5-vector
- * fold, bit-exactly, for min_kmer_count == 1.  min_kmer_count in [2,15] is order dependent in a
- * way that has no parallel form and returns KWG_ERR_UNSUPPORTED (hard part 1).
+ * fold, bit-exactly, for every min_kmer_count in [1,15] (the reference's default is 5), including
+ * the double increment when both hashes of one table meet on a slot.  One case is refused instead
+ * of reproduced: with min_kmer_count == 15 such a double increment can take a 4-bit counter from
+ * 14 to 16 = 0 in the reference; the library detects it and kwg_bloom_num_valid / kwg_bloom_finalize
+ * return KWG_ERR_UNSUPPORTED.
  *   log2_count_len : log2 of the counting-filter length, [18,32] (make_bloom.cpp:104-129)
  *   log2_max_len   : opt.max_log_2_filter_len, <= 32 (make_bloom.cpp:137-140)
  *

@@ -1,7 +1,7 @@
 // Bloom construction on sm_100a: read tiles -> 2-bit canonical k-mers -> murmur3 multi-hash ->
 //   raw mode      : red.or into the (L2-resident where it fits) filter
 //   counting mode : exact, order-free form of the reference's two 4-bit counting Bloom filters
-//                   for min_kmer_count == 1 (reference make_bloom.cpp:506-621):
+//                   (reference make_bloom.cpp:506-621).  min_kmer_count == 1:
 //        a slot of the counting filters is non-zero at the time occurrence t is processed iff an
 //        earlier occurrence touched it (counters only ever grow from 0 and never wrap for c == 1),
 //        so t is "valid" iff it is the FIRST toucher (minimum stream position) of at least one of
@@ -13,6 +13,11 @@
 //                appended to a compact list in HBM (instead of the reference's 5 x 2^Lmax valid_bits vectors)
 //        finalize: for every listed word set bit (hash_h & (2^L-1)), h < num_hash -- which is what
 //                the reference's fold of valid_bits[h] computes (make_bloom.cpp:337-354).
+//        min_kmer_count = c > 1: the conservative-update counters are resolved level by level, one
+//        resolve launch per counter value 0 .. c-1 over the same sorted records (bloom_count.cuh,
+//        resolve_kernel<true>); what persists between batches is the 4-bit counter of every slot, i.e.
+//        the reference's own two tables.  Exact, including the double increment when both hashes of a
+//        table meet; a 4-bit wrap (only possible for c == 15) is detected and reported as an error.
 #include "common.cuh"
 #include "bloom_count.cuh"
 
@@ -48,6 +53,8 @@ struct ScanParams {
 	uint64_t* const* list_chunks;
 	unsigned long long* counter; // valid k-mers (counting) or inserted occurrences (raw)
 	const uint32_t* loss;        // 4-bit counters, 8 positions per word: touches of the occurrence that lost
+	const uint32_t* elig;        // min_kmer_count > 1: bit per position, occurrence eligible at the last level (NULL: all)
+	uint32_t wins;               // `loss` holds wins of the last level (min_kmer_count > 1) instead of losses
 };
 
 template <int MODE, int NH>
@@ -126,7 +133,9 @@ kmer_scan_kernel(const ScanParams P)
 			bool valid = false;
 			if (ok) {
 				const uint64_t rel = rel0 + p;
-				valid = ((P.loss[rel >> 3] >> ((rel & 7u) << 2)) & 0xFu) < 4u;
+				const uint32_t a = (P.loss[rel >> 3] >> ((rel & 7u) << 2)) & 0xFu;
+				// min count 1: fewer than 4 touches lost; min count c > 1: eligible at level c-1 and a win there
+				valid = P.wins ? (a != 0u && (!P.elig || ((P.elig[rel >> 5] >> (rel & 31u)) & 1u))) : (a < 4u);
 			}
 			// block-aggregated append: valid words are compacted in shared memory first, so the
 			// whole tile costs ONE atomicAdd on the global list cursor and coalesced stores
@@ -203,7 +212,9 @@ struct kwg_bloom {
 	uint32_t k = 0, min_count = 0, lc = 0, lmax = 0, raw_nh = 0, raw_L = 0;
 	// counting mode
 	CountGeom geom{};
-	uint32_t* d_touched = nullptr;       // 2^(lc+1) bits: slot touched by an earlier batch of this accession
+	uint32_t* d_touched = nullptr;       // min_count == 1: 2^(lc+1) bits, slot touched by an earlier batch of this accession
+	uint16_t* d_cnt = nullptr;           // min_count > 1: 2^(lc+1) 4-bit counters (the reference's two tables)
+	uint32_t* d_elig = nullptr;  size_t elig_cap = 0;   // min_count > 1: eligibility bitmap of the current sub-batch
 	bool touched_dirty = false;          // false: nothing added since create/reset (the bitmap need not be read)
 	std::vector<uint64_t*> chunks;
 	uint64_t** d_chunk_table = nullptr;
@@ -253,11 +264,15 @@ static int grow(void** p, size_t* cap, size_t need)
 	return KWG_OK;
 }
 
+// d_counter[0] = valid k-mers so far, d_counter[1] != 0: a 4-bit counter wrapped (min_kmer_count == 15 only)
 static int read_counter(kwg_bloom* b, uint64_t* out)
 {
 	if (b->n_valid_known) { *out = b->n_valid_host; return KWG_OK; }
-	KWG_CUDA(cudaMemcpyAsync(b->h_counter, b->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+	KWG_CUDA(cudaMemcpyAsync(b->h_counter, b->d_counter, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
 	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	if (b->h_counter[1])
+		return fail(KWG_ERR_UNSUPPORTED, "a 4-bit counter of the counting filter wrapped from 15 to 0 (min_kmer_count 15 with both hashes of "
+			"a table on one slot, reference make_bloom.cpp:586-592); this order-dependent case is not reproduced on the device");
 	*out = *b->h_counter;
 	b->n_valid_host = *out;
 	b->n_valid_known = true;
@@ -330,7 +345,8 @@ static int count_kernels_init()
 {
 	KWG_CUDA(cudaFuncSetAttribute(partition_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem_bytes()));
 	KWG_CUDA(cudaFuncSetAttribute(regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)regroup_smem_bytes()));
-	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
+	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
+	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
 	return KWG_OK;
 }
 
@@ -359,6 +375,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	if ((rc = grow((void**)&b->d_loss, &b->loss_cap, loss_words * sizeof(uint32_t)))) return rc;
 	if ((rc = grow((void**)&b->d_rec1, &b->rec1_cap, (size_t)n_tiles * PT_REC * sizeof(uint64_t)))) return rc;
 	if ((rc = grow((void**)&b->d_offs1, &b->offs1_cap, (size_t)(F1 + 1) * ntp * sizeof(uint16_t)))) return rc;
+	if (b->min_count > 1 && (rc = grow((void**)&b->d_elig, &b->elig_cap, loss_words / 4 * sizeof(uint32_t)))) return rc;
 	KWG_CUDA(cudaMemsetAsync(b->d_loss, 0, loss_words * sizeof(uint32_t), b->stream));
 
 	PartParams K1{};
@@ -464,10 +481,29 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		K3.f2_log2 = G.f2_log2;
 	}
 	const unsigned rgrid = (unsigned)std::min<uint64_t>(K3.n_buckets, (uint64_t)sm_count(b->device));
+	const uint32_t* d_elig_final = nullptr;
 	b->timers.begin(KWG_T_RESOLVE, b->stream);
-	resolve_kernel<<<rgrid, RS_THREADS, resolve_smem_bytes(), b->stream>>>(K3);
+	if (b->min_count == 1) {
+		resolve_kernel<false><<<rgrid, RS_THREADS, resolve_smem_bytes(), b->stream>>>(K3);
+		KWG_LAUNCHED();
+	} else {
+		// one launch per counter level; between two levels the eligibility bitmap is narrowed
+		const uint64_t elig_words = n_tiles * PT_POS / 32;
+		K3.cnt = b->d_cnt;
+		K3.wrap_flag = reinterpret_cast<uint32_t*>(b->d_counter + 1);
+		for (uint32_t level = 0; level < b->min_count; ++level) {
+			if (level) {
+				elig_update_kernel<<<(unsigned)ceil_div(elig_words, 256), 256, 0, b->stream>>>(b->d_elig, b->d_loss, elig_words, level == 1);
+				KWG_LAUNCHED();
+			}
+			K3.level = level;
+			K3.elig = level ? b->d_elig : nullptr;
+			resolve_kernel<true><<<rgrid, RS_THREADS, resolve_smem_bytes(), b->stream>>>(K3);
+			KWG_LAUNCHED();
+		}
+		d_elig_final = b->min_count > 1 ? b->d_elig : nullptr;
+	}
 	b->timers.end(b->stream);
-	KWG_LAUNCHED();
 
 	b->touched_dirty = true;
 	b->n_valid_known = false;
@@ -476,6 +512,8 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	P.pos0 = pos0;
 	P.n_pos = n_pos;
 	P.loss = b->d_loss;
+	P.elig = d_elig_final;
+	P.wins = b->min_count > 1 ? 1u : 0u;
 	P.list_chunks = b->d_chunk_table;
 	return launch_scan<MODE_PASS_B>(b, P);
 }
@@ -532,9 +570,9 @@ static int bloom_alloc_common(kwg_bloom* b)
 		fprintf(stderr, "[kwg] L2 fetch granularity = %zu\n", v);
 	}
 	KWG_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-	KWG_CUDA(cudaMalloc(&b->d_counter, sizeof(unsigned long long)));
-	KWG_CUDA(cudaMallocHost(&b->h_counter, sizeof(unsigned long long)));
-	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(unsigned long long), b->stream));
+	KWG_CUDA(cudaMalloc(&b->d_counter, 2 * sizeof(unsigned long long)));
+	KWG_CUDA(cudaMallocHost(&b->h_counter, 2 * sizeof(unsigned long long)));
+	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, 2 * sizeof(unsigned long long), b->stream));
 	return KWG_OK;
 }
 
@@ -545,7 +583,7 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->d_touched);
+	cudaFree(b->d_touched); cudaFree(b->d_cnt); cudaFree(b->d_elig);
 	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
 	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_meta);
 	cudaFree(b->d_cfirst); cudaFree(b->d_loss); cudaFree(b->d_tot_rec); cudaFree(b->d_tot_chk);
@@ -572,9 +610,6 @@ int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t 
 	if (min_kmer_count < 1 || min_kmer_count > 15) return fail(KWG_ERR_INVALID_ARG, "min_kmer_count must be in [1,15] (reference make_bloom.cpp:61,90-92)");
 	if (log2_count_len < 18 || log2_count_len > 32) return fail(KWG_ERR_INVALID_ARG, "log2_count_len must be in [18,32] (reference make_bloom.cpp:21-22)");
 	if (log2_max_len > 32) return fail(KWG_ERR_INVALID_ARG, "log2_max_len must be <= 32 (32-bit hash)");
-	if (min_kmer_count != 1)
-		return fail(KWG_ERR_UNSUPPORTED, "counting mode with min_kmer_count > 1 is order dependent (conservative-update counters, "
-			"reference make_bloom.cpp:546-601) and is not implemented on the device");
 	int rc = select_device(device);
 	if (rc) return rc;
 	kwg_bloom* b = new kwg_bloom();
@@ -585,10 +620,11 @@ int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t 
 		b->geom = count_geometry(b->lc);
 		rc = count_kernels_init();
 		if (rc == KWG_OK) {
-			const size_t bytes = (size_t)1 << (b->lc + 1 - 3);       // two tables of 2^lc slots, one bit each
-			cudaError_t e = cudaMalloc(&b->d_touched, bytes);
-			if (e != cudaSuccess) rc = fail(KWG_ERR_NO_MEMORY, std::string("touched bitmap: ") + cudaGetErrorString(e));
-			else if (cudaMemsetAsync(b->d_touched, 0, bytes, b->stream) != cudaSuccess) rc = fail(KWG_ERR_CUDA, "memset of touched bitmap failed");
+			// two tables of 2^lc slots: one bit each (min count 1) or the reference's 4-bit counters.  Neither needs
+			// clearing: the first batch after create/reset writes every word without reading it (have_prior == 0)
+			const size_t bytes = (size_t)1 << (b->lc + 1 - (min_kmer_count == 1 ? 3 : 1));
+			cudaError_t e = (min_kmer_count == 1) ? cudaMalloc(&b->d_touched, bytes) : cudaMalloc(&b->d_cnt, bytes);
+			if (e != cudaSuccess) rc = fail(KWG_ERR_NO_MEMORY, std::string("counting-filter state: ") + cudaGetErrorString(e));
 		}
 	}
 	if (rc) { kwg_bloom_destroy(b); return rc; }
@@ -623,7 +659,7 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
 	int rc = select_device(b->device);
 	if (rc) return rc;
-	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(unsigned long long), b->stream));
+	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, 2 * sizeof(unsigned long long), b->stream));
 	b->n_valid_host = 0;
 	b->n_valid_known = true;
 	if (b->raw) {

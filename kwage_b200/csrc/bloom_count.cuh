@@ -46,6 +46,8 @@ constexpr int CHUNK_REC = 8192;                   // records per level-2 chunk
 constexpr int RS_THREADS = 1024;                  // resolve kernel block size
 constexpr uint32_t SLOT_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t MAX_COUNT_POS = 1ull << 28;    // positions per counting sub-batch (record: 28-bit position)
+constexpr uint32_t REC_POS_MASK = (1u << 28) - 1u;
+constexpr uint32_t REC_DOUBLE = 1u << 28;         // record flag: the occurrence touches this slot through both hashes of the table
 
 struct CountGeom {
 	uint32_t lc;             // log2 counting-filter length (per table)
@@ -178,6 +180,9 @@ partition_scan_kernel(const PartParams P)
 			for (int j = 0; j < 4; ++j) {
 				const uint32_t hm = h[j] & P.count_mask;
 				s_hm[j * PT_POS + p] = hm;
+				// both hashes of one table on the same slot (reference: the counter is read once and incremented
+				// twice, make_bloom.cpp:553-554,586-592): ONE record of weight 2, carried by the even hash
+				if ((j & 1) && hm == (h[j - 1] & P.count_mask)) continue;
 				const uint32_t b1 = (hm >> P.shift1) | ((uint32_t)(j >> 1) << P.table_shift);
 				atomicAdd(&s_hist[b1], 1u);
 			}
@@ -204,11 +209,15 @@ partition_scan_kernel(const PartParams P)
 		if ((s_ok[p >> 5] >> (p & 31)) & 1u) {
 			const uint32_t pos = (uint32_t)(rel0 + p);
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const uint32_t hm = s_hm[j * PT_POS + p];
-				const uint32_t b1 = (hm >> P.shift1) | ((uint32_t)(j >> 1) << P.table_shift);
-				const uint32_t idx = atomicAdd(&s_cursor[b1], 1u);
-				s_sorted[idx] = ((uint64_t)(hm & low_mask) << 32) | pos;
+			for (int j = 0; j < 4; j += 2) {
+				const uint32_t hm0 = s_hm[j * PT_POS + p], hm1 = s_hm[(j + 1) * PT_POS + p];
+				const uint32_t dbl = (hm0 == hm1) ? REC_DOUBLE : 0u;
+				const uint32_t b0 = (hm0 >> P.shift1) | ((uint32_t)(j >> 1) << P.table_shift);
+				s_sorted[atomicAdd(&s_cursor[b0], 1u)] = ((uint64_t)(hm0 & low_mask) << 32) | pos | dbl;
+				if (!dbl) {
+					const uint32_t b1 = (hm1 >> P.shift1) | ((uint32_t)(j >> 1) << P.table_shift);
+					s_sorted[atomicAdd(&s_cursor[b1], 1u)] = ((uint64_t)(hm1 & low_mask) << 32) | pos;
+				}
 			}
 		}
 	}
@@ -662,7 +671,12 @@ struct ResolveParams {
 	uint32_t n_buckets;          // final buckets
 	uint32_t* touched;           // persistent bitmap, FINAL_SLOTS bits per final bucket
 	uint32_t have_prior;         // 0: first batch after create/reset, the bitmap is known to be all zero
-	uint32_t* loss;              // 4-bit loss counters, 8 positions per word
+	uint32_t* loss;              // 4-bit counters, 8 positions per word: losses (resolve_kernel<false>) or wins (<true>)
+	// min_kmer_count > 1 (resolve_kernel<true>): one launch per counter level
+	uint16_t* cnt;               // persistent 4-bit counters of the two counting filters, 4 slots per u16, bucket-major
+	const uint32_t* elig;        // bit per position: occurrence read counters >= level on all four slots (NULL: level 0)
+	uint32_t level;              // this launch decides which slots go from `level` to level + 1 (+ 2 for a weight-2 winner)
+	uint32_t* wrap_flag;         // set when a counter would pass 15 (the reference wraps to 0, bloom.h 4-bit field)
 };
 
 constexpr uint32_t RS_LONG = 64;                             // runs longer than this are read directly, not staged
@@ -675,20 +689,48 @@ __device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
 	return r;
 }
 
-__device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* loss, uint64_t rec)
+// One touch record against the tile.  Tile entry = ((position + 1) << 1) | (single ? 1 : 0) of the earliest
+// (eligible) occurrence seen so far, 0 = the slot already holds a larger count than this launch looks at,
+// SLOT_EMPTY = untouched.  A weight-2 record stands for both hashes of one table on the same slot.
+//
+// LEVELS == false (min_kmer_count == 1): every occurrence takes part, and `acct` counts LOSSES per occurrence
+//     (touches that found the slot taken; valid <=> fewer than 4): on low-coverage input almost every touch wins,
+//     so counting the losers keeps the global atomics rare.  First touches are noted in the bitmap.
+// LEVELS == true : `acct` counts WINS per occurrence (eligible at the next level <=> no win; valid <=> a win at the
+//     last level): min_kmer_count > 1 is what one uses on high-coverage input, where almost every touch loses.  A
+//     record that cannot lower the tile entry has no effect at all, so it is dropped after ONE shared-memory read
+//     (a stale value is safe: entries only decrease) and only the few would-be winners look up their eligibility.
+template <bool LEVELS>
+__device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* acct, const uint32_t* elig, uint64_t rec)
 {
 	const uint32_t slot = (uint32_t)(rec >> 32) & (FINAL_SLOTS - 1);
-	const uint32_t pos = (uint32_t)rec;
-	const uint32_t v = pos + 1u;                       // 0 = touched by an earlier batch
+	const uint32_t lo = (uint32_t)rec;
+	const uint32_t pos = lo & REC_POS_MASK;
+	const uint32_t dbl = (lo >> 28) & 1u;
+	const uint32_t v = ((pos + 1u) << 1) | (dbl ^ 1u);
+	if (LEVELS) {
+		if (*reinterpret_cast<volatile uint32_t*>(&s_tile[slot]) < v) return;
+		if (elig && !((__ldg(&elig[pos >> 5]) >> (pos & 31u)) & 1u)) return;
+		const uint32_t old = atomicMin(&s_tile[slot], v);
+		if (old > v) {
+			atomicAdd(&acct[pos >> 3], (1u + dbl) << ((pos & 7u) << 2));
+			if (old != SLOT_EMPTY) {
+				// a later occurrence had been processed first and has just been displaced: take its win back
+				// (the two updates of a nibble may land in either order; the sum of the word is what counts)
+				const uint32_t q = (old >> 1) - 1u;
+				atomicSub(&acct[q >> 3], (2u - (old & 1u)) << ((q & 7u) << 2));
+			}
+		}
+		return;
+	}
 	const uint32_t old = atomicMin(&s_tile[slot], v);
 	if (old <= v) {
-		// an earlier occurrence (or an earlier batch, or the same occurrence through its other hash
-		// of this table) holds the slot: this touch read a non-zero counter
-		atomicAdd(&loss[pos >> 3], 1u << ((pos & 7u) << 2));
+		// an earlier occurrence (or an earlier batch) holds the slot: this touch read a non-zero counter
+		atomicAdd(&acct[pos >> 3], (1u + dbl) << ((pos & 7u) << 2));
 	} else if (old != SLOT_EMPTY) {
 		// a later occurrence had been processed first and has just been displaced
-		const uint32_t q = old - 1u;
-		atomicAdd(&loss[q >> 3], 1u << ((q & 7u) << 2));
+		const uint32_t q = (old >> 1) - 1u;
+		atomicAdd(&acct[q >> 3], (2u - (old & 1u)) << ((q & 7u) << 2));
 	} else {
 		atomicOr(&s_bm[slot >> 5], 1u << (slot & 31u));      // first touch of the slot in this accession
 	}
@@ -697,6 +739,7 @@ __device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm,
 // what a thread needs of a bucket before it can start: its word of the touched bitmap and run tid
 struct BucketPrefetch { uint32_t bmw, len, off; };    // off: record index (< 2^30)
 
+template <bool LEVELS>
 __device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P, uint32_t b)
 {
 	const uint32_t tid = threadIdx.x;
@@ -707,7 +750,7 @@ __device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P
 	const uint64_t pitch = P.row_pitch ? P.row_pitch : (uint64_t)nci;
 	const uint16_t* row_s = P.offs + (uint64_t)c0 * (F2 + 1) + (uint64_t)j * pitch;
 	BucketPrefetch r;
-	r.bmw = P.have_prior ? P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] : 0u;
+	r.bmw = (!LEVELS && P.have_prior) ? P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] : 0u;
 	r.len = 0; r.off = 0;
 	if (tid < nci) {
 		const uint32_t s = row_s[tid], e = row_s[pitch + tid];
@@ -721,6 +764,17 @@ __device__ __forceinline__ BucketPrefetch prefetch_bucket(const ResolveParams& P
 // One final bucket at a time per (persistent) block: 2^15 slots as a 128 KiB tile of u32 "smallest
 // position that touched the slot".  The bucket's runs (one per chunk, ~26 records) are gathered into the
 // staging buffer by bulk async copies while the tile is initialised, then resolved one record per lane.
+//
+// LEVELS (min_kmer_count > 1): the conservative-update counters of the reference (make_bloom.cpp:546-601) are
+// resolved level by level.  Let T_v(s) be the stream position whose increment takes slot s to a count >= v.  An
+// occurrence t reads min >= v iff t > T_v(s) for all its slots ("eligible at level v"), and
+//     T_{v+1}(s) = min { t touching s : t eligible at level v },
+// because the earliest such t still reads exactly v on s, v as its minimum, and therefore increments s.  One launch
+// per level v = 0 .. c-1: the tile starts at 0 where the persistent counter is already above v (earlier batch, or
+// a weight-2 winner of level v-1) and at SLOT_EMPTY elsewhere, eligible touches go through atomicMin, the losers'
+// wins are summed per occurrence (eligible at v+1 <=> it won nothing), winners raise the counter.  An occurrence is
+// valid (reads min == c-1) iff it is eligible at level c-1 and wins at least one slot there.
+template <bool LEVELS>
 __global__ void __launch_bounds__(RS_THREADS, 1)
 resolve_kernel(const ResolveParams P)
 {
@@ -744,8 +798,9 @@ resolve_kernel(const ResolveParams P)
 
 	uint32_t b = blockIdx.x;
 	BucketPrefetch pf{0u, 0u, 0u};
-	if (b < P.n_buckets) pf = prefetch_bucket(P, b);
+	if (b < P.n_buckets) pf = prefetch_bucket<LEVELS>(P, b);
 
+	const bool use_cnt = LEVELS && (P.have_prior || P.level > 0);   // else the counters are known to be all zero
 	for (; b < P.n_buckets; b += gridDim.x) {
 		const uint32_t i = b >> P.f2_log2, j = b & (F2 - 1);
 		const uint32_t c0 = P.cfirst ? P.cfirst[i] : 0u;
@@ -754,10 +809,10 @@ resolve_kernel(const ResolveParams P)
 		const uint16_t* row_s = P.offs + (uint64_t)c0 * (F2 + 1) + (uint64_t)j * pitch;
 
 		uint32_t my_off = pf.off, my_len = pf.len;
-		s_bm[tid] = pf.bmw;
+		if (!LEVELS) s_bm[tid] = pf.bmw;
 		// tables of the next bucket travel while this one is resolved, and its runs are pulled into L2
 		if (b + gridDim.x < P.n_buckets) {
-			pf = prefetch_bucket(P, b + gridDim.x);
+			pf = prefetch_bucket<LEVELS>(P, b + gridDim.x);
 			if (pf.len) {
 				const char* p0 = reinterpret_cast<const char*>(P.rec + pf.off);
 				const char* p1 = p0 + (size_t)min(pf.len, RS_LONG) * 8 - 1;
@@ -807,8 +862,20 @@ resolve_kernel(const ResolveParams P)
 					mbar_arrive(&s_bar[0]);
 				}
 				if (!tile_ready) {
-					// tile <- touched bitmap of this bucket, while the copies are in flight
-					if (P.have_prior) {
+					// tile <- touched bitmap / counters of this bucket, while the copies are in flight
+					if (LEVELS && use_cnt) {
+						const uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
+#pragma unroll
+						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
+							const uint32_t n4 = cn[q * RS_THREADS + tid];
+							uint4 v;
+							v.x = ((n4 & 15u) > P.level) ? 0u : SLOT_EMPTY;
+							v.y = (((n4 >> 4) & 15u) > P.level) ? 0u : SLOT_EMPTY;
+							v.z = (((n4 >> 8) & 15u) > P.level) ? 0u : SLOT_EMPTY;
+							v.w = ((n4 >> 12) > P.level) ? 0u : SLOT_EMPTY;
+							reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = v;
+						}
+					} else if (!LEVELS && P.have_prior) {
 #pragma unroll
 						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
 							const uint32_t s4 = (q * RS_THREADS + tid) * 4;
@@ -836,10 +903,37 @@ resolve_kernel(const ResolveParams P)
 				}
 				__syncthreads();
 				const uint32_t extent = s_misc[1];
-				for (uint32_t e = tid; e < extent; e += RS_THREADS) {
-					const uint64_t rec = s_stage[e];
-					if ((uint32_t)(rec >> 32) != REC_NULL_HI) {
-						resolve_record(s_tile, s_bm, P.loss, rec);
+				if (LEVELS && P.elig) {
+					// four records per thread at a time: the eligibility look-ups of the would-be winners (the only
+					// global loads of this loop) are issued together instead of one latency after the other
+					for (uint32_t e0 = tid; e0 < extent; e0 += 4 * RS_THREADS) {
+						uint64_t r[4];
+						uint32_t ew[4];
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							const uint32_t e = e0 + q * RS_THREADS;
+							r[q] = (e < extent) ? s_stage[e] : REC_NULL;
+						}
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							const uint32_t slot = (uint32_t)(r[q] >> 32) & (FINAL_SLOTS - 1);
+							const uint32_t lo = (uint32_t)r[q];
+							const uint32_t pos = lo & REC_POS_MASK;
+							const uint32_t v = ((pos + 1u) << 1) | (((lo >> 28) & 1u) ^ 1u);
+							ew[q] = 0u;
+							if ((uint32_t)(r[q] >> 32) != REC_NULL_HI && *reinterpret_cast<volatile uint32_t*>(&s_tile[slot]) > v)
+								ew[q] = (__ldg(&P.elig[pos >> 5]) >> (pos & 31u)) & 1u;
+						}
+#pragma unroll
+						for (int q = 0; q < 4; ++q)
+							if (ew[q]) resolve_record<LEVELS>(s_tile, s_bm, P.loss, nullptr, r[q]);
+					}
+				} else {
+					for (uint32_t e = tid; e < extent; e += RS_THREADS) {
+						const uint64_t rec = s_stage[e];
+						if ((uint32_t)(rec >> 32) != REC_NULL_HI) {
+							resolve_record<LEVELS>(s_tile, s_bm, P.loss, P.elig, rec);
+						}
 					}
 				}
 				__syncthreads();
@@ -849,15 +943,65 @@ resolve_kernel(const ResolveParams P)
 			for (uint32_t q = warp; q < nlong; q += RS_THREADS / 32) {
 				const uint64_t* run = P.rec + s_off[q];
 				const uint32_t len = s_len[q];
-				for (uint32_t x = lane; x < len; x += 32) resolve_record(s_tile, s_bm, P.loss, ld_nc_u64(run + x));
+				for (uint32_t x = lane; x < len; x += 32) resolve_record<LEVELS>(s_tile, s_bm, P.loss, P.elig, ld_nc_u64(run + x));
 			}
 			__syncthreads();
 		}
 
-		// the bitmap now holds the earlier batches' bits plus every slot first touched here
-		P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] = s_bm[tid];
+		if (LEVELS && !tile_ready) {
+			// a bucket without a single run: nothing changes (counters not yet written are all zero)
+			if (!use_cnt) {
+				uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
+				for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) cn[q * RS_THREADS + tid] = 0;
+			}
+		} else if (LEVELS) {
+			// winners of this level raise their slot's counter: level -> level + 1 (+ 2 for a weight-2 winner)
+			uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
+#pragma unroll
+			for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
+				const uint4 t = reinterpret_cast<const uint4*>(s_tile)[q * RS_THREADS + tid];
+				const uint32_t tv[4] = {t.x, t.y, t.z, t.w};
+				const uint32_t o4 = use_cnt ? (uint32_t)cn[q * RS_THREADS + tid] : 0u;
+				uint32_t n4 = o4;
+#pragma unroll
+				for (int e = 0; e < 4; ++e) {
+					if (tv[e] != 0u && tv[e] != SLOT_EMPTY) {
+						const uint32_t nv = P.level + 2u - (tv[e] & 1u);
+						if (nv > 15u) *P.wrap_flag = 1u;
+						n4 = (n4 & ~(15u << (4 * e))) | ((nv & 15u) << (4 * e));
+					}
+				}
+				if (n4 != o4 || !use_cnt) cn[q * RS_THREADS + tid] = (uint16_t)n4;
+			}
+		} else {
+			// the bitmap now holds the earlier batches' bits plus every slot first touched here
+			P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] = s_bm[tid];
+		}
 		__syncthreads();
 	}
+}
+
+// Between two levels: eligible at the next level <=> eligible at this one and no slot won (win nibble == 0).
+// One thread per 32 positions; the win counters are cleared for the next launch.
+__global__ void __launch_bounds__(256)
+elig_update_kernel(uint32_t* __restrict__ elig, uint32_t* __restrict__ wins, uint64_t n_words, uint32_t first)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_words) return;
+	const uint4 l = reinterpret_cast<const uint4*>(wins)[i];
+	const uint32_t w[4] = {l.x, l.y, l.z, l.w};
+	uint32_t bits = 0;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		uint32_t m = w[q] | (w[q] >> 1);
+		m = (m | (m >> 2)) & 0x11111111u;                // bit 4j <=> nibble j != 0
+		m = (m | (m >> 3)) & 0x03030303u;                // 2 bits per byte
+		m = (m | (m >> 6)) & 0x000F000Fu;                // 4 bits per half
+		m = (m | (m >> 12)) & 0xFFu;
+		bits |= (m ^ 0xFFu) << (8 * q);
+	}
+	elig[i] = first ? bits : (elig[i] & bits);
+	reinterpret_cast<uint4*>(wins)[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 } // namespace kwg

@@ -46,7 +46,7 @@ def test_argument_validation_precedes_device_use():
     assert b"word.h" in L.kwg_last_error()
     assert L.kwg_bloom_create(C.byref(h), 0, 31, 16, 20, 24) == capi.KWG_ERR_INVALID_ARG     # min count > 15
     assert L.kwg_bloom_create(C.byref(h), 0, 31, 1, 17, 24) == capi.KWG_ERR_INVALID_ARG      # Lc < 18
-    assert L.kwg_bloom_create(C.byref(h), 0, 31, 5, 20, 24) == capi.KWG_ERR_UNSUPPORTED      # order-dependent mode
+    assert L.kwg_bloom_create(C.byref(h), 0, 31, 0, 20, 24) == capi.KWG_ERR_INVALID_ARG      # min count 0
     assert L.kwg_bloom_create_raw(C.byref(h), 0, 31, 9, 20) == capi.KWG_ERR_INVALID_ARG      # > 8 hashes (hash.cpp:243)
     assert L.kwg_transpose(0, None, 4, 64, None) == capi.KWG_ERR_INVALID_ARG
 

@@ -66,7 +66,7 @@ def test_raw_insert_edge_inputs():
 
 def run_counting(case, bases, offsets, split=None):
     lc = O.counting_log2_len(case["num_bp"])
-    with capi.BloomBuilder(case["k"], min_kmer_count=1, log2_count_len=lc, log2_max_len=case["lmax"]) as b:
+    with capi.BloomBuilder(case["k"], min_kmer_count=case["min_count"], log2_count_len=lc, log2_max_len=case["lmax"]) as b:
         if split is None:
             b.add_reads(bases, offsets)
         else:   # the same stream delivered in several calls (the reference adds one fragment at a time)
@@ -80,7 +80,8 @@ def run_counting(case, bases, offsets, split=None):
     return lc, n_valid, param, bits
 
 
-@pytest.mark.parametrize("name", ["uniform_k31", "ragged_k21", "k32", "k15_dups", "small_count_filter", "cfg1_mt64"])
+@pytest.mark.parametrize("name", ["uniform_k31", "ragged_k21", "k32", "k15_dups", "small_count_filter", "cfg1_mt64",
+                                  "min_count_2", "min_count_5"])
 def test_counting_mode_matches_reference_golden(name):
     g = load_golden("make_bloom")[name]
     case = dict(S.MAKE_BLOOM_CASES[name])
@@ -93,7 +94,8 @@ def test_counting_mode_matches_reference_golden(name):
     assert util.sha256(bits) == g["bits_sha256"]
 
 
-@pytest.mark.parametrize("name,split", [("ragged_k21", 7), ("small_count_filter", 3), ("k15_dups", 40)])
+@pytest.mark.parametrize("name,split", [("ragged_k21", 7), ("small_count_filter", 3), ("k15_dups", 40), ("min_count_2", 5),
+                                        ("min_count_5", 3)])
 def test_counting_mode_is_stream_order_exact_across_calls(name, split):
     g = load_golden("make_bloom")[name]
     case = dict(S.MAKE_BLOOM_CASES[name])
@@ -197,10 +199,112 @@ def test_counting_mode_reset_and_invalid_statuses():
         assert b.num_valid() == n_a
 
 
+# ------------------------------------------------------------------------------ min_kmer_count > 1
+# k = 31 k-mers whose murmur3 values for seeds 0 and 1 agree in their low 18 bits: with log2_count_len = 18 both
+# hashes of the first counting filter fall on one slot, which the reference increments twice per visit
+# (make_bloom.cpp:553-554,586-592)
+DUP_KMERS = [b"CTGATCATTGGGTAATACATTGAAGGCCCAT", b"CCTTGATATGCCACGCAAGCTCGTCTTCCAA"]
+
+
+def test_dup_kmers_really_collide():
+    for s in DUP_KMERS:
+        w, _ = O.canonical_kmers(s, 31)
+        assert (O.murmur3_word(w[0], 31, 0) ^ O.murmur3_word(w[0], 31, 1)) & 0x3FFFF == 0
+
+
+def reads_from_list(reads):
+    lens = np.array([len(r) for r in reads], np.uint64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    return np.concatenate([np.frombuffer(bytes(r), np.uint8) for r in reads]), offsets
+
+
+def abundance_case(seed, genome=60000, n_reads=9000, read_len=100, dup_copies=(11, 6)):
+    """Coverage ~15x cut by non-ACGT bytes (k-mer abundances spread around 10, on both sides of every threshold
+    tested), plus the slot-doubling k-mers as stand-alone reads scattered through the stream."""
+    case = dict(kind="coverage", seed=seed, genome=genome, n_reads=n_reads, read_len=read_len, num_bp=-1)
+    bases, offsets = S.make_bloom_reads(case)
+    bases = S.mutate(bases, seed, n_rate=211, lower_rate=9)
+    reads = [bases[int(offsets[i]): int(offsets[i + 1])] for i in range(n_reads)]
+    for kmer, copies in zip(DUP_KMERS, dup_copies):
+        for j in range(copies):
+            at = int(S.rnd(seed, 0xD0 + copies, np.array([j], np.uint64))[0] % np.uint64(len(reads)))
+            reads.insert(at, np.frombuffer(kmer, np.uint8))
+    return reads_from_list(reads)
+
+
+def check_against_oracle(bases, offsets, k, c, lc, lmax, split=1, params=((22, 3), (24, 5))):
+    ob = O.Builder(k, c, lc, lmax)
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(k, min_kmer_count=c, log2_count_len=lc, log2_max_len=lmax) as b:
+        n = len(offsets) - 1
+        cuts = [0] + [n * i // split for i in range(1, split)] + [n]
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            b.add_reads(bases, offsets[a: z + 1])
+        assert b.num_valid() == ob.num_valid()
+        for L, h in params:
+            assert np.array_equal(b.finalize(L, h), ob.finalize(L, h)), (L, h)
+        n_valid = b.num_valid()
+    ob.close()
+    return n_valid
+
+
+@pytest.mark.parametrize("c,lc,split", [(2, 18, 1), (2, 24, 3), (3, 18, 4), (3, 30, 1), (5, 18, 1), (5, 20, 2), (5, 23, 1), (5, 25, 5),
+                                        (5, 30, 2), (8, 18, 3), (8, 27, 1), (14, 18, 2), (15, 18, 1), (15, 24, 2), (15, 32, 1)])
+def test_min_kmer_count_levels_match_sequential_counters(c, lc, split):
+    # conservative-update counters resolved level by level must equal the reference's sequential loop for every
+    # threshold, partition geometry and batching; lc = 18 makes slot collisions (and weight-2 records) common
+    bases, offsets = abundance_case(100 + c)
+    n_valid = check_against_oracle(bases, offsets, 31, c, lc, 24, split)
+    assert n_valid > 1000
+
+
+@pytest.mark.parametrize("c", [2, 5, 9])
+def test_min_kmer_count_on_skewed_input(c):
+    # poly-A block + repeated reads: runs of >64 records (read straight from HBM) and multi-round buckets
+    bases, offsets = skewed_case(300 + c)
+    check_against_oracle(bases, offsets, 31, c, 22, 24, split=2)
+
+
+@pytest.mark.parametrize("c,copies", [(2, 1), (2, 2), (2, 3), (3, 2), (3, 3), (3, 4), (6, 5), (6, 6), (14, 13), (14, 14), (15, 14)])
+def test_weight2_records_follow_the_double_increment(c, copies):
+    # one k-mer whose two first-filter hashes share a slot: the slot goes 0 -> 2 -> 2 -> 4 ... while the second
+    # filter's slots go up by one, so the k-mer turns valid at a visit that depends on the double increments
+    reads = [np.frombuffer(DUP_KMERS[0], np.uint8)] * copies + [np.frombuffer(DUP_KMERS[1], np.uint8)] * (copies - 1)
+    bases, offsets = reads_from_list(reads)
+    check_against_oracle(bases, offsets, 31, c, 18, 24, params=((20, 3),))
+    check_against_oracle(bases, offsets, 31, c, 18, 24, split=max(1, copies // 2), params=((20, 5),))
+
+
+def test_counter_wrap_is_reported_not_mimicked():
+    # min_kmer_count 15: the 15th visit of the slot-doubling k-mer takes its 4-bit counter from 14 to 16 = 0 in the
+    # reference (bloom.h 4-bit field).  That order-dependent wrap is the one case the device refuses, loudly.
+    bases, offsets = reads_from_list([np.frombuffer(DUP_KMERS[0], np.uint8)] * 15)
+    with capi.BloomBuilder(31, min_kmer_count=15, log2_count_len=18, log2_max_len=24) as b:
+        b.add_reads(bases, offsets)
+        with pytest.raises(capi.KwageError) as e:
+            b.num_valid()
+        assert e.value.code == capi.KWG_ERR_UNSUPPORTED and "wrapped" in str(e.value)
+    # the same stream with a different counting-filter length has no shared slot and no wrap
+    check_against_oracle(bases, offsets, 31, 15, 19, 24, params=((20, 3),))
+
+
+def test_min_kmer_count_reset_between_accessions():
+    bases, offsets = abundance_case(7, n_reads=3000)
+    ob = O.Builder(31, 4, 20, 24)
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(31, min_kmer_count=4, log2_count_len=20, log2_max_len=24) as b:
+        b.add_reads(bases, offsets[:1501])
+        b.reset()
+        b.add_reads(bases, offsets)
+        assert b.num_valid() == ob.num_valid()
+        assert np.array_equal(b.finalize(24, 3), ob.finalize(24, 3))
+    ob.close()
+
+
 def test_unsupported_and_bad_arguments_raise():
     with pytest.raises(capi.KwageError) as e:
-        capi.BloomBuilder(31, min_kmer_count=5, log2_count_len=20, log2_max_len=24)
-    assert e.value.code == capi.KWG_ERR_UNSUPPORTED
+        capi.BloomBuilder(31, min_kmer_count=16, log2_count_len=20, log2_max_len=24)
+    assert e.value.code == capi.KWG_ERR_INVALID_ARG
     with pytest.raises(capi.KwageError):
         capi.BloomBuilder(33, raw_num_hash=3, raw_log2_len=20)
     with capi.BloomBuilder(31, raw_num_hash=3, raw_log2_len=20) as b:

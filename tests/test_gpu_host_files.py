@@ -25,7 +25,8 @@ def sha_file(path):
     return util.sha256(np.fromfile(path, dtype=np.uint8))
 
 
-@pytest.mark.parametrize("name", ["uniform_k31", "ragged_k21", "k32", "k15_dups", "small_count_filter", "invalid_too_many", "no_kmers"])
+@pytest.mark.parametrize("name", ["uniform_k31", "ragged_k21", "k32", "k15_dups", "small_count_filter", "invalid_too_many", "no_kmers",
+                                  "min_count_2", "min_count_5"])
 def test_make_bloom_filter_writes_the_reference_file(name, tmp_path):
     g = load_golden("make_bloom")[name]
     case = dict(S.MAKE_BLOOM_CASES[name])
@@ -45,13 +46,18 @@ def test_make_bloom_filter_writes_the_reference_file(name, tmp_path):
         assert not os.path.exists(str(tmp_path / (g["accession"] + ".bloom")))
 
 
-def test_make_bloom_filter_unsupported_min_count_fails_loudly(tmp_path):
+def test_make_bloom_filter_default_min_count_5_no_cpu_path(tmp_path):
+    # the reference's default --min-kmer-count is 5 (options.h); the device path must be the one that ran
+    from kwage_b200 import capi
     case = dict(S.MAKE_BLOOM_CASES["min_count_5"])
     bases, offsets = S.make_bloom_reads(case)
     reads = str(tmp_path / "SRR000007.reads")
     S.write_reads_file(reads, bases, offsets)
+    before = capi.launch_count()
     r = H.make_bloom_file("SRR000007", reads, case["num_bp"], str(tmp_path), k=31, min_kmer_count=5, max_log2=24)
-    assert r["status"] == H.STATUS_BLOOM_FAIL and "kwg_bloom_create" in r["error"]    # no silent CPU path
+    assert r["status"] == H.STATUS_BLOOM_SUCCESS, r
+    assert r["num_kmer"] == load_golden("make_bloom")["min_count_5"]["num_kmer"]
+    assert capi.launch_count() > before
 
 
 @pytest.mark.parametrize("name", list(S.BUILD_DB_CASES))
