@@ -215,6 +215,8 @@ struct kwg_bloom {
 	uint32_t* d_touched = nullptr;       // min_count == 1: 2^(lc+1) bits, slot touched by an earlier batch of this accession
 	uint16_t* d_cnt = nullptr;           // min_count > 1: 2^(lc+1) 4-bit counters (the reference's two tables)
 	uint32_t* d_elig = nullptr;  size_t elig_cap = 0;   // min_count > 1: eligibility bitmap of the current sub-batch
+	uint64_t* d_dense = nullptr;         // min_count > 1: dense per-bucket copies of the records for the levels >= 1
+	uint32_t* d_dense_len = nullptr;     // [n_buckets] extents, [1] number of buckets without a dense copy, [n_buckets] their list
 	bool touched_dirty = false;          // false: nothing added since create/reset (the bitmap need not be read)
 	std::vector<uint64_t*> chunks;
 	uint64_t** d_chunk_table = nullptr;
@@ -335,9 +337,9 @@ static size_t regroup_smem_bytes()
 	return (size_t)2 * STAGE_REC * 8 + (size_t)(CHUNK_REC + 2) * 8 + 32 + 2 * sizeof(RegroupUnit) +
 	       (size_t)(2 * MAX_FAN + 2 + (MAX_FAN + 1) + MAX_FAN + 16 + 4) * 4;
 }
-static size_t resolve_smem_bytes()
+static size_t resolve_smem_bytes(bool levels = false)
 {
-	return (size_t)FINAL_SLOTS * 4 + (size_t)STAGE_REC * 8 + 16 + (size_t)(FINAL_SLOTS / 32 + 2 * RS_THREADS + 32 + 2) * 4 +
+	return (size_t)FINAL_SLOTS * 4 + (size_t)STAGE_REC * 8 + 16 + (size_t)((levels ? FINAL_SLOTS / 8 : FINAL_SLOTS / 32) + 2 * RS_THREADS + 32 + 2) * 4 +
 	       (size_t)RS_THREADS * 2;
 }
 
@@ -346,7 +348,8 @@ static int count_kernels_init()
 	KWG_CUDA(cudaFuncSetAttribute(partition_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem_bytes()));
 	KWG_CUDA(cudaFuncSetAttribute(regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)regroup_smem_bytes()));
 	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
-	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
+	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes(true)));
+	KWG_CUDA(cudaFuncSetAttribute(resolve_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes(true)));
 	return KWG_OK;
 }
 
@@ -491,6 +494,11 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		const uint64_t elig_words = n_tiles * PT_POS / 32;
 		K3.cnt = b->d_cnt;
 		K3.wrap_flag = reinterpret_cast<uint32_t*>(b->d_counter + 1);
+		K3.dense = b->d_dense;
+		K3.dense_len = b->d_dense_len;
+		K3.n_not_dense = b->d_dense_len ? b->d_dense_len + K3.n_buckets : nullptr;
+		K3.nd_list = b->d_dense_len ? b->d_dense_len + K3.n_buckets + 1 : nullptr;
+		if (K3.dense) KWG_CUDA(cudaMemsetAsync(K3.n_not_dense, 0, sizeof(uint32_t), b->stream));
 		for (uint32_t level = 0; level < b->min_count; ++level) {
 			if (level) {
 				elig_update_kernel<<<(unsigned)ceil_div(elig_words, 256), 256, 0, b->stream>>>(b->d_elig, b->d_loss, elig_words, level == 1);
@@ -498,7 +506,11 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 			}
 			K3.level = level;
 			K3.elig = level ? b->d_elig : nullptr;
-			resolve_kernel<true><<<rgrid, RS_THREADS, resolve_smem_bytes(), b->stream>>>(K3);
+			if (level && K3.dense) {
+				resolve_dense_kernel<<<rgrid, RS_THREADS, resolve_smem_bytes(true), b->stream>>>(K3);
+				KWG_LAUNCHED();
+			}
+			resolve_kernel<true><<<rgrid, RS_THREADS, resolve_smem_bytes(true), b->stream>>>(K3);     // (level >= 1: only the buckets without a dense copy)
 			KWG_LAUNCHED();
 		}
 		d_elig_final = b->min_count > 1 ? b->d_elig : nullptr;
@@ -583,7 +595,7 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->d_touched); cudaFree(b->d_cnt); cudaFree(b->d_elig);
+	cudaFree(b->d_touched); cudaFree(b->d_cnt); cudaFree(b->d_elig); cudaFree(b->d_dense); cudaFree(b->d_dense_len);
 	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
 	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_meta);
 	cudaFree(b->d_cfirst); cudaFree(b->d_loss); cudaFree(b->d_tot_rec); cudaFree(b->d_tot_chk);
@@ -620,11 +632,22 @@ int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t 
 		b->geom = count_geometry(b->lc);
 		rc = count_kernels_init();
 		if (rc == KWG_OK) {
-			// two tables of 2^lc slots: one bit each (min count 1) or the reference's 4-bit counters.  Neither needs
-			// clearing: the first batch after create/reset writes every word without reading it (have_prior == 0)
+			// two tables of 2^lc slots: one bit each (min count 1: the first batch after create/reset writes every word
+			// without reading it) or the reference's 4-bit counters (cleared here and by reset)
 			const size_t bytes = (size_t)1 << (b->lc + 1 - (min_kmer_count == 1 ? 3 : 1));
 			cudaError_t e = (min_kmer_count == 1) ? cudaMalloc(&b->d_touched, bytes) : cudaMalloc(&b->d_cnt, bytes);
 			if (e != cudaSuccess) rc = fail(KWG_ERR_NO_MEMORY, std::string("counting-filter state: ") + cudaGetErrorString(e));
+			else if (b->d_cnt && cudaMemsetAsync(b->d_cnt, 0, bytes, b->stream) != cudaSuccess) rc = fail(KWG_ERR_CUDA, "memset of the counting filters failed");
+			if (rc == KWG_OK && min_kmer_count > 1 && !getenv("KWG_NO_DENSE")) {
+				// one staging window per final bucket (4.5 GiB at lc = 30); optional: without it every level gathers again
+				const size_t nb = (size_t)1 << b->geom.nb_log2;
+				if (cudaMalloc(&b->d_dense, nb * STAGE_REC * sizeof(uint64_t)) != cudaSuccess ||
+				    cudaMalloc(&b->d_dense_len, (2 * nb + 1) * sizeof(uint32_t)) != cudaSuccess) {
+					cudaGetLastError();
+					cudaFree(b->d_dense); cudaFree(b->d_dense_len);
+					b->d_dense = nullptr; b->d_dense_len = nullptr;
+				}
+			}
 		}
 	}
 	if (rc) { kwg_bloom_destroy(b); return rc; }
@@ -666,6 +689,7 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 		KWG_CUDA(cudaMemsetAsync(b->d_filter, 0, (size_t)1 << (b->raw_L - 3), b->stream));
 	} else {
 		b->touched_dirty = false;            // the next batch rewrites every word of the touched bitmap
+		if (b->d_cnt) KWG_CUDA(cudaMemsetAsync(b->d_cnt, 0, (size_t)1 << b->lc, b->stream));
 	}
 	return KWG_OK;
 }

@@ -673,10 +673,16 @@ struct ResolveParams {
 	uint32_t have_prior;         // 0: first batch after create/reset, the bitmap is known to be all zero
 	uint32_t* loss;              // 4-bit counters, 8 positions per word: losses (resolve_kernel<false>) or wins (<true>)
 	// min_kmer_count > 1 (resolve_kernel<true>): one launch per counter level
-	uint16_t* cnt;               // persistent 4-bit counters of the two counting filters, 4 slots per u16, bucket-major
+	uint16_t* cnt;               // persistent 4-bit counters of the two counting filters: bucket-major, slot s of a bucket = nibble s
 	const uint32_t* elig;        // bit per position: occurrence read counters >= level on all four slots (NULL: level 0)
 	uint32_t level;              // this launch decides which slots go from `level` to level + 1 (+ 2 for a weight-2 winner)
 	uint32_t* wrap_flag;         // set when a counter would pass 15 (the reference wraps to 0, bloom.h 4-bit field)
+	// dense copies of the buckets for the launches of level >= 1 (resolve_dense_kernel): level 0 stores the staged
+	// records of every bucket that fits one staging window at dense + b * STAGE_REC and notes the extent
+	uint64_t* dense;             // NULL: not used
+	uint32_t* dense_len;         // [n_buckets] records (even), 0: the bucket has to be gathered again
+	uint32_t* n_not_dense;       // buckets with records that have no dense copy
+	uint32_t* nd_list;           // ... and which they are
 };
 
 constexpr uint32_t RS_LONG = 64;                             // runs longer than this are read directly, not staged
@@ -701,7 +707,7 @@ __device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
 //     record that cannot lower the tile entry has no effect at all, so it is dropped after ONE shared-memory read
 //     (a stale value is safe: entries only decrease) and only the few would-be winners look up their eligibility.
 template <bool LEVELS>
-__device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* acct, const uint32_t* elig, uint64_t rec)
+__device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* acct, const uint32_t* elig, uint32_t level, uint64_t rec)
 {
 	const uint32_t slot = (uint32_t)(rec >> 32) & (FINAL_SLOTS - 1);
 	const uint32_t lo = (uint32_t)rec;
@@ -709,7 +715,9 @@ __device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm,
 	const uint32_t dbl = (lo >> 28) & 1u;
 	const uint32_t v = ((pos + 1u) << 1) | (dbl ^ 1u);
 	if (LEVELS) {
+		// s_bm holds the bucket's 4-bit counters here (8 slots per word)
 		if (*reinterpret_cast<volatile uint32_t*>(&s_tile[slot]) < v) return;
+		if (((s_bm[slot >> 3] >> ((slot & 7u) << 2)) & 15u) > level) return;      // the slot is already above this level
 		if (elig && !((__ldg(&elig[pos >> 5]) >> (pos & 31u)) & 1u)) return;
 		const uint32_t old = atomicMin(&s_tile[slot], v);
 		if (old > v) {
@@ -734,6 +742,21 @@ __device__ __forceinline__ void resolve_record(uint32_t* s_tile, uint32_t* s_bm,
 	} else {
 		atomicOr(&s_bm[slot >> 5], 1u << (slot & 31u));      // first touch of the slot in this accession
 	}
+}
+
+// LEVELS, after all records of the bucket went through resolve_record: is this record the winner of its slot?  Then
+// the slot's counter goes from level to level + weight and the tile entry is handed back clean.
+__device__ __forceinline__ bool settle_winner(uint32_t* s_tile, uint32_t* s_cn, uint32_t level, uint32_t* wrap_flag, uint64_t rec)
+{
+	const uint32_t slot = (uint32_t)(rec >> 32) & (FINAL_SLOTS - 1);
+	const uint32_t lo = (uint32_t)rec;
+	const uint32_t v = (((lo & REC_POS_MASK) + 1u) << 1) | (((lo >> 28) & 1u) ^ 1u);
+	if (s_tile[slot] != v) return false;
+	const uint32_t w = 2u - (v & 1u);
+	if (level + w > 15u) *wrap_flag = 1u;           // the reference's 4-bit field would wrap to 0: reported, not mimicked
+	else atomicAdd(&s_cn[slot >> 3], w << ((slot & 7u) << 2));
+	s_tile[slot] = SLOT_EMPTY;
+	return true;
 }
 
 // what a thread needs of a bucket before it can start: its word of the touched bitmap and run tid
@@ -778,12 +801,14 @@ template <bool LEVELS>
 __global__ void __launch_bounds__(RS_THREADS, 1)
 resolve_kernel(const ResolveParams P)
 {
+	// LEVELS: the bitmap region holds the bucket's 4-bit counters instead (16 KiB)
+	constexpr uint32_t BM_WORDS = LEVELS ? FINAL_SLOTS / 8 : FINAL_SLOTS / 32;
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);                           // FINAL_SLOTS
 	uint64_t* s_stage = reinterpret_cast<uint64_t*>(s_tile + FINAL_SLOTS);              // STAGE_REC
 	unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_stage + STAGE_REC);        // 1 (+1 pad)
-	uint32_t* s_bm = reinterpret_cast<uint32_t*>(s_bar + 2);                            // FINAL_SLOTS / 32
-	uint32_t* s_off = s_bm + FINAL_SLOTS / 32;                                          // RS_THREADS: record index of every run
+	uint32_t* s_bm = reinterpret_cast<uint32_t*>(s_bar + 2);                            // BM_WORDS (16-byte aligned)
+	uint32_t* s_off = s_bm + BM_WORDS;                                                  // RS_THREADS: record index of every run
 	uint32_t* s_len = s_off + RS_THREADS;                                               // RS_THREADS
 	uint32_t* s_warp = s_len + RS_THREADS;                                              // 32
 	uint32_t* s_misc = s_warp + 32;                                                     // [0] long runs, [1] staged extent of the round
@@ -793,26 +818,38 @@ resolve_kernel(const ResolveParams P)
 	const uint32_t F2 = 1u << P.f2_log2;
 
 	if (tid == 0) { mbar_init(&s_bar[0], RS_THREADS); mbar_init_fence(); }
+	if (LEVELS) {
+		// the tile is handed back clean by every bucket (settle_winner / the sweep below): filled once
+		const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY);
+#pragma unroll
+		for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q)
+			reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = e4;
+	}
 	__syncthreads();
 	uint32_t parity = 0;
 
-	uint32_t b = blockIdx.x;
+	// work list: all buckets, or (levels >= 1 with dense copies) the few buckets that have none
+	const bool listed = LEVELS && P.level > 0 && P.dense;
+	const uint32_t n_work = listed ? *P.n_not_dense : P.n_buckets;
+	uint32_t it = blockIdx.x;
+	uint32_t b = 0;
 	BucketPrefetch pf{0u, 0u, 0u};
-	if (b < P.n_buckets) pf = prefetch_bucket<LEVELS>(P, b);
+	if (it < n_work) { b = listed ? P.nd_list[it] : it; pf = prefetch_bucket<LEVELS>(P, b); }
 
-	const bool use_cnt = LEVELS && (P.have_prior || P.level > 0);   // else the counters are known to be all zero
-	for (; b < P.n_buckets; b += gridDim.x) {
+	for (; it < n_work; it += gridDim.x) {
 		const uint32_t i = b >> P.f2_log2, j = b & (F2 - 1);
 		const uint32_t c0 = P.cfirst ? P.cfirst[i] : 0u;
 		const uint32_t nci = P.cfirst ? P.cfirst[i + 1] - c0 : P.single_nci;
 		const uint64_t pitch = P.row_pitch ? P.row_pitch : (uint64_t)nci;
 		const uint16_t* row_s = P.offs + (uint64_t)c0 * (F2 + 1) + (uint64_t)j * pitch;
+		const uint32_t b_cur = b;
 
 		uint32_t my_off = pf.off, my_len = pf.len;
 		if (!LEVELS) s_bm[tid] = pf.bmw;
 		// tables of the next bucket travel while this one is resolved, and its runs are pulled into L2
-		if (b + gridDim.x < P.n_buckets) {
-			pf = prefetch_bucket<LEVELS>(P, b + gridDim.x);
+		if (it + gridDim.x < n_work) {
+			b = listed ? P.nd_list[it + gridDim.x] : it + gridDim.x;
+			pf = prefetch_bucket<LEVELS>(P, b);
 			if (pf.len) {
 				const char* p0 = reinterpret_cast<const char*>(P.rec + pf.off);
 				const char* p1 = p0 + (size_t)min(pf.len, RS_LONG) * 8 - 1;
@@ -822,6 +859,8 @@ resolve_kernel(const ResolveParams P)
 		}
 
 		bool tile_ready = false;
+		bool stage_whole = false, has_records = false;       // LEVELS: every record of the bucket is in the staging buffer
+		uint32_t whole_extent = 0;
 		for (uint32_t cb = 0; cb < nci; cb += RS_THREADS) {
 			const uint32_t nrt = min((uint32_t)RS_THREADS, nci - cb);
 			if (cb) {          // run tables beyond the prefetched first RS_THREADS runs
@@ -853,29 +892,21 @@ resolve_kernel(const ResolveParams P)
 				// the last run of the previous round may overhang the window: the first run of this one then
 				// starts a few records in, and what lies before it must not be resolved a second time
 				if (r0 && tid < RS_LONG + 2) s_stage[tid] = REC_NULL;
+				if (LEVELS && tid == 0) bulk_wait_read();     // bulk stores of the previous bucket have left shared memory
 				fence_async_smem();
 				__syncthreads();
-				if (mine) {
-					mbar_arrive_expect_tx(&s_bar[0], span * 8u);
-					bulk_g2s(s_stage + (so - r0), P.rec + (my_off - lead), span * 8u, &s_bar[0]);
+				// LEVELS: the bucket's counters travel with the first round
+				const uint32_t cn_bytes = (LEVELS && !tile_ready && tid == 0) ? (uint32_t)(BM_WORDS * 4) : 0u;
+				if (mine || cn_bytes) {
+					mbar_arrive_expect_tx(&s_bar[0], (mine ? span * 8u : 0u) + cn_bytes);
+					if (mine) bulk_g2s(s_stage + (so - r0), P.rec + (my_off - lead), span * 8u, &s_bar[0]);
+					if (cn_bytes) bulk_g2s(s_bm, P.cnt + (uint64_t)b_cur * (FINAL_SLOTS / 4), cn_bytes, &s_bar[0]);
 				} else {
 					mbar_arrive(&s_bar[0]);
 				}
-				if (!tile_ready) {
-					// tile <- touched bitmap / counters of this bucket, while the copies are in flight
-					if (LEVELS && use_cnt) {
-						const uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
-#pragma unroll
-						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
-							const uint32_t n4 = cn[q * RS_THREADS + tid];
-							uint4 v;
-							v.x = ((n4 & 15u) > P.level) ? 0u : SLOT_EMPTY;
-							v.y = (((n4 >> 4) & 15u) > P.level) ? 0u : SLOT_EMPTY;
-							v.z = (((n4 >> 8) & 15u) > P.level) ? 0u : SLOT_EMPTY;
-							v.w = ((n4 >> 12) > P.level) ? 0u : SLOT_EMPTY;
-							reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = v;
-						}
-					} else if (!LEVELS && P.have_prior) {
+				if (!LEVELS && !tile_ready) {
+					// tile <- touched bitmap of this bucket, while the copies are in flight
+					if (P.have_prior) {
 #pragma unroll
 						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
 							const uint32_t s4 = (q * RS_THREADS + tid) * 4;
@@ -893,8 +924,8 @@ resolve_kernel(const ResolveParams P)
 						for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q)
 							reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = e4;
 					}
-					tile_ready = true;
 				}
+				tile_ready = true;
 				mbar_wait(&s_bar[0], parity);
 				parity ^= 1u;
 				if (mine) {
@@ -903,37 +934,10 @@ resolve_kernel(const ResolveParams P)
 				}
 				__syncthreads();
 				const uint32_t extent = s_misc[1];
-				if (LEVELS && P.elig) {
-					// four records per thread at a time: the eligibility look-ups of the would-be winners (the only
-					// global loads of this loop) are issued together instead of one latency after the other
-					for (uint32_t e0 = tid; e0 < extent; e0 += 4 * RS_THREADS) {
-						uint64_t r[4];
-						uint32_t ew[4];
-#pragma unroll
-						for (int q = 0; q < 4; ++q) {
-							const uint32_t e = e0 + q * RS_THREADS;
-							r[q] = (e < extent) ? s_stage[e] : REC_NULL;
-						}
-#pragma unroll
-						for (int q = 0; q < 4; ++q) {
-							const uint32_t slot = (uint32_t)(r[q] >> 32) & (FINAL_SLOTS - 1);
-							const uint32_t lo = (uint32_t)r[q];
-							const uint32_t pos = lo & REC_POS_MASK;
-							const uint32_t v = ((pos + 1u) << 1) | (((lo >> 28) & 1u) ^ 1u);
-							ew[q] = 0u;
-							if ((uint32_t)(r[q] >> 32) != REC_NULL_HI && *reinterpret_cast<volatile uint32_t*>(&s_tile[slot]) > v)
-								ew[q] = (__ldg(&P.elig[pos >> 5]) >> (pos & 31u)) & 1u;
-						}
-#pragma unroll
-						for (int q = 0; q < 4; ++q)
-							if (ew[q]) resolve_record<LEVELS>(s_tile, s_bm, P.loss, nullptr, r[q]);
-					}
-				} else {
-					for (uint32_t e = tid; e < extent; e += RS_THREADS) {
-						const uint64_t rec = s_stage[e];
-						if ((uint32_t)(rec >> 32) != REC_NULL_HI) {
-							resolve_record<LEVELS>(s_tile, s_bm, P.loss, P.elig, rec);
-						}
+				for (uint32_t e = tid; e < extent; e += RS_THREADS) {
+					const uint64_t rec = s_stage[e];
+					if ((uint32_t)(rec >> 32) != REC_NULL_HI) {
+						resolve_record<LEVELS>(s_tile, s_bm, P.loss, P.elig, P.level, rec);
 					}
 				}
 				__syncthreads();
@@ -943,42 +947,123 @@ resolve_kernel(const ResolveParams P)
 			for (uint32_t q = warp; q < nlong; q += RS_THREADS / 32) {
 				const uint64_t* run = P.rec + s_off[q];
 				const uint32_t len = s_len[q];
-				for (uint32_t x = lane; x < len; x += 32) resolve_record<LEVELS>(s_tile, s_bm, P.loss, P.elig, ld_nc_u64(run + x));
+				for (uint32_t x = lane; x < len; x += 32) resolve_record<LEVELS>(s_tile, s_bm, P.loss, P.elig, P.level, ld_nc_u64(run + x));
 			}
 			__syncthreads();
+			if (LEVELS) {
+				has_records = has_records || staged != 0u || nlong != 0u;
+				stage_whole = nci <= (uint32_t)RS_THREADS && staged <= RS_ROUND && nlong == 0u && staged != 0u;
+				whole_extent = s_misc[1];
+			}
 		}
 
-		if (LEVELS && !tile_ready) {
-			// a bucket without a single run: nothing changes (counters not yet written are all zero)
-			if (!use_cnt) {
-				uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
-				for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) cn[q * RS_THREADS + tid] = 0;
-			}
-		} else if (LEVELS) {
-			// winners of this level raise their slot's counter: level -> level + 1 (+ 2 for a weight-2 winner)
-			uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
-#pragma unroll
-			for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q) {
-				const uint4 t = reinterpret_cast<const uint4*>(s_tile)[q * RS_THREADS + tid];
-				const uint32_t tv[4] = {t.x, t.y, t.z, t.w};
-				const uint32_t o4 = use_cnt ? (uint32_t)cn[q * RS_THREADS + tid] : 0u;
-				uint32_t n4 = o4;
-#pragma unroll
-				for (int e = 0; e < 4; ++e) {
-					if (tv[e] != 0u && tv[e] != SLOT_EMPTY) {
-						const uint32_t nv = P.level + 2u - (tv[e] & 1u);
-						if (nv > 15u) *P.wrap_flag = 1u;
-						n4 = (n4 & ~(15u << (4 * e))) | ((nv & 15u) << (4 * e));
+		if (LEVELS) {
+			if (tile_ready) {
+				if (stage_whole) {
+					// the usual case: the winners are found by one more pass over the staged records; they are
+					// blanked (a winner is not eligible at any higher level) before the dense copy leaves
+					for (uint32_t e = tid; e < whole_extent; e += RS_THREADS) {
+						const uint64_t rec = s_stage[e];
+						if ((uint32_t)(rec >> 32) != REC_NULL_HI && settle_winner(s_tile, s_bm, P.level, P.wrap_flag, rec)) s_stage[e] = REC_NULL;
+					}
+				} else if (has_records) {
+					// several rounds / long runs: sweep the whole tile
+#pragma unroll 1
+					for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / RS_THREADS); ++q) {
+						const uint32_t slot = q * RS_THREADS + tid;
+						const uint32_t t = s_tile[slot];
+						if (t != SLOT_EMPTY) {
+							const uint32_t w = 2u - (t & 1u);
+							if (P.level + w > 15u) *P.wrap_flag = 1u;
+							else atomicAdd(&s_bm[slot >> 3], w << ((slot & 7u) << 2));
+							s_tile[slot] = SLOT_EMPTY;
+						}
 					}
 				}
-				if (n4 != o4 || !use_cnt) cn[q * RS_THREADS + tid] = (uint16_t)n4;
+				fence_async_smem();
+				__syncthreads();
+				if (tid == 0) {
+					if (has_records) bulk_s2g(P.cnt + (uint64_t)b_cur * (FINAL_SLOTS / 4), s_bm, BM_WORDS * 4u);
+					if (P.level == 0 && P.dense && stage_whole) bulk_s2g(P.dense + (uint64_t)b_cur * STAGE_REC, s_stage, whole_extent * 8u);
+				}
+			}
+			if (P.level == 0 && P.dense && tid == 0) {
+				const bool dense_ok = tile_ready && stage_whole;
+				P.dense_len[b_cur] = dense_ok ? whole_extent : 0u;
+				if (!dense_ok && has_records) P.nd_list[atomicAdd(P.n_not_dense, 1u)] = b_cur;
 			}
 		} else {
 			// the bitmap now holds the earlier batches' bits plus every slot first touched here
-			P.touched[(uint64_t)b * (FINAL_SLOTS / 32) + tid] = s_bm[tid];
+			P.touched[(uint64_t)b_cur * (FINAL_SLOTS / 32) + tid] = s_bm[tid];
+			__syncthreads();
+		}
+	}
+	if (LEVELS && tid == 0) bulk_wait_all();
+}
+
+// Levels >= 1 of min_kmer_count > 1 for the buckets that have a dense copy (the usual case: every bucket whose
+// records fit one staging window): two bulk copies per bucket (records, counters) instead of ~256 small gathers, the
+// next bucket's copy is pulled into L2 meanwhile, nothing sweeps the whole tile, and the winners of this level are
+// blanked in the dense copy so that later levels drop them without an eligibility look-up.
+__global__ void __launch_bounds__(RS_THREADS, 1)
+resolve_dense_kernel(const ResolveParams P)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);                           // FINAL_SLOTS
+	uint64_t* s_stage = reinterpret_cast<uint64_t*>(s_tile + FINAL_SLOTS);              // STAGE_REC
+	unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_stage + STAGE_REC);
+	uint32_t* s_cn = reinterpret_cast<uint32_t*>(s_bar + 2);                            // FINAL_SLOTS / 8
+
+	const uint32_t tid = threadIdx.x;
+	if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init_fence(); }
+	{
+		const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY);
+#pragma unroll
+		for (uint32_t q = 0; q < (uint32_t)(FINAL_SLOTS / (4 * RS_THREADS)); ++q)
+			reinterpret_cast<uint4*>(s_tile)[q * RS_THREADS + tid] = e4;
+	}
+	__syncthreads();
+	uint32_t parity = 0;
+
+	uint32_t b = blockIdx.x;
+	uint32_t dlen_n = (b < P.n_buckets) ? P.dense_len[b] : 0u;
+	for (; b < P.n_buckets; b += gridDim.x) {
+		const uint32_t dlen = dlen_n;
+		uint64_t* seg = P.dense + (uint64_t)b * STAGE_REC;
+		uint16_t* cn = P.cnt + (uint64_t)b * (FINAL_SLOTS / 4);
+		if (dlen && tid == 0) {
+			// (the previous bucket's accesses to shared memory ended at its last barrier)
+			bulk_wait_read();
+			fence_async_smem();
+			mbar_arrive_expect_tx(&s_bar[0], dlen * 8u + (uint32_t)(FINAL_SLOTS / 2));
+			bulk_g2s(s_stage, seg, dlen * 8u, &s_bar[0]);
+			bulk_g2s(s_cn, cn, (uint32_t)(FINAL_SLOTS / 2), &s_bar[0]);
+		}
+		if (b + gridDim.x < P.n_buckets) {
+			const uint32_t bn = b + gridDim.x;
+			dlen_n = P.dense_len[bn];
+			if (tid * 16u < dlen_n) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.dense + (uint64_t)bn * STAGE_REC + tid * 16u));
+			if (dlen_n && tid < (uint32_t)(FINAL_SLOTS / 2 / 128))
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(P.cnt + (uint64_t)bn * (FINAL_SLOTS / 4)) + tid * 128u));
+		}
+		if (dlen == 0u) continue;          // block-uniform: gathered by resolve_kernel<true> (or empty)
+
+		mbar_wait(&s_bar[0], parity);
+		parity ^= 1u;
+		for (uint32_t e = tid; e < dlen; e += RS_THREADS) {
+			const uint64_t rec = s_stage[e];
+			if ((uint32_t)(rec >> 32) != REC_NULL_HI) resolve_record<true>(s_tile, s_cn, P.loss, P.elig, P.level, rec);
 		}
 		__syncthreads();
+		bool any = false;
+		for (uint32_t e = tid; e < dlen; e += RS_THREADS) {
+			const uint64_t rec = s_stage[e];
+			if ((uint32_t)(rec >> 32) != REC_NULL_HI && settle_winner(s_tile, s_cn, P.level, P.wrap_flag, rec)) { seg[e] = REC_NULL; any = true; }
+		}
+		fence_async_smem();
+		if (__syncthreads_or(any) && tid == 0) bulk_s2g(cn, s_cn, (uint32_t)(FINAL_SLOTS / 2));
 	}
+	if (tid == 0) bulk_wait_all();
 }
 
 // Between two levels: eligible at the next level <=> eligible at this one and no slot won (win nibble == 0).
