@@ -94,6 +94,9 @@ int kwg_bloom_num_valid(kwg_bloom_t* b, uint64_t* n);
  * May be called more than once (e.g. with different parameters). */
 int kwg_bloom_finalize(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* out_bits);
 int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* d_out_bits);
+/* kwg_bloom_finalize that also returns BitVector::crc32 of the filter bits (bloom.cpp:328-336: zlib crc32 seeded with 0),
+ * computed on the device while the bits travel to the host; replaces filter.update_crc32() (make_bloom.cpp:395). */
+int kwg_bloom_finalize_crc(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* out_bits, uint32_t* crc32);
 
 /* Forget everything added so far; keeps the allocations for the next accession. */
 int kwg_bloom_reset(kwg_bloom_t* b);
@@ -116,6 +119,19 @@ int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_fi
  * Runs on `stream` (a cudaStream_t, may be NULL) and does not synchronise. */
 int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitch, uint32_t n_filters,
 	uint64_t chunk_bits, uint8_t* d_dest, uint64_t dest_pitch, void* stream);
+/* kwg_transpose that also advances the two kinds of running zlib crc32 values build_db keeps, on the device:
+ *   filter_crc[j] : crc32_z(filter_crc[j], chunk of filter j)   -- build_db.cpp:281-282 (checked against the .bloom header, 321-333)
+ *   *dest_crc     : crc32_z(*dest_crc, dest, chunk_bits * ceil(n_filters/8))   -- build_db.cpp:307 (DBFileHeader::crc32)
+ * Either pointer may be NULL.  Needs chunk_bits % 32 == 0 and, for dest_crc, n_filters % 32 == 0 (messages made of
+ * 32-bit words); otherwise KWG_ERR_INVALID_ARG and the caller keeps the host crc32. */
+int kwg_transpose_crc(int device, const uint8_t* const* filter_chunks, uint32_t n_filters,
+	uint64_t chunk_bits, uint8_t* dest, uint32_t* filter_crc, uint32_t* dest_crc);
+
+/* zlib crc32(crc_in, message) of a message resident in HBM: n_rows rows of row_bytes bytes, row r at d_data + r*row_pitch
+ * (row_pitch == row_bytes or n_rows == 1: a flat buffer).  row_bytes, row_pitch and d_data multiples of 4.
+ * Runs on `stream`, synchronises it, writes the host word *crc_out. */
+int kwg_crc32_dev(int device, const uint8_t* d_data, uint64_t n_rows, uint64_t row_bytes, uint64_t row_pitch,
+	uint32_t crc_in, uint32_t* crc_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Search.  Replaces, inside search() (kwage.cpp:340): k-mer extraction 352-366, the per-k-mer

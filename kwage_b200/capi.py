@@ -23,9 +23,9 @@ KWG_ERR_STATE = -5
 EXPORTS = [
     "kwg_last_error", "kwg_version", "kwg_device_count", "kwg_launch_count",
     "kwg_bloom_create", "kwg_bloom_create_raw", "kwg_bloom_add_reads", "kwg_bloom_add_reads_dev",
-    "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_reset",
+    "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_finalize_crc", "kwg_bloom_reset",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
-    "kwg_transpose", "kwg_transpose_dev",
+    "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev",
     "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
     "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev", "kwg_synth_plant_dev",
@@ -77,6 +77,9 @@ def lib():
     L.kwg_bloom_stream.argtypes = [vp, pvp]
     L.kwg_transpose.argtypes = [i32, vp, u32, u64, vp]
     L.kwg_transpose_dev.argtypes = [i32, vp, u64, u32, u64, vp, u64, vp]
+    L.kwg_transpose_crc.argtypes = [i32, vp, u32, u64, vp, vp, vp]
+    L.kwg_crc32_dev.argtypes = [i32, vp, u64, u64, u64, u32, C.POINTER(u32), vp]
+    L.kwg_bloom_finalize_crc.argtypes = [vp, u32, u32, vp, C.POINTER(u32)]
     L.kwg_db_load.argtypes = [pvp, i32, vp, u32, u32, u32, u32, u32, u32]
     L.kwg_db_alloc.argtypes = [pvp, i32, u32, u32, u32, u32, u32, u32]
     L.kwg_db_upload_rows.argtypes = [vp, u64, u64, vp]
@@ -180,6 +183,15 @@ class BloomBuilder:
         check(lib().kwg_bloom_finalize(self.h, log2_len, num_hash, _np_ptr(out)))
         return out
 
+    def finalize_crc(self, log2_len=None, num_hash=None):
+        """-> (bits, zlib crc32 of the bits computed on the device)"""
+        if self.raw:
+            log2_len, num_hash = self.log2_len, self.num_hash
+        out = np.empty((1 << log2_len) // 8, dtype=np.uint8)
+        crc = C.c_uint32(0)
+        check(lib().kwg_bloom_finalize_crc(self.h, log2_len, num_hash, _np_ptr(out), C.byref(crc)))
+        return out, crc.value
+
     def finalize_ptr(self, log2_len, num_hash, out_ptr):
         check(lib().kwg_bloom_finalize(self.h, log2_len, num_hash, C.c_void_p(out_ptr)))
 
@@ -235,6 +247,26 @@ def transpose(filters, chunk_bits, *, device=0):
     dest = np.empty(chunk_bits * row, dtype=np.uint8)
     check(lib().kwg_transpose(device, ptrs, n, chunk_bits, _np_ptr(dest)))
     return dest.reshape(chunk_bits, row)
+
+
+def transpose_crc(filters, chunk_bits, filter_crc=None, dest_crc=None, *, device=0):
+    """kwg_transpose_crc: -> (slices, running per-filter crc32 array or None, running slice crc32 or None)"""
+    n = len(filters)
+    keep = [np.ascontiguousarray(f, dtype=np.uint8) for f in filters]
+    ptrs = (C.c_void_p * max(n, 1))(*[f.ctypes.data for f in keep])
+    row = (n + 7) // 8
+    dest = np.empty(chunk_bits * row, dtype=np.uint8)
+    fc = None if filter_crc is None else np.ascontiguousarray(filter_crc, dtype=np.uint32).copy()
+    dc = None if dest_crc is None else C.c_uint32(dest_crc)
+    check(lib().kwg_transpose_crc(device, ptrs, n, chunk_bits, _np_ptr(dest), None if fc is None else _np_ptr(fc),
+                                  None if dc is None else C.byref(dc)))
+    return dest.reshape(chunk_bits, row), fc, (None if dc is None else dc.value)
+
+
+def crc32_dev(d_ptr, n_rows, row_bytes, row_pitch, crc_in=0, *, device=0, stream=0):
+    out = C.c_uint32(0)
+    check(lib().kwg_crc32_dev(device, C.c_void_p(d_ptr), n_rows, row_bytes, row_pitch, crc_in, C.byref(out), C.c_void_p(stream)))
+    return out.value
 
 
 def transpose_dev(d_filters_ptr, filter_pitch, n_filters, chunk_bits, d_dest_ptr, dest_pitch, *, device=0, stream=0):

@@ -252,6 +252,8 @@ struct kwg_bloom {
 	size_t offsets_cap = 0;
 	uint32_t* d_start = nullptr;
 	size_t start_cap = 0;
+	uint32_t* d_crc_ws = nullptr; size_t crc_ws_cap = 0;   // kwg_bloom_finalize_crc
+	uint32_t* h_crc = nullptr;                             // pinned
 	KernelTimers timers;
 };
 
@@ -606,6 +608,8 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_counter);
 	if (b->h_counter) cudaFreeHost(b->h_counter);
 	cudaFree(b->d_filter);
+	cudaFree(b->d_crc_ws);
+	if (b->h_crc) cudaFreeHost(b->h_crc);
 	cudaFree(b->d_bases);
 	cudaFree(b->d_offsets);
 	cudaFree(b->d_start);
@@ -809,6 +813,40 @@ int kwg_bloom_finalize(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uin
 	if (rc) return rc;
 	KWG_CUDA(cudaMemcpyAsync(out_bits, b->d_filter, bytes, cudaMemcpyDeviceToHost, b->stream));
 	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	return KWG_OK;
+}
+
+int kwg_bloom_finalize_crc(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* out_bits, uint32_t* crc32)
+{
+	if (!b || !out_bits || !crc32) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	int rc = select_device(b->device);
+	if (rc) return rc;
+	if (log2_len < 5 || log2_len > 32) return fail(KWG_ERR_INVALID_ARG, "log2_len must be in [5,32]");
+	const size_t bytes = (size_t)1 << (log2_len - 3);
+	const uint8_t* d_bits = nullptr;
+	if (b->raw) {
+		if (log2_len != b->raw_L || num_hash != b->raw_nh) return fail(KWG_ERR_INVALID_ARG, "raw mode: parameters differ from creation");
+		d_bits = reinterpret_cast<const uint8_t*>(b->d_filter);
+	} else {
+		rc = grow((void**)&b->d_filter, &b->filter_cap, bytes);
+		if (rc) return rc;
+		rc = kwg_bloom_finalize_dev(b, log2_len, num_hash, reinterpret_cast<uint8_t*>(b->d_filter));
+		if (rc) return rc;
+		d_bits = reinterpret_cast<const uint8_t*>(b->d_filter);
+	}
+	const size_t ws_words = crc32_workspace_words(1, bytes) + 1;
+	rc = grow((void**)&b->d_crc_ws, &b->crc_ws_cap, ws_words * sizeof(uint32_t));
+	if (rc) return rc;
+	if (!b->h_crc) KWG_CUDA(cudaMallocHost(&b->h_crc, sizeof(uint32_t)));
+	// the checksum kernels read the filter while it is still warm in L2; the 4-byte result rides behind the bits
+	b->timers.begin(KWG_T_AUX, b->stream);
+	rc = crc32_launch(b->device, d_bits, 1, 0, 1, bytes, bytes, nullptr, b->d_crc_ws + ws_words - 1, b->d_crc_ws, b->stream);
+	b->timers.end(b->stream);
+	if (rc) return rc;
+	KWG_CUDA(cudaMemcpyAsync(out_bits, d_bits, bytes, cudaMemcpyDeviceToHost, b->stream));
+	KWG_CUDA(cudaMemcpyAsync(b->h_crc, b->d_crc_ws + ws_words - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	*crc32 = *b->h_crc;
 	return KWG_OK;
 }
 

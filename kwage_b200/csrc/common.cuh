@@ -70,6 +70,12 @@ struct KernelTimers {
 int select_device(int device);   // cudaSetDevice with validation
 int sm_count(int device);
 
+// crc32.cu: zlib crc32 of n_seg equal-length messages resident in HBM, queued on `stream` (no synchronisation).
+// Message s = n_rows rows of row_bytes at d_base + s * seg_stride + r * row_pitch; d_crc_in (NULL: 0) / d_crc_out: [n_seg].
+size_t crc32_workspace_words(uint64_t n_seg, uint64_t message_bytes);
+int crc32_launch(int device, const uint8_t* d_base, uint64_t n_seg, uint64_t seg_stride, uint64_t n_rows, uint64_t row_bytes,
+	uint64_t row_pitch, const uint32_t* d_crc_in, uint32_t* d_crc_out, uint32_t* d_ws, cudaStream_t stream);
+
 // ---------------------------------------------------------------- device: memory access helpers
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p)
 {

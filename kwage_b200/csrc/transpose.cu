@@ -110,12 +110,15 @@ int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitc
 	return transpose_launch(d_filters, filter_pitch, n_filters, chunk_bits, d_dest, dest_pitch, (cudaStream_t)stream);
 }
 
-int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest)
+static int transpose_host(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest,
+	uint32_t* filter_crc, uint32_t* dest_crc)
 {
 	if (!filter_chunks || !dest) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
 	if (n_filters == 0) return fail(KWG_ERR_INVALID_ARG, "n_filters must be > 0 (reference build_db.cpp:30-32)");
 	if (chunk_bits % 8) return fail(KWG_ERR_INVALID_ARG, "chunk_bits must be a multiple of 8 (reference build_db.cpp:238-243)");
 	if (chunk_bits == 0) return KWG_OK;
+	if ((filter_crc || dest_crc) && chunk_bits % 32) return fail(KWG_ERR_INVALID_ARG, "device crc32 needs chunk_bits % 32 == 0");
+	if (dest_crc && n_filters % 32) return fail(KWG_ERR_INVALID_ARG, "device crc32 of the slices needs n_filters % 32 == 0");
 	int rc = select_device(device);
 	if (rc) return rc;
 
@@ -131,15 +134,23 @@ int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_fi
 
 	cudaStream_t stream = nullptr;
 	uint8_t *d_in = nullptr, *d_out = nullptr;
+	uint32_t *d_crc = nullptr, *d_ws = nullptr;      // d_crc: [n_filters] running filter values, then the slice value
 	auto cleanup = [&]() {
 		if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
-		cudaFree(d_in); cudaFree(d_out);
+		cudaFree(d_in); cudaFree(d_out); cudaFree(d_crc); cudaFree(d_ws);
 	};
 #define KWG_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); \
 	return fail(_e == cudaErrorMemoryAllocation ? KWG_ERR_NO_MEMORY : KWG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
 	KWG_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 	KWG_TRY(cudaMalloc(&d_in, (size_t)n_filters * piece_pitch));
 	KWG_TRY(cudaMalloc(&d_out, (size_t)piece_bits * dest_pitch));
+	if (filter_crc || dest_crc) {
+		const size_t ws = std::max(crc32_workspace_words(n_filters, piece_bits / 8), crc32_workspace_words(1, piece_bits * row_bytes));
+		KWG_TRY(cudaMalloc(&d_ws, ws * sizeof(uint32_t)));
+		KWG_TRY(cudaMalloc(&d_crc, ((size_t)n_filters + 1) * sizeof(uint32_t)));
+		if (filter_crc) KWG_TRY(cudaMemcpyAsync(d_crc, filter_crc, (size_t)n_filters * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+		if (dest_crc) KWG_TRY(cudaMemcpyAsync(d_crc + n_filters, dest_crc, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+	}
 
 	for (uint64_t bit0 = 0; bit0 < chunk_bits; bit0 += piece_bits) {
 		const uint64_t bits = std::min(piece_bits, chunk_bits - bit0);
@@ -151,15 +162,37 @@ int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_fi
 			if (!filter_chunks[j]) { cleanup(); return fail(KWG_ERR_INVALID_ARG, "NULL filter chunk"); }
 			KWG_TRY(cudaMemcpyAsync(d_in + (uint64_t)j * piece_pitch, filter_chunks[j] + bit0 / 8, bytes, cudaMemcpyHostToDevice, stream));
 		}
+		if (filter_crc) {      // every filter's piece is one message of `bytes` bytes at d_in + j * piece_pitch
+			rc = crc32_launch(device, d_in, n_filters, piece_pitch, 1, bytes, bytes, d_crc, d_crc, d_ws, stream);
+			if (rc) { cleanup(); return rc; }
+		}
 		rc = transpose_launch(d_in, piece_pitch, n_filters, bits32, d_out, dest_pitch, stream);
 		if (rc) { cleanup(); return rc; }
+		if (dest_crc) {        // the slices of the piece: `bits` rows of row_bytes at dest_pitch, one running message
+			rc = crc32_launch(device, d_out, 1, 0, bits, row_bytes, dest_pitch, d_crc + n_filters, d_crc + n_filters, d_ws, stream);
+			if (rc) { cleanup(); return rc; }
+		}
 		KWG_TRY(cudaMemcpy2DAsync(dest + bit0 * row_bytes, row_bytes, d_out, dest_pitch, row_bytes, bits, cudaMemcpyDeviceToHost, stream));
 		KWG_TRY(cudaStreamSynchronize(stream));
 	}
 	(void)chunk_bytes;
+	if (filter_crc) KWG_TRY(cudaMemcpyAsync(filter_crc, d_crc, (size_t)n_filters * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	if (dest_crc) KWG_TRY(cudaMemcpyAsync(dest_crc, d_crc + n_filters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	if (filter_crc || dest_crc) KWG_TRY(cudaStreamSynchronize(stream));
 #undef KWG_TRY
 	cleanup();
 	return KWG_OK;
+}
+
+int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest)
+{
+	return transpose_host(device, filter_chunks, n_filters, chunk_bits, dest, nullptr, nullptr);
+}
+
+int kwg_transpose_crc(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest,
+	uint32_t* filter_crc, uint32_t* dest_crc)
+{
+	return transpose_host(device, filter_chunks, n_filters, chunk_bits, dest, filter_crc, dest_crc);
 }
 
 } // extern "C"

@@ -131,11 +131,17 @@ uint32_t crc32_bytes(uint32_t crc, const uint8_t* p, size_t n)
 
 void write_bloom_file(std::ostream& out, const BloomParam& param, const FilterInfo& info, const uint8_t* bits)
 {
+	const size_t nbytes = param.filter_len() / 8 + ((param.filter_len() % 8) ? 1 : 0);
+	write_bloom_file(out, param, info, bits, crc32_bytes((uint32_t)::crc32_z(0L, Z_NULL, 0), bits, nbytes));
+}
+
+// crc: BitVector::crc32 of the bits (bloom.cpp:328-336), e.g. from kwg_bloom_finalize_crc
+void write_bloom_file(std::ostream& out, const BloomParam& param, const FilterInfo& info, const uint8_t* bits, uint32_t crc)
+{
 	const std::streampos begin = out.tellp();
 	put(out, (unsigned char)KWAGE_BLOOM_MAGIC_IN_PROGRESS);
 	binary_write(out, param);
 	const size_t nbytes = param.filter_len() / 8 + ((param.filter_len() % 8) ? 1 : 0);
-	const uint32_t crc = crc32_bytes((uint32_t)::crc32_z(0L, Z_NULL, 0), bits, nbytes);
 	put(out, crc);
 	binary_write(out, info);
 	out.write(reinterpret_cast<const char*>(bits), (std::streamsize)nbytes);

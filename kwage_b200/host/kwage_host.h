@@ -121,6 +121,7 @@ void binary_read(std::istream& in, DBFileHeader& h);
 
 // .bloom writer/reader (reference binary_io.cpp:182-237): magic, param, crc32(bits), info, bits
 void write_bloom_file(std::ostream& out, const BloomParam& param, const FilterInfo& info, const uint8_t* bits);
+void write_bloom_file(std::ostream& out, const BloomParam& param, const FilterInfo& info, const uint8_t* bits, uint32_t crc);
 struct BloomFileHeader { BloomParam param; uint32_t crc32; FilterInfo info; std::streampos bits_start; };
 void read_bloom_header(std::istream& in, BloomFileHeader& h);   // leaves the stream at the first bit byte
 uint32_t crc32_bytes(uint32_t crc, const uint8_t* p, size_t n); // zlib crc32_z (bloom.cpp:328-336)

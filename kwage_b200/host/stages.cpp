@@ -183,7 +183,9 @@ unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAcc
 		}
 
 		std::vector<uint8_t> bits(param.filter_len() / 8 + ((param.filter_len() % 8) ? 1 : 0));
-		cuda_check(kwg_bloom_finalize(builder, param.log_2_filter_len, param.num_hash, bits.data()),
+		// the bits and their crc32 (filter.update_crc32(), make_bloom.cpp:395) both come from the device
+		uint32_t bits_crc = 0;
+		cuda_check(kwg_bloom_finalize_crc(builder, param.log_2_filter_len, param.num_hash, bits.data(), &bits_crc),
 			__FILE__ ":make_bloom_filter: kwg_bloom_finalize failed");
 		kwg_bloom_destroy(builder);
 		builder = NULL;
@@ -191,7 +193,7 @@ unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAcc
 		const std::string output_file = bloom_dir + "/" + accession_to_str(acc) + ".bloom";
 		std::ofstream fout(output_file.c_str(), std::ios::binary);
 		if (!fout) throw __FILE__ ":main: Unable to open Bloom filter file for writing";
-		write_bloom_file(fout, param, info, bits.data());
+		write_bloom_file(fout, param, info, bits.data(), bits_crc);
 		fout.close();
 	}
 	catch (const char* error) {
@@ -280,18 +282,27 @@ bool build_db(const std::string& filename, const BloomParam& param, const std::d
 		for (size_t i = 0; i < filter_len; i += max_buffer_slice) {
 			const size_t num_buffer_slice = std::min(max_buffer_slice, filter_len - i);
 			const size_t chunk_bytes = num_buffer_slice / 8 + ((num_buffer_slice % 8) ? 1 : 0);
+			// the running crc32 values (per source filter, build_db.cpp:281-282; of the slices, 307) are advanced on the
+			// device next to the transposition when the messages are made of whole 32-bit words, else by zlib here
+			const bool dev_filter_crc = num_buffer_slice % 32 == 0;
+			const bool dev_dest_crc = dev_filter_crc && num_filter % 32 == 0;
 			for (size_t j = 0; j < num_filter; ++j) {
 				uint8_t* p = src.data() + j * chunk_bytes;
 				fin[j]->read(reinterpret_cast<char*>(p), (std::streamsize)chunk_bytes);
 				if (!*fin[j]) throw __FILE__ ":build_db: Error reading filter bytes";
-				running_crc[j] = crc32_bytes(running_crc[j], p, chunk_bytes);
+				if (!dev_filter_crc) running_crc[j] = crc32_bytes(running_crc[j], p, chunk_bytes);
 				chunk_ptr[j] = p;
 			}
 			// the bitwise transposition at the heart of the bit-sliced approach (build_db.cpp:288-303)
-			cuda_check(kwg_transpose(g_build_db_device, chunk_ptr.data(), (uint32_t)num_filter, num_buffer_slice, dest.data()),
-				__FILE__ ":build_db: kwg_transpose failed");
 			const size_t curr_dest_len = num_buffer_slice * bytes_per_slice;
-			header.crc32 = crc32_bytes(header.crc32, dest.data(), curr_dest_len);
+			if (dev_filter_crc) {
+				cuda_check(kwg_transpose_crc(g_build_db_device, chunk_ptr.data(), (uint32_t)num_filter, num_buffer_slice, dest.data(),
+					running_crc.data(), dev_dest_crc ? &header.crc32 : NULL), __FILE__ ":build_db: kwg_transpose failed");
+			} else {
+				cuda_check(kwg_transpose(g_build_db_device, chunk_ptr.data(), (uint32_t)num_filter, num_buffer_slice, dest.data()),
+					__FILE__ ":build_db: kwg_transpose failed");
+			}
+			if (!dev_dest_crc) header.crc32 = crc32_bytes(header.crc32, dest.data(), curr_dest_len);
 			fout.write(reinterpret_cast<const char*>(dest.data()), (std::streamsize)curr_dest_len);
 			if (!fout) throw __FILE__ ":build_db: Unable to write transpose buffer to disk";
 		}
