@@ -256,7 +256,7 @@ def stage_construct(D, args, windows):
         bw.add_reads_ptr(h_bases[w].data_ptr(), h_offsets.data_ptr(), n_reads)
         n_valid = bw.num_valid()
         L, h = H.optimal_bloom_param(K, n_valid, P_FALSE, LMIN, LMAX)
-        bw.finalize_ptr(L, h, h_out[w].data_ptr())
+        bw.finalize_crc_ptr(L, h, h_out[w].data_ptr())      # bits + their crc32, what make_bloom_filter writes into the .bloom file
 
     def run_workers(per_worker):
         def loop(w):
@@ -406,6 +406,40 @@ def stage_transpose(D, args, windows):
                          "traffic": NCU_TRAFFIC["transpose_kernel"] if (n_filters, L) == (4096, 26) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
                          "algorithmic_bytes": 2 * bits // 8, "peak_source": peak_src},
             "gpu_launches": int(capi.launch_count() - launches0)}
+
+
+# ---------------------------------------------------------------------------------------------- checksums
+def stage_crc32(D, args, windows):
+    """zlib-compatible crc32 on the device (crc32.cu): the checksum of a 64 MiB filter (.bloom header) and of a 4 GiB
+    slice region (.db header)."""
+    torch = D.torch
+    from kwage_b200 import capi
+    peak, peak_src = measured_peaks()
+    res = {}
+    for name, n_bytes in (("filter_64MiB", 64 << 20), ("slices_4GiB", 4 << 30)):
+        buf = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+        capi.synth_filter_bits_dev(31 + D.rank, 0, 1, n_bytes, n_bytes, buf.data_ptr(), device=D.device)
+        st = torch.cuda.Stream()
+        capi.crc32_dev(buf.data_ptr(), 1, n_bytes, n_bytes, device=D.device, stream=st.cuda_stream)
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record(st)
+        for _ in range(reps):
+            crc = capi.crc32_dev(buf.data_ptr(), 1, n_bytes, n_bytes, device=D.device, stream=st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        windows.append((w0, time.time()))
+        sec = e0.elapsed_time(e1) / 1e3 / reps
+        res[name] = {"bytes": n_bytes, "ms": sec * 1e3, "GBps": n_bytes / sec / 1e9, "frac_of_hbm_peak": n_bytes / sec / 1e9 / peak, "crc32": crc}
+        del buf
+    big = res["slices_4GiB"]
+    return {"metric": "crc32 bytes/s", "value": D.world * big["bytes"] / (big["ms"] / 1e3), "unit": "bytes/s", "ms_per_step": big["ms"],
+            "e2e": {"value": D.world * big["bytes"] / (big["ms"] / 1e3), "unit": "bytes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                    "note": "the message is produced on the device (filter / slices); only the 4-byte checksum leaves"},
+            "roofline": {"bound": "hbm", "kernel": "crc_tile_kernel", "achieved": big["GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": big["GBps"] / peak, "traffic": None, "algorithmic_bytes": big["bytes"], "peak_source": peak_src},
+            "points": res}
 
 
 # ---------------------------------------------------------------------------------------------- search
@@ -565,7 +599,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--stages", default="construct,construct_c5,transpose,search")
+    ap.add_argument("--stages", default="construct,construct_c5,crc32,transpose,search")
     ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (handles) per GPU in the construct e2e arm")
     ap.add_argument("--reads", type=int, default=1000000, help="reads per accession (step)")
     ap.add_argument("--min-kmer-count", type=int, default=1, help="counting-filter threshold (reference default 5; needs --coverage)")
@@ -623,6 +657,8 @@ def main():
         a5.min_kmer_count, a5.coverage = 5, 30.0
         out["construct_c5"] = stage_construct(D, a5, windows)
         out["construct_c5"]["config"] = {"min_kmer_count": 5, "coverage": 30.0, "reads_per_accession": args.reads}
+    if "crc32" in stages:
+        out["crc32"] = stage_crc32(D, args, windows)
     if "transpose" in stages:
         out["transpose"] = stage_transpose(D, args, windows)
     if "search" in stages:

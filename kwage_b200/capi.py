@@ -192,6 +192,11 @@ class BloomBuilder:
         check(lib().kwg_bloom_finalize_crc(self.h, log2_len, num_hash, _np_ptr(out), C.byref(crc)))
         return out, crc.value
 
+    def finalize_crc_ptr(self, log2_len, num_hash, out_ptr):
+        crc = C.c_uint32(0)
+        check(lib().kwg_bloom_finalize_crc(self.h, log2_len, num_hash, C.c_void_p(out_ptr), C.byref(crc)))
+        return crc.value
+
     def finalize_ptr(self, log2_len, num_hash, out_ptr):
         check(lib().kwg_bloom_finalize(self.h, log2_len, num_hash, C.c_void_p(out_ptr)))
 
