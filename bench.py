@@ -408,6 +408,75 @@ def stage_transpose(D, args, windows):
             "gpu_launches": int(capi.launch_count() - launches0)}
 
 
+# ---------------------------------------------------------------------------------------------- raw construction
+def stage_construct_raw(D, args, windows):
+    """Raw mode (north_star: canonical k-mers + multi-hash + atomicOr into an L2-resident filter; the reference's
+    ground-truth rig bloom_test.cpp:268-275): one accession of --reads reads, k=31, 3 hashes, 2^29 bits."""
+    torch = D.torch
+    from kwage_b200 import capi
+    n_reads, L, h = args.reads, 29, 3
+    n_bases = n_reads * READ_LEN
+    kmers = n_reads * (READ_LEN - K + 1)
+    dev = D.device
+    pool = 4
+    d_bases = [torch.empty(n_bases + 16, dtype=torch.uint8, device="cuda") for _ in range(pool)]
+    d_offsets = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
+    for i in range(pool):
+        capi.synth_reads_dev(22345 + D.rank * 100000 + i, 0, n_reads, READ_LEN, d_bases[i].data_ptr(), d_offsets.data_ptr(), device=dev)
+    d_out = torch.empty((1 << L) // 8, dtype=torch.uint8, device="cuda")
+    b = capi.BloomBuilder(K, device=dev, raw_num_hash=h, raw_log2_len=L)
+
+    def step_dev(i):
+        b.reset()
+        b.add_reads_dev(d_bases[i % pool].data_ptr(), d_offsets.data_ptr(), n_reads, n_bases)
+        b.finalize_dev(L, h, d_out.data_ptr())
+
+    for i in range(3):
+        step_dev(i)
+    b.sync()
+    b.set_timing(True)
+    b.get_timing()
+    launches0 = capi.launch_count()
+    steps = max(args.steps, 5)
+    sec = timed(D, b.stream(), step_dev, steps, 0, windows)
+    launches = capi.launch_count() - launches0
+    ms, nl = b.get_timing()
+    b.set_timing(False)
+    t_scan = float(ms[capi.T_SCAN_A]) / steps / 1e3
+
+    h_bases = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
+    h_bases.copy_(d_bases[0][:n_bases])
+    h_offsets = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
+    h_offsets.copy_(d_offsets)
+    h_out = torch.empty((1 << L) // 8, dtype=torch.uint8).pin_memory()
+
+    def step_host(i):
+        b.reset()
+        b.add_reads_ptr(h_bases.data_ptr(), h_offsets.data_ptr(), n_reads)
+        b.finalize_crc_ptr(L, h, h_out.data_ptr())
+
+    sec_e2e = timed(D, b.stream(), step_host, steps, 1, windows)
+    b.close()
+    del d_bases, d_out
+    torch.cuda.empty_cache()
+    peak, peak_src = measured_peaks()
+    n = D.world
+    # algorithmic HBM bytes: the bases and the read-start bitmap in, the filter cleared once and copied out once; the
+    # 3 bit sets per k-mer are L2 atomics on a 64 MiB filter that never leaves the 126 MB L2
+    alg = n_bases * (1 + 1 / 8) + 2 * (1 << L) / 8
+    return {"metric": "Bloom k-mer inserts/s (raw mode)", "value": n * kmers * steps / sec, "unit": "kmer_inserts/s", "ms_per_step": sec / steps * 1e3,
+            "config": {"reads_per_accession": n_reads, "kmer_len": K, "num_hash": h, "log2_filter_len": L},
+            "e2e": {"value": n * kmers * steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
+                    "d2h_bytes_per_step": (1 << L) // 8 + 4, "ms_per_step": sec_e2e / steps * 1e3},
+            "gpu_launches": int(launches),
+            "l2_atomics_per_s": kmers * h / t_scan if t_scan > 0 else None,
+            "roofline": {"bound": "hbm", "kernel": "kmer_scan_kernel<RAW,3> (bound by L2 atomics and integer issue, not by HBM: see l2_atomics_per_s)",
+                         "achieved": alg / t_scan / 1e9 if t_scan > 0 else None, "peak": peak, "unit": "GB/s",
+                         "frac": alg / t_scan / 1e9 / peak if t_scan > 0 else None, "traffic": None, "algorithmic_bytes": alg,
+                         "peak_source": peak_src, "kernel_ms": t_scan * 1e3},
+            "kernel_ms_per_step": {"kmer_scan_raw": t_scan * 1e3}}
+
+
 # ---------------------------------------------------------------------------------------------- checksums
 def stage_crc32(D, args, windows):
     """zlib-compatible crc32 on the device (crc32.cu): the checksum of a 64 MiB filter (.bloom header) and of a 4 GiB
@@ -599,7 +668,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--stages", default="construct,construct_c5,crc32,transpose,search")
+    ap.add_argument("--stages", default="construct,construct_c5,construct_raw,crc32,transpose,search")
     ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (handles) per GPU in the construct e2e arm")
     ap.add_argument("--reads", type=int, default=1000000, help="reads per accession (step)")
     ap.add_argument("--min-kmer-count", type=int, default=1, help="counting-filter threshold (reference default 5; needs --coverage)")
@@ -657,6 +726,8 @@ def main():
         a5.min_kmer_count, a5.coverage = 5, 30.0
         out["construct_c5"] = stage_construct(D, a5, windows)
         out["construct_c5"]["config"] = {"min_kmer_count": 5, "coverage": 30.0, "reads_per_accession": args.reads}
+    if "construct_raw" in stages:
+        out["construct_raw"] = stage_construct_raw(D, args, windows)
     if "crc32" in stages:
         out["crc32"] = stage_crc32(D, args, windows)
     if "transpose" in stages:
