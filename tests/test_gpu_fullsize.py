@@ -70,3 +70,51 @@ def test_full_geometry_prefix_matches_oracle(accession):
         assert b.num_valid() == ob.num_valid()
         assert np.array_equal(b.finalize(26, 4), ob.finalize(26, 4))
     ob.close()
+
+
+# ------------------------------------------------------------------------------ min_kmer_count 5 (the reference default)
+@pytest.fixture(scope="module")
+def covered_accession():
+    """1e6 reads sampled from a 5 Mb random genome: ~30x coverage, so most k-mers pass the threshold of 5."""
+    genome = O.gen_reads(20260202, 0, 1, 5_000_000)
+    rng = np.random.default_rng(20260203)
+    starts = rng.integers(0, len(genome) - READ_LEN, N_READS)
+    bases = np.empty(N_READS * READ_LEN, np.uint8)
+    step = 100_000
+    for a in range(0, N_READS, step):
+        idx = starts[a: a + step, None] + np.arange(READ_LEN)[None, :]
+        bases[a * READ_LEN: (a + step) * READ_LEN] = genome[idx].reshape(-1)
+    offsets = np.arange(N_READS + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    return bases, offsets
+
+
+def test_full_size_min_count_5_is_split_invariant_and_matches_oracle_prefix(covered_accession):
+    bases, offsets = covered_accession
+    with capi.BloomBuilder(K, min_kmer_count=5, log2_count_len=30, log2_max_len=LMAX) as b:
+        b.add_reads(bases, offsets)
+        n_one = b.num_valid()
+        # every 31-mer of the genome seen at least 5 times turns valid exactly once: a little under 5e6 of them
+        assert 4_500_000 < n_one < 5_000_000
+        L, h = H.optimal_bloom_param(K, n_one, 0.25, 18, LMAX)
+        bits_one, crc = b.finalize_crc(L, h)
+        import zlib
+        assert crc == zlib.crc32(bits_one.tobytes())
+        # the counters of the first pass persist: the same reads again add nothing new (all counters are >= 5 or the
+        # k-mer stays below the threshold only if it still has fewer than 5 occurrences -- so count again from scratch)
+        b.reset()
+        cuts = [0, 3, 250_000, 250_001, 777_777, N_READS]
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            b.add_reads(bases, offsets[a: z + 1])
+        assert b.num_valid() == n_one
+        assert np.array_equal(b.finalize(L, h), bits_one)
+    # the full-size geometry on a prefix the oracle does in seconds, thresholds 2 and 5
+    n = 80_000
+    for c in (2, 5):
+        ob = O.Builder(K, c, 30, 26)
+        ob.add_reads(bases, offsets[: n + 1])
+        with capi.BloomBuilder(K, min_kmer_count=c, log2_count_len=30, log2_max_len=26) as b:
+            b.add_reads(bases, offsets[: n // 3 + 1])
+            b.add_reads(bases, offsets[n // 3: n + 1])
+            assert b.num_valid() == ob.num_valid()
+            assert np.array_equal(b.finalize(24, 3), ob.finalize(24, 3))
+        ob.close()
