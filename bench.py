@@ -485,6 +485,7 @@ def stage_crc32(D, args, windows):
     from kwage_b200 import capi
     peak, peak_src = measured_peaks()
     res = {}
+    launches0 = capi.launch_count()
     for name, n_bytes in (("filter_64MiB", 64 << 20), ("slices_4GiB", 4 << 30)):
         buf = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
         capi.synth_filter_bits_dev(31 + D.rank, 0, 1, n_bytes, n_bytes, buf.data_ptr(), device=D.device)
@@ -503,7 +504,7 @@ def stage_crc32(D, args, windows):
         res[name] = {"bytes": n_bytes, "ms": sec * 1e3, "GBps": n_bytes / sec / 1e9, "frac_of_hbm_peak": n_bytes / sec / 1e9 / peak, "crc32": crc}
         del buf
     big = res["slices_4GiB"]
-    return {"metric": "crc32 bytes/s", "value": D.world * big["bytes"] / (big["ms"] / 1e3), "unit": "bytes/s", "ms_per_step": big["ms"],
+    return {"gpu_launches": int(capi.launch_count() - launches0), "metric": "crc32 bytes/s", "value": D.world * big["bytes"] / (big["ms"] / 1e3), "unit": "bytes/s", "ms_per_step": big["ms"],
             "e2e": {"value": D.world * big["bytes"] / (big["ms"] / 1e3), "unit": "bytes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
                     "note": "the message is produced on the device (filter / slices); only the 4-byte checksum leaves"},
             "roofline": {"bound": "hbm", "kernel": "crc_tile_kernel", "achieved": big["GBps"], "peak": peak, "unit": "GB/s",
