@@ -334,21 +334,30 @@ int kwg_crc32_dev(int device, const uint8_t* d_data, uint64_t n_rows, uint64_t r
 	int rc = select_device(device);
 	if (rc) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
-	uint32_t* d_ws = nullptr;
+	// grow-only workspace per device; the call synchronises its stream before returning, so holding the lock for the
+	// whole call is what keeps concurrent callers on one device apart
+	struct Ws { uint32_t* p = nullptr; size_t words = 0; uint32_t* h = nullptr; };
+	static std::mutex mu;
+	static std::vector<Ws> cache;
+	std::lock_guard<std::mutex> lock(mu);
+	if ((int)cache.size() <= device) cache.resize(device + 1);
+	Ws& W = cache[device];
 	const size_t words = crc32_workspace_words(1, n_rows * row_bytes) + 2;
-	KWG_CUDA(cudaMalloc(&d_ws, words * sizeof(uint32_t)));
-	uint32_t* d_io = d_ws + words - 2;
-	cudaError_t e = cudaMemcpyAsync(d_io, &crc_in, sizeof(uint32_t), cudaMemcpyHostToDevice, st);
-	if (e == cudaSuccess) {
-		rc = crc32_launch(device, d_data, 1, 0, n_rows, row_bytes, row_pitch, d_io, d_io + 1, d_ws, st);
-		if (rc == KWG_OK) {
-			e = cudaMemcpyAsync(crc_out, d_io + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-		}
+	if (words > W.words) {
+		if (W.p) KWG_CUDA(cudaFree(W.p));
+		W.p = nullptr; W.words = 0;
+		KWG_CUDA(cudaMalloc(&W.p, (words + words / 4) * sizeof(uint32_t)));
+		W.words = words + words / 4;
 	}
-	cudaFree(d_ws);
+	if (!W.h) KWG_CUDA(cudaMallocHost(&W.h, 2 * sizeof(uint32_t)));
+	uint32_t* d_io = W.p + W.words - 2;
+	W.h[0] = crc_in;
+	KWG_CUDA(cudaMemcpyAsync(d_io, W.h, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	rc = crc32_launch(device, d_data, 1, 0, n_rows, row_bytes, row_pitch, d_io, d_io + 1, W.p, st);
 	if (rc) return rc;
-	if (e != cudaSuccess) return fail(KWG_ERR_CUDA, std::string("kwg_crc32_dev: ") + cudaGetErrorString(e));
+	KWG_CUDA(cudaMemcpyAsync(W.h + 1, d_io + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	KWG_CUDA(cudaStreamSynchronize(st));
+	*crc_out = W.h[1];
 	return KWG_OK;
 }
 

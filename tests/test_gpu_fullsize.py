@@ -118,3 +118,44 @@ def test_full_size_min_count_5_is_split_invariant_and_matches_oracle_prefix(cove
             assert b.num_valid() == ob.num_valid()
             assert np.array_equal(b.finalize(24, 3), ob.finalize(24, 3))
         ob.close()
+
+
+# ------------------------------------------------------------------------------ more than 2^28 start positions in one call
+@pytest.mark.parametrize("c", [1, 3])
+def test_device_batch_longer_than_one_sub_batch(c):
+    """kwg_bloom_add_reads_dev cuts a batch into sub-batches of 2^28 start positions (a touch record carries a 28-bit
+    position); reads straddle the cut and the counting-filter state has to carry over.  The same 3.3e8 bases delivered in
+    one call and in three calls cut elsewhere must give the same filter."""
+    import torch
+    n_reads, glen = 2_200_000, 40_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4711)
+    genome = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")[torch.randint(0, 4, (glen,), generator=g, device="cuda")]
+    starts = torch.randint(0, glen - READ_LEN, (n_reads,), generator=g, device="cuda")
+    bases = torch.empty(n_reads * READ_LEN + 16, dtype=torch.uint8, device="cuda")
+    for a in range(0, n_reads, 100_000):
+        z = min(n_reads, a + 100_000)
+        idx = starts[a:z, None] + torch.arange(READ_LEN, device="cuda")[None, :]
+        bases[a * READ_LEN: z * READ_LEN] = genome[idx].reshape(-1)
+    del genome, idx
+    offsets = torch.arange(n_reads + 1, dtype=torch.int64, device="cuda") * READ_LEN
+    n_bases = n_reads * READ_LEN
+    assert n_bases > (1 << 28) and (1 << 28) % READ_LEN != 0          # the cut falls inside a read
+    lc = H.counting_filter_log2_len(n_bases)
+    torch.cuda.synchronize()
+    with capi.BloomBuilder(K, min_kmer_count=c, log2_count_len=lc, log2_max_len=LMAX) as b:
+        b.add_reads_dev(bases.data_ptr(), offsets.data_ptr(), n_reads, n_bases)
+        n_one = b.num_valid()
+        L, h = H.optimal_bloom_param(K, n_one, 0.25, 18, LMAX)
+        bits_one = b.finalize(L, h)
+        b.reset()
+        cuts = [0, 700_000, 1_500_008, n_reads]          # (device pointers must stay 16-byte aligned: multiples of 8 reads)
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            off = (offsets[a: z + 1] - offsets[a]).contiguous()
+            assert (a * READ_LEN) % 16 == 0
+            b.add_reads_dev(bases.data_ptr() + a * READ_LEN, off.data_ptr(), z - a, (z - a) * READ_LEN)
+        b.sync()
+        assert b.num_valid() == n_one
+        assert np.array_equal(b.finalize(L, h), bits_one)
+    # ~8x coverage: with c = 1 every distinct 31-mer of the covered genome counts once, with c = 3 those seen 3 times
+    assert (3.0e7 < n_one < 4.1e7) if c == 1 else (1.5e7 < n_one < 4.0e7)
