@@ -127,6 +127,11 @@ int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitc
 int kwg_transpose_crc(int device, const uint8_t* const* filter_chunks, uint32_t n_filters,
 	uint64_t chunk_bits, uint8_t* dest, uint32_t* filter_crc, uint32_t* dest_crc);
 
+/* Page-locked host memory for the staging buffers of the calls above (filter chunks, slices, read batches): the
+ * library's copies then run at PCIe rate and overlap with its kernels.  Optional: any host pointer works. */
+void* kwg_host_alloc(uint64_t bytes);
+void kwg_host_free(void* p);
+
 /* zlib crc32(crc_in, message) of a message resident in HBM: n_rows rows of row_bytes bytes, row r at d_data + r*row_pitch
  * (row_pitch == row_bytes or n_rows == 1: a flat buffer).  row_bytes, row_pitch and d_data multiples of 4.
  * Runs on `stream`, synchronises it, writes the host word *crc_out. */

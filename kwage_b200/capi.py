@@ -25,7 +25,7 @@ EXPORTS = [
     "kwg_bloom_create", "kwg_bloom_create_raw", "kwg_bloom_add_reads", "kwg_bloom_add_reads_dev",
     "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_finalize_crc", "kwg_bloom_reset",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
-    "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev",
+    "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev", "kwg_host_alloc", "kwg_host_free",
     "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
     "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev", "kwg_synth_plant_dev",
@@ -79,6 +79,10 @@ def lib():
     L.kwg_transpose_dev.argtypes = [i32, vp, u64, u32, u64, vp, u64, vp]
     L.kwg_transpose_crc.argtypes = [i32, vp, u32, u64, vp, vp, vp]
     L.kwg_crc32_dev.argtypes = [i32, vp, u64, u64, u64, u32, C.POINTER(u32), vp]
+    L.kwg_host_alloc.argtypes = [u64]
+    L.kwg_host_alloc.restype = vp
+    L.kwg_host_free.argtypes = [vp]
+    L.kwg_host_free.restype = None
     L.kwg_bloom_finalize_crc.argtypes = [vp, u32, u32, vp, C.POINTER(u32)]
     L.kwg_db_load.argtypes = [pvp, i32, vp, u32, u32, u32, u32, u32, u32]
     L.kwg_db_alloc.argtypes = [pvp, i32, u32, u32, u32, u32, u32, u32]

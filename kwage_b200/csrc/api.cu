@@ -65,4 +65,20 @@ int kwg_device_count(int* count)
 
 uint64_t kwg_launch_count(void) { return kwg::g_launches.load(); }
 
+void* kwg_host_alloc(uint64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+		cudaGetLastError();
+		kwg::set_error("kwg_host_alloc: cudaMallocHost failed");
+		return nullptr;
+	}
+	return p;
+}
+
+void kwg_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
 } // extern "C"

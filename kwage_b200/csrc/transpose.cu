@@ -8,6 +8,9 @@
 // sectors of four rows.  Pure HBM streaming: 1 bit read + 1 bit written per bit moved.
 #include "common.cuh"
 
+#include <cstdlib>
+#include <mutex>
+
 #include <algorithm>
 #include <vector>
 
@@ -110,6 +113,16 @@ int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitc
 	return transpose_launch(d_filters, filter_pitch, n_filters, chunk_bits, d_dest, dest_pitch, (cudaStream_t)stream);
 }
 
+struct TransposeCache {
+	cudaStream_t stream[2] = {nullptr, nullptr};
+	cudaEvent_t crc_done[2] = {nullptr, nullptr};
+	uint8_t* d_in[2] = {nullptr, nullptr};
+	uint8_t* d_out[2] = {nullptr, nullptr};
+	uint32_t* d_ws[2] = {nullptr, nullptr};
+	uint32_t* d_crc = nullptr;
+	size_t in_cap[2] = {0, 0}, out_cap[2] = {0, 0}, ws_cap[2] = {0, 0}, crc_cap = 0;
+};
+
 static int transpose_host(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest,
 	uint32_t* filter_crc, uint32_t* dest_crc)
 {
@@ -126,61 +139,101 @@ static int transpose_host(int device, const uint8_t* const* filter_chunks, uint3
 	const uint64_t dest_pitch = round_up(row_bytes, 16);
 	const uint64_t chunk_bytes = chunk_bits / 8;
 
-	// Work through the slice axis in pieces that keep the staging buffers bounded (<= ~1 GiB each).
-	const uint64_t budget = 1ull << 30;
+	// The slice axis is worked through in pieces of ~128 MiB on TWO lanes (stream + staging buffers each): while one
+	// piece is transposed and copied back, the next one is already coming in -- the two copy directions and the
+	// kernel overlap.  The running crc32 values chain from piece to piece through an event.
+	uint64_t budget = 128ull << 20;
+	if (const char* e = getenv("KWG_TR_BUDGET_MIB")) budget = (uint64_t)atoll(e) << 20;      // experiment knob
 	uint64_t piece_bits = std::max<uint64_t>(1024, (budget / std::max<uint64_t>(n_filters / 8, 16)) & ~1023ull);
 	piece_bits = std::min(piece_bits, round_up(chunk_bits, 32));
 	const uint64_t piece_pitch = round_up(piece_bits / 8, 16);
+	const int n_lanes = (chunk_bits > piece_bits && !getenv("KWG_TR_ONE_LANE")) ? 2 : 1;
+	for (uint32_t j = 0; j < n_filters; ++j)
+		if (!filter_chunks[j]) return fail(KWG_ERR_INVALID_ARG, "NULL filter chunk");
+	size_t src_stride = 0;                           // != 0: filter_chunks[j] == filter_chunks[0] + j * src_stride
+	if (n_filters > 1 && filter_chunks[1] > filter_chunks[0] && (size_t)(filter_chunks[1] - filter_chunks[0]) >= chunk_bytes) {
+		src_stride = (size_t)(filter_chunks[1] - filter_chunks[0]);
+		for (uint32_t j = 2; j < n_filters && src_stride; ++j)
+			if (filter_chunks[j] != filter_chunks[0] + (size_t)j * src_stride) src_stride = 0;
+	}
+	const bool want_crc = filter_crc || dest_crc;
 
-	cudaStream_t stream = nullptr;
-	uint8_t *d_in = nullptr, *d_out = nullptr;
-	uint32_t *d_crc = nullptr, *d_ws = nullptr;      // d_crc: [n_filters] running filter values, then the slice value
-	auto cleanup = [&]() {
-		if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
-		cudaFree(d_in); cudaFree(d_out); cudaFree(d_crc); cudaFree(d_ws);
+	// Streams and staging buffers live in a per-device cache that only grows: build_db calls this once per chunk, and
+	// allocating / releasing gigabytes per call costs anything from 10 to 400 ms.  The lock is held for the whole call
+	// (it synchronises before returning), which is what keeps concurrent callers on one device apart.
+	static std::mutex mu;
+	static std::vector<TransposeCache> caches;
+	std::lock_guard<std::mutex> lock(mu);
+	if ((int)caches.size() <= device) caches.resize(device + 1);
+	TransposeCache& C = caches[device];
+	cudaStream_t* stream = C.stream;
+	cudaEvent_t* crc_done = C.crc_done;
+	uint8_t** d_in = C.d_in;
+	uint8_t** d_out = C.d_out;
+	uint32_t** d_ws = C.d_ws;
+	auto cleanup = [&]() {            // after an error: drain whatever was queued
+		for (int l = 0; l < 2; ++l) if (stream[l]) cudaStreamSynchronize(stream[l]);
 	};
 #define KWG_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); \
 	return fail(_e == cudaErrorMemoryAllocation ? KWG_ERR_NO_MEMORY : KWG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
-	KWG_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-	KWG_TRY(cudaMalloc(&d_in, (size_t)n_filters * piece_pitch));
-	KWG_TRY(cudaMalloc(&d_out, (size_t)piece_bits * dest_pitch));
-	if (filter_crc || dest_crc) {
-		const size_t ws = std::max(crc32_workspace_words(n_filters, piece_bits / 8), crc32_workspace_words(1, piece_bits * row_bytes));
-		KWG_TRY(cudaMalloc(&d_ws, ws * sizeof(uint32_t)));
-		KWG_TRY(cudaMalloc(&d_crc, ((size_t)n_filters + 1) * sizeof(uint32_t)));
-		if (filter_crc) KWG_TRY(cudaMemcpyAsync(d_crc, filter_crc, (size_t)n_filters * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-		if (dest_crc) KWG_TRY(cudaMemcpyAsync(d_crc + n_filters, dest_crc, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+#define KWG_GROW(ptr, cap, need) do { if ((need) > (cap)) { if (ptr) KWG_TRY(cudaFree(ptr)); (ptr) = nullptr; (cap) = 0; \
+	KWG_TRY(cudaMalloc(&(ptr), (need))); (cap) = (need); } } while (0)
+	for (int l = 0; l < n_lanes; ++l) {
+		if (!stream[l]) KWG_TRY(cudaStreamCreateWithFlags(&stream[l], cudaStreamNonBlocking));
+		if (!crc_done[l]) KWG_TRY(cudaEventCreateWithFlags(&crc_done[l], cudaEventDisableTiming));
+		KWG_GROW(d_in[l], C.in_cap[l], (size_t)n_filters * piece_pitch);
+		KWG_GROW(d_out[l], C.out_cap[l], (size_t)piece_bits * dest_pitch);
+		if (want_crc) {
+			const size_t ws = std::max(crc32_workspace_words(n_filters, piece_bits / 8), crc32_workspace_words(1, piece_bits * row_bytes));
+			KWG_GROW(d_ws[l], C.ws_cap[l], ws * sizeof(uint32_t));
+		}
+	}
+	uint32_t*& d_crc = C.d_crc;                      // [n_filters] running filter values, then the slice value
+	if (want_crc) {
+		KWG_GROW(d_crc, C.crc_cap, ((size_t)n_filters + 1) * sizeof(uint32_t));
+		if (filter_crc) KWG_TRY(cudaMemcpyAsync(d_crc, filter_crc, (size_t)n_filters * sizeof(uint32_t), cudaMemcpyHostToDevice, stream[0]));
+		if (dest_crc) KWG_TRY(cudaMemcpyAsync(d_crc + n_filters, dest_crc, sizeof(uint32_t), cudaMemcpyHostToDevice, stream[0]));
 	}
 
-	for (uint64_t bit0 = 0; bit0 < chunk_bits; bit0 += piece_bits) {
+	uint64_t piece = 0;
+	for (uint64_t bit0 = 0; bit0 < chunk_bits; bit0 += piece_bits, ++piece) {
+		const int l = (int)(piece % n_lanes);
+		cudaStream_t st = stream[l];
 		const uint64_t bits = std::min(piece_bits, chunk_bits - bit0);
 		const uint64_t bytes = bits / 8;
 		const uint64_t bits32 = round_up(bits, 32);
-		if (bits32 != bits) KWG_TRY(cudaMemsetAsync(d_in, 0, (size_t)n_filters * piece_pitch, stream));
-		// one strided copy per filter: host pointers are unrelated
-		for (uint32_t j = 0; j < n_filters; ++j) {
-			if (!filter_chunks[j]) { cleanup(); return fail(KWG_ERR_INVALID_ARG, "NULL filter chunk"); }
-			KWG_TRY(cudaMemcpyAsync(d_in + (uint64_t)j * piece_pitch, filter_chunks[j] + bit0 / 8, bytes, cudaMemcpyHostToDevice, stream));
+		// (work queued on this lane two pieces ago has to be over before its buffers are filled again: stream order)
+		if (bits32 != bits) KWG_TRY(cudaMemsetAsync(d_in[l], 0, (size_t)n_filters * piece_pitch, st));
+		if (src_stride) {
+			// the caller's chunks are equally spaced (one staging buffer, as in build_db): ONE pitched copy per piece --
+			// a copy call costs ~20 us whatever its size, 2048 of them per piece would cost more than the transfer
+			KWG_TRY(cudaMemcpy2DAsync(d_in[l], piece_pitch, filter_chunks[0] + bit0 / 8, src_stride, bytes, n_filters, cudaMemcpyHostToDevice, st));
+		} else {
+			for (uint32_t j = 0; j < n_filters; ++j)
+				KWG_TRY(cudaMemcpyAsync(d_in[l] + (uint64_t)j * piece_pitch, filter_chunks[j] + bit0 / 8, bytes, cudaMemcpyHostToDevice, st));
 		}
+		// the running checksums of this piece continue those of the previous piece (other lane)
+		if (want_crc && piece > 0 && n_lanes == 2) KWG_TRY(cudaStreamWaitEvent(st, crc_done[1 - l], 0));
 		if (filter_crc) {      // every filter's piece is one message of `bytes` bytes at d_in + j * piece_pitch
-			rc = crc32_launch(device, d_in, n_filters, piece_pitch, 1, bytes, bytes, d_crc, d_crc, d_ws, stream);
+			rc = crc32_launch(device, d_in[l], n_filters, piece_pitch, 1, bytes, bytes, d_crc, d_crc, d_ws[l], st);
 			if (rc) { cleanup(); return rc; }
 		}
-		rc = transpose_launch(d_in, piece_pitch, n_filters, bits32, d_out, dest_pitch, stream);
+		rc = transpose_launch(d_in[l], piece_pitch, n_filters, bits32, d_out[l], dest_pitch, st);
 		if (rc) { cleanup(); return rc; }
 		if (dest_crc) {        // the slices of the piece: `bits` rows of row_bytes at dest_pitch, one running message
-			rc = crc32_launch(device, d_out, 1, 0, bits, row_bytes, dest_pitch, d_crc + n_filters, d_crc + n_filters, d_ws, stream);
+			rc = crc32_launch(device, d_out[l], 1, 0, bits, row_bytes, dest_pitch, d_crc + n_filters, d_crc + n_filters, d_ws[l], st);
 			if (rc) { cleanup(); return rc; }
 		}
-		KWG_TRY(cudaMemcpy2DAsync(dest + bit0 * row_bytes, row_bytes, d_out, dest_pitch, row_bytes, bits, cudaMemcpyDeviceToHost, stream));
-		KWG_TRY(cudaStreamSynchronize(stream));
+		if (want_crc) KWG_TRY(cudaEventRecord(crc_done[l], st));
+		KWG_TRY(cudaMemcpy2DAsync(dest + bit0 * row_bytes, row_bytes, d_out[l], dest_pitch, row_bytes, bits, cudaMemcpyDeviceToHost, st));
 	}
 	(void)chunk_bytes;
-	if (filter_crc) KWG_TRY(cudaMemcpyAsync(filter_crc, d_crc, (size_t)n_filters * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	if (dest_crc) KWG_TRY(cudaMemcpyAsync(dest_crc, d_crc + n_filters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	if (filter_crc || dest_crc) KWG_TRY(cudaStreamSynchronize(stream));
+	const int last = (int)((piece + n_lanes - 1) % n_lanes);
+	if (filter_crc) KWG_TRY(cudaMemcpyAsync(filter_crc, d_crc, (size_t)n_filters * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream[last]));
+	if (dest_crc) KWG_TRY(cudaMemcpyAsync(dest_crc, d_crc + n_filters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream[last]));
+	for (int l = 0; l < n_lanes; ++l) KWG_TRY(cudaStreamSynchronize(stream[l]));
+#undef KWG_GROW
 #undef KWG_TRY
-	cleanup();
 	return KWG_OK;
 }
 

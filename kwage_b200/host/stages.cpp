@@ -236,6 +236,24 @@ unsigned char make_bloom_filter(const SraAccession& acc, const FilterInfo& info,
 	}
 }
 
+// page-locked when the CUDA library can provide it, plain memory otherwise (the calls accept any host pointer)
+class PinnedBuffer {
+public:
+	explicit PinnedBuffer(size_t n) : p(NULL), pinned(true)
+	{
+		p = static_cast<uint8_t*>(kwg_host_alloc(n ? n : 1));
+		if (!p) { pinned = false; p = static_cast<uint8_t*>(malloc(n ? n : 1)); }
+		if (!p) throw __FILE__ ":build_db: Unable to allocate a staging buffer";
+	}
+	~PinnedBuffer() { if (pinned) kwg_host_free(p); else free(p); }
+	uint8_t* data() { return p; }
+private:
+	PinnedBuffer(const PinnedBuffer&);
+	PinnedBuffer& operator=(const PinnedBuffer&);
+	uint8_t* p;
+	bool pinned;
+};
+
 // ================================================================ transposition
 // Mirrors build_db() (reference build_db.cpp:24-456): same validation, same chunking of the slice
 // axis (4,194,304 slices per chunk, build_db.cpp:243), same CRC bookkeeping, same file layout.
@@ -274,8 +292,9 @@ bool build_db(const std::string& filename, const BloomParam& param, const std::d
 		const size_t filter_len = param.filter_len();
 		const size_t max_buffer_slice = size_t(524288) * 8;
 		const size_t bytes_per_slice = num_filter / 8 + ((num_filter % 8) ? 1 : 0);
-		std::vector<uint8_t> src(num_filter * (std::min(max_buffer_slice, filter_len) / 8 + 1));
-		std::vector<uint8_t> dest(std::min(max_buffer_slice, filter_len) * bytes_per_slice);
+		// staging buffers in page-locked memory: the transposition's copies run at PCIe rate and overlap its kernels
+		PinnedBuffer src(num_filter * (std::min(max_buffer_slice, filter_len) / 8 + 1));
+		PinnedBuffer dest(std::min(max_buffer_slice, filter_len) * bytes_per_slice);
 		std::vector<const uint8_t*> chunk_ptr(num_filter);
 		std::vector<uint32_t> running_crc(num_filter, 0);
 
