@@ -36,6 +36,11 @@ constexpr int TILE_VEC = TILE_LOAD / 16;         // 16-base groups per tile
 constexpr uint64_t LIST_CHUNK_LOG2 = 22;         // valid-word list grows in 32 MiB chunks
 constexpr uint64_t LIST_CHUNK = 1ull << LIST_CHUNK_LOG2;
 constexpr uint64_t MAX_BATCH_BASES = 1ull << 28; // host batches are cut at read boundaries near this
+// A filter of up to 2^29 bits (64 MiB) stays in the 126 MB L2 and takes ~2e11 red.or per second; a larger one lives in
+// HBM, where every bit set is a DRAM sector read-modify-write (2.6e10 /s, profiles/r1e_sweep.md).  Larger filters are
+// therefore filled one 64 MiB window at a time: every pass re-derives the hashes (cheap next to the atomics it saves)
+// and only sets the bits that fall into its window.
+constexpr uint32_t WINDOW_LOG2 = 29;
 
 enum ScanMode { MODE_RAW = 0, MODE_PASS_B = 2 };
 
@@ -47,6 +52,7 @@ struct ScanParams {
 	// raw
 	uint32_t* filter;
 	uint32_t filter_mask;
+	uint32_t win_id, n_win;      // filters beyond WINDOW_LOG2 bits: this launch only sets the bits of window win_id
 	// counting
 	uint64_t pos0;               // absolute base index of the first start position of this sub-batch
 	uint64_t n_pos;              // start positions in this sub-batch
@@ -124,9 +130,9 @@ kmer_scan_kernel(const ScanParams P)
 #pragma unroll
 				for (int s = 0; s < NH; ++s) {
 					const uint32_t bit = h[s] & P.filter_mask;
-					atomicOr(P.filter + (bit >> 5), 1u << (bit & 31));
+					if (P.n_win == 1 || (bit >> WINDOW_LOG2) == P.win_id) atomicOr(P.filter + (bit >> 5), 1u << (bit & 31));
 				}
-				++raw_local;
+				if (P.win_id == 0) ++raw_local;
 			}
 		} else {
 			const uint32_t lane = tid & 31;
@@ -185,7 +191,7 @@ __global__ void mark_read_starts_kernel(const uint64_t* __restrict__ offsets, ui
 template <int NH>
 __global__ void __launch_bounds__(256)
 insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint32_t k, uint32_t* __restrict__ filter,
-	uint32_t filter_mask)
+	uint32_t filter_mask, uint32_t win_id, uint32_t n_win)
 {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
@@ -196,7 +202,7 @@ insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint
 #pragma unroll
 		for (int s = 0; s < NH; ++s) {
 			const uint32_t bit = h[s] & filter_mask;
-			atomicOr(filter + (bit >> 5), 1u << (bit & 31));
+			if (n_win == 1 || (bit >> WINDOW_LOG2) == win_id) atomicOr(filter + (bit >> 5), 1u << (bit & 31));
 		}
 	}
 }
@@ -563,7 +569,10 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	if (b->raw) {
 		P.filter = b->d_filter;
 		P.filter_mask = (b->raw_L >= 32) ? 0xFFFFFFFFu : ((1u << b->raw_L) - 1u);
-		return launch_scan<MODE_RAW>(b, P);
+		P.n_win = (b->raw_L > WINDOW_LOG2 && !getenv("KWG_NO_WINDOWS")) ? 1u << (b->raw_L - WINDOW_LOG2) : 1u;
+		for (P.win_id = 0; P.win_id < P.n_win; ++P.win_id)
+			if ((rc = launch_scan<MODE_RAW>(b, P))) return rc;
+		return KWG_OK;
 	}
 
 	// counting mode: sub-batches of at most 2^28 start positions (a record carries a 28-bit position)
@@ -783,13 +792,16 @@ int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 		const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n_valid, 256), (uint64_t)sm_count(b->device) * 16);
 		uint32_t* f = reinterpret_cast<uint32_t*>(d_out_bits);
 		b->timers.begin(KWG_T_INSERT, b->stream);
-		switch (num_hash) {
-#define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_valid, b->k, f, mask); break;
-			KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5)
-#undef KWG_CASE
+#define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_valid, b->k, f, mask, w, n_win); break;
+		const uint32_t n_win = (log2_len > WINDOW_LOG2 && !getenv("KWG_NO_WINDOWS")) ? 1u << (log2_len - WINDOW_LOG2) : 1u;
+		for (uint32_t w = 0; w < n_win; ++w) {
+			switch (num_hash) {
+				KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5)
+			}
+			KWG_LAUNCHED();
 		}
+#undef KWG_CASE
 		b->timers.end(b->stream);
-		KWG_LAUNCHED();
 	}
 	return KWG_OK;
 }

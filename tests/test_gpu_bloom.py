@@ -17,7 +17,7 @@ def ragged_case(seed, n_reads=400, max_len=170, n_rate=37, lower_rate=5):
 
 
 @pytest.mark.parametrize("k,nh,L", [(31, 3, 20), (31, 1, 12), (21, 5, 18), (32, 4, 22), (1, 2, 8), (4, 8, 10), (15, 7, 16),
-                                    (25, 3, 26), (31, 3, 29), (17, 2, 32)])
+                                    (25, 3, 26), (31, 3, 29), (17, 2, 32), (31, 3, 30), (21, 5, 31)])
 def test_raw_insert_bit_exact(k, nh, L):
     bases, offsets = ragged_case(1000 + k * 7 + nh)
     exp, n = O.raw_insert(bases, offsets, k, nh, L)
@@ -116,6 +116,22 @@ def test_counting_mode_finalize_any_parameters_equals_fold():
         assert b.num_valid() == ob.num_valid()
         for L, h in [(18, 1), (19, 5), (22, 3), (26, 2)]:
             assert np.array_equal(b.finalize(L, h), ob.finalize(L, h)), (L, h)
+    ob.close()
+
+
+def test_filters_beyond_one_l2_window_are_filled_window_by_window():
+    # filters of more than 2^29 bits are filled one 64 MiB window per pass (raw scan and counting-mode finalize alike)
+    case = dict(S.MAKE_BLOOM_CASES["uniform_k31"])
+    bases, offsets = S.make_bloom_reads(case)
+    lc = O.counting_log2_len(case["num_bp"])
+    ob = O.Builder(case["k"], 1, lc, 32)
+    ob.add_reads(bases, offsets)
+    with capi.BloomBuilder(case["k"], min_kmer_count=1, log2_count_len=lc, log2_max_len=32) as b:
+        b.add_reads(bases, offsets)
+        for L, h in [(30, 3), (32, 5)]:
+            got = b.finalize(L, h)
+            assert np.array_equal(got, ob.finalize(L, h)), (L, h)
+            del got
     ob.close()
 
 
