@@ -166,6 +166,13 @@ int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer
 int kwg_db_alloc(kwg_db_t** out, int device, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len,
 	uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end);
 int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
+/* Several database files as one column slab (the reference keeps <= 2048 filters per file: 256-byte rows; wide rows gather
+ * at three times the HBM rate).  After kwg_db_alloc(n_filters_total = sum of the files' filters, 0, n_filters_total):
+ * rows [row_begin, row_begin + n_rows) of a file with n_cols filters -- n_rows * ceil(n_cols/8) host bytes, exactly the
+ * file's slice region -- go to the columns [col_begin, col_begin + n_cols) of the slab; any bit offset.  Each column range
+ * may be written once (bits are OR-ed into the zero-initialised slab).  Hits then carry slab column indices. */
+int kwg_db_upload_columns(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
+
 /* Use slices that are already in HBM (e.g. written by kwg_transpose_dev); row k at
  * d_slices + k*row_pitch, row_pitch % 16 == 0, bits >= n_filters in a row must be zero.
  * The memory is borrowed, not owned. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_finalize_crc", "kwg_bloom_reset",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
     "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev", "kwg_host_alloc", "kwg_host_free",
-    "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
+    "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_upload_columns", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
     "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev", "kwg_synth_plant_dev",
     "kwg_bloom_set_timing", "kwg_bloom_get_timing", "kwg_db_set_timing", "kwg_db_get_timing",
@@ -87,6 +87,7 @@ def lib():
     L.kwg_db_load.argtypes = [pvp, i32, vp, u32, u32, u32, u32, u32, u32]
     L.kwg_db_alloc.argtypes = [pvp, i32, u32, u32, u32, u32, u32, u32]
     L.kwg_db_upload_rows.argtypes = [vp, u64, u64, vp]
+    L.kwg_db_upload_columns.argtypes = [vp, u32, u32, u64, u64, vp]
     L.kwg_db_attach_dev.argtypes = [pvp, i32, vp, u64, u32, u32, u32, u32]
     L.kwg_db_unload.argtypes = [vp]
     L.kwg_db_unload.restype = None
@@ -307,6 +308,18 @@ class Database:
         h = C.c_void_p()
         check(lib().kwg_db_alloc(C.byref(h), device, kmer_len, num_hash, log2_len, n_filters_total, col_begin, col_end))
         return cls(h, col_end - col_begin, col_begin)
+
+    @classmethod
+    def alloc(cls, kmer_len, num_hash, log2_len, n_filters, *, device=0):
+        h = C.c_void_p()
+        check(lib().kwg_db_alloc(C.byref(h), device, kmer_len, num_hash, log2_len, n_filters, 0, n_filters))
+        return cls(h, n_filters)
+
+    def upload_columns(self, col_begin, n_cols, row_begin, rows):
+        """rows: (n_rows, ceil(n_cols/8)) uint8 = a file's slices -> columns [col_begin, col_begin + n_cols) of the slab"""
+        r = np.ascontiguousarray(rows, dtype=np.uint8)
+        assert r.shape[1] == (n_cols + 7) // 8
+        check(lib().kwg_db_upload_columns(self.h, col_begin, n_cols, row_begin, r.shape[0], _np_ptr(r)))
 
     def upload_rows(self, row_begin, rows):
         r = np.ascontiguousarray(rows, dtype=np.uint8)

@@ -471,6 +471,60 @@ int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const 
 	return KWG_OK;
 }
 
+// ---- several database files as ONE column slab
+// The reference keeps at most 2048 filters per .db file (options.h:137-138): rows of 256 bytes.  A gather of 256-byte rows
+// reaches a third of the HBM rate a gather of >= 1 KiB rows does (profiles/r1e_sweep.md), so files with the same (k, hashes,
+// length) are laid side by side in one slab: file f owns the columns [col_begin_f, col_begin_f + n_f) of every row.
+__global__ void __launch_bounds__(256)
+place_columns_kernel(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t n_cols, uint32_t col_begin, uint64_t n_rows,
+	uint32_t* __restrict__ slab, uint64_t slab_pitch_words, uint32_t w0, uint32_t n_words)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_rows * n_words) return;
+	const uint64_t row = i / n_words;
+	const uint32_t w = w0 + (uint32_t)(i % n_words);
+	const uint32_t lo = max(32u * w, col_begin), hi = min(32u * w + 32u, col_begin + n_cols);      // destination bits of this word
+	const uint32_t s = lo - col_begin, n = hi - lo;                                                // source bits [s, s + n)
+	const uint8_t* p = src + row * src_pitch;
+	const uint32_t b0 = s >> 3, b1 = (s + n - 1) >> 3;
+	uint64_t v = 0;
+	for (uint32_t b = b0; b <= b1; ++b) v |= (uint64_t)p[b] << (8 * (b - b0));                    // at most 5 bytes
+	uint32_t bits = (uint32_t)(v >> (s & 7u));
+	if (n < 32) bits &= (1u << n) - 1u;
+	bits <<= (lo & 31u);
+	if (bits) atomicOr(slab + row * slab_pitch_words + w, bits);
+}
+
+int kwg_db_upload_columns(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
+{
+	if (!db || !rows) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	if (!db->owns_slab || db->n_filters_total == 0) return fail(KWG_ERR_STATE, "handle was not created by kwg_db_alloc");
+	if (n_cols == 0 || (uint64_t)col_begin + n_cols > db->n_filters) return fail(KWG_ERR_INVALID_ARG, "column range outside the slab");
+	if (row_begin + n_rows > (1ull << db->log2_len)) return fail(KWG_ERR_INVALID_ARG, "row range outside the filter");
+	if (n_rows == 0) return KWG_OK;
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	const uint64_t src_pitch = ceil_div(n_cols, 8);
+	if (col_begin % 8 == 0 && n_cols % 8 == 0) {
+		// whole bytes: a pitched copy straight into the rows
+		KWG_CUDA(cudaMemcpy2DAsync(db->slab + row_begin * db->row_pitch + col_begin / 8, db->row_pitch, rows, src_pitch, src_pitch, n_rows,
+			cudaMemcpyHostToDevice, db->stream));
+	} else {
+		// any bit offset: stage the piece, then OR its bits into place (the slab starts out all zero)
+		rc = grow_db((void**)&db->d_bases, &db->bases_cap, (size_t)(n_rows * src_pitch));
+		if (rc) return rc;
+		KWG_CUDA(cudaMemcpyAsync(db->d_bases, rows, (size_t)(n_rows * src_pitch), cudaMemcpyHostToDevice, db->stream));
+		const uint32_t w0 = col_begin / 32, n_words = (col_begin + n_cols - 1) / 32 - w0 + 1;
+		const uint64_t total = n_rows * n_words;
+		if (ceil_div(total, 256) > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "piece too large: upload fewer rows per call");
+		place_columns_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, db->stream>>>(reinterpret_cast<const uint8_t*>(db->d_bases), src_pitch, n_cols,
+			col_begin, n_rows, reinterpret_cast<uint32_t*>(db->slab + row_begin * db->row_pitch), db->row_pitch / 4, w0, n_words);
+		KWG_LAUNCHED();
+	}
+	KWG_CUDA(cudaStreamSynchronize(db->stream));   // the caller may reuse `rows`
+	return KWG_OK;
+}
+
 int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer_len, uint32_t num_hash,
 	uint32_t log2_len, uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end)
 {

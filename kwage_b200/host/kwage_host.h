@@ -195,7 +195,16 @@ struct MatchResult {                     // reference output.h:9-33
 class SubjectDatabase {
 public:
 	explicit SubjectDatabase(const std::string& filename, int device = 0);
+	// Several database files with the same (kmer_len, num_hash, log_2_filter_len, hash_func) side by side in ONE column
+	// slab: the reference keeps <= 2048 filters per file (options.h:137-138), i.e. 256-byte slices, and wide slices are
+	// gathered three times faster.  Filter indices of the slab run through the files in the order given; header() is the
+	// first file's with num_filter = the sum.  Throws if the files do not agree.
+	explicit SubjectDatabase(const std::vector<std::string>& filenames, int device = 0);
 	~SubjectDatabase();
+	// can these files share a slab?  (reads the two headers)
+	static bool compatible(const std::string& file_a, const std::string& file_b);
+	// bytes of HBM the slices of this file need as part of a slab
+	static uint64_t slab_bytes(const std::string& filename);
 	const DBFileHeader& header() const { return hdr; }
 	// Batched form of search(): all queries against this file in one pass over the device.
 	// Returns true if any query matched.  results[query_id] gets one MatchResult per matching filter.
@@ -205,7 +214,9 @@ public:
 private:
 	SubjectDatabase(const SubjectDatabase&);
 	SubjectDatabase& operator=(const SubjectDatabase&);
-	std::ifstream fin;
+	void open_files(const std::vector<std::string>& filenames, int device);
+	struct Part { std::ifstream* fin; DBFileHeader hdr; uint32_t col_begin; };
+	std::vector<Part> parts;     // one per file, in column order
 	DBFileHeader hdr;
 	kwg_db_t* db;
 };

@@ -106,6 +106,8 @@ int usage()
 		"\t-d <database search path> (can be repeated)\n"
 		"\t[-i <input sequence file>] (can be repeated)\n"
 		"\t[--device <CUDA device>] (default is 0)\n"
+		"\t[--max-slab-gib <GiB>] (database files with equal Bloom parameters share one slab in HBM up to this size;\n"
+		"\t\t0 = one file at a time; default is 48)\n"
 		"\t[<DNA sequence>] (can be repeated)\n";
 	return EXIT_FAILURE;
 }
@@ -118,6 +120,7 @@ int main(int argc, char* argv[])
 		SearchOptions opt;
 		std::string output_file;
 		std::deque<std::string> db_paths, query_files, query_seq;
+		double max_slab_gib = 48.0;
 		for (int i = 1; i < argc; ++i) {
 			const std::string a = argv[i];
 			if (a == "-o" && i + 1 < argc) output_file = argv[++i];
@@ -127,6 +130,7 @@ int main(int argc, char* argv[])
 			else if (a == "-d" && i + 1 < argc) db_paths.push_back(argv[++i]);
 			else if (a == "-i" && i + 1 < argc) query_files.push_back(argv[++i]);
 			else if (a == "--device" && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+			else if (a == "--max-slab-gib" && i + 1 < argc) max_slab_gib = std::atof(argv[++i]);
 			else if (a == "-h" || a == "-?") return usage();
 			else if (!a.empty() && a[0] == '-') { std::cerr << '"' << a << "\" is not a valid option!" << std::endl; return usage(); }
 			else query_seq.push_back(a);
@@ -148,10 +152,22 @@ int main(int argc, char* argv[])
 		for (size_t i = 0; i < file_ids.size(); ++i) file_ids[i] = i;
 
 		std::unordered_map<size_t, std::deque<MatchResult> > cmd_results, file_results;
-		for (size_t f = 0; f < subject_files.size(); ++f) {          // one database file resident in HBM at a time
-			SubjectDatabase subject(subject_files[f], opt.device);
+		// consecutive files with equal Bloom parameters share one column slab in HBM (one pass of wide rows instead of
+		// one pass of 256-byte rows per file); the match set is the same either way
+		const uint64_t max_slab_bytes = (uint64_t)(max_slab_gib * 1073741824.0);
+		for (size_t f = 0; f < subject_files.size();) {
+			std::vector<std::string> group(1, subject_files[f]);
+			uint64_t bytes = SubjectDatabase::slab_bytes(subject_files[f]);
+			size_t g = f + 1;
+			while (g < subject_files.size() && SubjectDatabase::compatible(subject_files[f], subject_files[g]) &&
+			       bytes + SubjectDatabase::slab_bytes(subject_files[g]) <= max_slab_bytes) {
+				bytes += SubjectDatabase::slab_bytes(subject_files[g]);
+				group.push_back(subject_files[g++]);
+			}
+			SubjectDatabase subject(group, opt.device);
 			subject.search(cmd_results, cmd_seqs, cmd_ids, opt);
 			subject.search(file_results, file_seqs, file_ids, opt);
+			f = g;
 		}
 		for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = cmd_results.begin(); i != cmd_results.end(); ++i)
 			std::sort(i->second.begin(), i->second.end());

@@ -353,39 +353,112 @@ bool build_db(const std::string& filename, const BloomParam& param, const std::d
 }
 
 // ================================================================ search
-SubjectDatabase::SubjectDatabase(const std::string& filename, int device) : fin(filename.c_str(), std::ios::binary), db(NULL)
+static void read_db_header(std::ifstream& fin, DBFileHeader& h)
 {
 	if (!fin) throw __FILE__ ":main: I/O error";
-	binary_read(fin, hdr);
+	binary_read(fin, h);
 	if (!fin) throw __FILE__ ":main: Unable to read header";
-	if (hdr.magic != KWAGE_MAGIC_NUMBER) throw __FILE__ ":main: Not a KWAGE database file";
-	const size_t slice_size = hdr.num_filter / 8 + ((hdr.num_filter % 8) ? 1 : 0);
-	cuda_check(kwg_db_alloc(&db, device, hdr.kmer_len, hdr.num_hash, hdr.log_2_filter_len, hdr.num_filter, 0, hdr.num_filter),
-		__FILE__ ":search: kwg_db_alloc failed");
-	// stream the slice region into HBM in bounded pieces (the region can exceed host memory)
-	const uint64_t n_rows = 1ULL << hdr.log_2_filter_len;
-	const uint64_t piece_rows = std::max<uint64_t>(1, (uint64_t(256) << 20) / std::max<size_t>(slice_size, 1));
-	std::vector<uint8_t> buf((size_t)(std::min(piece_rows, n_rows) * slice_size));
-	for (uint64_t r = 0; r < n_rows; r += piece_rows) {
-		const uint64_t rows = std::min(piece_rows, n_rows - r);
-		fin.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(rows * slice_size));
-		if (!fin) { kwg_db_unload(db); db = NULL; throw __FILE__ ":search: Error reading slice from file (1)"; }
-		const int rc = kwg_db_upload_rows(db, r, rows, buf.data());
-		if (rc != KWG_OK) { kwg_db_unload(db); db = NULL; cuda_check(rc, __FILE__ ":search: kwg_db_upload_rows failed"); }
+	if (h.magic != KWAGE_MAGIC_NUMBER) throw __FILE__ ":main: Not a KWAGE database file";
+}
+
+SubjectDatabase::SubjectDatabase(const std::string& filename, int device) : db(NULL)
+{
+	open_files(std::vector<std::string>(1, filename), device);
+}
+
+SubjectDatabase::SubjectDatabase(const std::vector<std::string>& filenames, int device) : db(NULL)
+{
+	if (filenames.empty()) throw __FILE__ ":main: No database file";
+	open_files(filenames, device);
+}
+
+bool SubjectDatabase::compatible(const std::string& file_a, const std::string& file_b)
+{
+	try {
+		std::ifstream fa(file_a.c_str(), std::ios::binary), fb(file_b.c_str(), std::ios::binary);
+		DBFileHeader a, b;
+		read_db_header(fa, a);
+		read_db_header(fb, b);
+		return a.kmer_len == b.kmer_len && a.num_hash == b.num_hash && a.log_2_filter_len == b.log_2_filter_len &&
+		       a.hash_func == b.hash_func && a.compression == b.compression;
+	}
+	catch (...) { return false; }
+}
+
+uint64_t SubjectDatabase::slab_bytes(const std::string& filename)
+{
+	std::ifstream f(filename.c_str(), std::ios::binary);
+	DBFileHeader h;
+	read_db_header(f, h);
+	return (uint64_t(1) << h.log_2_filter_len) * (h.num_filter / 8 + 1);
+}
+
+void SubjectDatabase::open_files(const std::vector<std::string>& filenames, int device)
+{
+	try {
+		uint64_t total = 0;
+		for (size_t f = 0; f < filenames.size(); ++f) {
+			Part p;
+			p.fin = new std::ifstream(filenames[f].c_str(), std::ios::binary);
+			parts.push_back(p);
+			Part& q = parts.back();
+			read_db_header(*q.fin, q.hdr);
+			q.col_begin = (uint32_t)total;
+			total += q.hdr.num_filter;
+			const DBFileHeader& h0 = parts[0].hdr;
+			if (q.hdr.kmer_len != h0.kmer_len || q.hdr.num_hash != h0.num_hash || q.hdr.log_2_filter_len != h0.log_2_filter_len ||
+			    q.hdr.hash_func != h0.hash_func)
+				throw __FILE__ ":main: Database files with different Bloom parameters cannot share a slab";
+		}
+		if (total == 0 || total > 0xFFFFFFFFull) throw __FILE__ ":main: Bad number of filters";
+		hdr = parts[0].hdr;
+		hdr.num_filter = (uint32_t)total;
+		cuda_check(kwg_db_alloc(&db, device, hdr.kmer_len, hdr.num_hash, hdr.log_2_filter_len, hdr.num_filter, 0, hdr.num_filter),
+			__FILE__ ":search: kwg_db_alloc failed");
+		// stream every file's slice region into its columns in bounded pieces (a region can exceed host memory)
+		const uint64_t n_rows = 1ULL << hdr.log_2_filter_len;
+		for (size_t f = 0; f < parts.size(); ++f) {
+			Part& q = parts[f];
+			const size_t slice_size = q.hdr.num_filter / 8 + ((q.hdr.num_filter % 8) ? 1 : 0);
+			const uint64_t piece_rows = std::max<uint64_t>(1, (uint64_t(256) << 20) / std::max<size_t>(slice_size, 1));
+			std::vector<uint8_t> buf((size_t)(std::min(piece_rows, n_rows) * slice_size));
+			for (uint64_t r = 0; r < n_rows; r += piece_rows) {
+				const uint64_t rows = std::min(piece_rows, n_rows - r);
+				q.fin->read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(rows * slice_size));
+				if (!*q.fin) throw __FILE__ ":search: Error reading slice from file (1)";
+				const int rc = (parts.size() == 1) ? kwg_db_upload_rows(db, r, rows, buf.data())
+				                                   : kwg_db_upload_columns(db, q.col_begin, q.hdr.num_filter, r, rows, buf.data());
+				cuda_check(rc, __FILE__ ":search: kwg_db_upload failed");
+			}
+		}
+	}
+	catch (...) {
+		if (db) { kwg_db_unload(db); db = NULL; }
+		for (size_t f = 0; f < parts.size(); ++f) delete parts[f].fin;
+		parts.clear();
+		throw;
 	}
 }
 
-SubjectDatabase::~SubjectDatabase() { if (db) kwg_db_unload(db); }
+SubjectDatabase::~SubjectDatabase()
+{
+	if (db) kwg_db_unload(db);
+	for (size_t f = 0; f < parts.size(); ++f) delete parts[f].fin;
+}
 
 FilterInfo SubjectDatabase::filter_info(uint32_t filter)
 {
-	fin.clear();
-	fin.seekg((std::streamoff)(hdr.info_start + (uint64_t)filter * sizeof(uint64_t)));
+	size_t f = 0;
+	while (f + 1 < parts.size() && filter >= parts[f + 1].col_begin) ++f;      // the file that owns this column
+	Part& q = parts[f];
+	const uint32_t local = filter - q.col_begin;
+	q.fin->clear();
+	q.fin->seekg((std::streamoff)(q.hdr.info_start + (uint64_t)local * sizeof(uint64_t)));
 	uint64_t loc = 0;
-	fin.read(reinterpret_cast<char*>(&loc), sizeof(loc));
-	fin.seekg((std::streamoff)loc);
+	q.fin->read(reinterpret_cast<char*>(&loc), sizeof(loc));
+	q.fin->seekg((std::streamoff)loc);
 	FilterInfo info;
-	binary_read(fin, info);
+	binary_read(*q.fin, info);
 	return info;
 }
 

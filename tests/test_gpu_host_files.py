@@ -145,6 +145,46 @@ def test_kwage_cli_matches_reference_output(name, tmp_path):
         assert strip(ref.stdout) == strip(r.stdout)
 
 
+def test_kwage_cli_several_files_share_one_slab(tmp_path):
+    # a directory of .db files with equal Bloom parameters (uneven filter counts: any bit offset) is searched as ONE column
+    # slab by default and file by file with --max-slab-gib 0; both must print the same matches, and so must the reference
+    k, L, h = 31, 14, 3
+    widths = [13, 64, 21]
+    dbs, j = [], 0
+    dbdir = tmp_path / "dbs"
+    dbdir.mkdir()
+    for fi, w in enumerate(widths):
+        files = []
+        for _ in range(w):
+            path = str(tmp_path / (util.fixture_accession(j) + ".bloom"))
+            bases, offsets = S.uniform_reads(900 + j, 0, 40, 120)
+            bits, _ = O.raw_insert(bases, offsets, k, h, L)
+            H.write_bloom_file(path, util.fixture_accession(j), k, L, h, bits)
+            files.append(path)
+            j += 1
+        db = str(dbdir / ("part%d.db" % fi))
+        assert H.build_db(db, k, L, h, files)
+        dbs.append(db)
+    fa = str(tmp_path / "q.fa")
+    with open(fa, "w") as f:
+        for acc in (0, 12, 13, 76, 77, 97):                    # first / last filters of every file
+            bases, _ = S.uniform_reads(900 + acc, 0, 2, 120)
+            f.write(">from_%d\n%s\n" % (acc, bytes(bases).decode()))
+        f.write(">random\n%s\n" % bytes(O.gen_reads(1, 0, 1, 500)).decode())
+    outs = []
+    for extra in ([], ["--max-slab-gib", "0"]):
+        r = subprocess.run([H.KWAGE_BIN, "-d", str(dbdir), "-i", fa, "-t", "0.5", "--o.csv"] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(parse_csv(r.stdout))
+    assert outs[0] == outs[1] and len(outs[0]) >= 6
+    found = {(q, acc) for q, _, _, acc in outs[0]}
+    for acc in (0, 12, 13, 76, 77, 97):
+        assert ("from_%d" % acc, util.fixture_accession(acc)) in found
+    if O.have_ref():
+        ref = O.ref_kwage(["-d", str(dbdir), "-i", fa, "-t", "0.5", "--o.csv"], omp_threads=1)
+        assert ref.returncode == 0 and parse_csv(ref.stdout) == outs[0]
+
+
 def test_kwage_cli_errors():
     r = subprocess.run([H.KWAGE_BIN, "-i", "nothing.fa"], capture_output=True, text=True)
     assert r.returncode != 0 and "database" in r.stderr

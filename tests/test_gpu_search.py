@@ -108,3 +108,33 @@ def test_search_bad_arguments():
         capi.Database.load(dbd["slices"], 33, 3, dbd["L"], dbd["n"])
     with pytest.raises(capi.KwageError):
         capi.Database.load(dbd["slices"], 31, 3, dbd["L"], dbd["n"], col_begin=4, col_end=64)
+
+
+# ------------------------------------------------------------------------------ several files as one column slab
+@pytest.mark.parametrize("widths", [[13, 64, 21], [8, 2048, 5, 3], [2048, 2048], [1, 1, 30, 33, 7]])
+def test_files_side_by_side_in_one_slab_search_like_one_database(widths):
+    # kwg_db_upload_columns lays the slice regions of several files (any filter counts -> any bit offsets) side by side;
+    # counts and hits must equal those of a database built from all the filters at once
+    k, h, L = 25, 3, 12
+    total = sum(widths)
+    filters = [O.gen_filter_bits(4242, j, (1 << L) // 8) for j in range(total)]
+    all_slices = O.transpose(filters, 1 << L)
+    queries = [bytes(O.gen_reads(5 + i, 0, 1, 200 + 37 * i)).decode() for i in range(6)]
+    with capi.Database.load(all_slices, k, h, L, total) as one:
+        exp_counts, exp_nk = one.search_counts(queries)
+        exp_hits, _ = one.search(queries, 0.3)
+    with capi.Database.alloc(k, h, L, total) as slab:
+        col = 0
+        for w in widths:
+            part = O.transpose(filters[col: col + w], 1 << L)          # what this file's slice region holds
+            half = (1 << L) // 2 + 3
+            slab.upload_columns(col, w, 0, part[:half])                 # in two row pieces, like the streaming loader
+            slab.upload_columns(col, w, half, part[half:])
+            col += w
+        got_counts, got_nk = slab.search_counts(queries)
+        got_hits, _ = slab.search(queries, 0.3)
+    assert np.array_equal(got_nk, exp_nk) and np.array_equal(got_counts, exp_counts)
+    assert np.array_equal(got_hits, exp_hits)
+    with capi.Database.alloc(k, h, L, total) as slab:
+        with pytest.raises(capi.KwageError):
+            slab.upload_columns(total - 2, 5, 0, np.zeros((4, 1), np.uint8))    # column range outside the slab
