@@ -1,5 +1,6 @@
-// Counting-mode construction (reference make_bloom.cpp:506-621, min_kmer_count == 1) as a radix
-// partition of "touch" records followed by first-touch resolution in shared memory.
+// Counting-mode construction (reference make_bloom.cpp:506-621) as a radix partition of "touch" records
+// followed by first-touch resolution in shared memory: once for min_kmer_count == 1, once per counter
+// level for min_kmer_count > 1 (resolve_kernel<true>, resolve_dense_kernel, elig_update_kernel below).
 //
 // Why this shape (measured on B200, profiles/ubench): a random atomic into an HBM-resident table
 // runs at ~2.0e10 /s (DRAM sector read-modify-write), into an L2-resident table at ~1.3e11 /s, into
@@ -25,6 +26,10 @@
 //                              written back.
 //   pass B (kmer_scan_kernel)  occurrence is valid <=> loss counter < 4  (it is the first toucher of at
 //                              least one of its four slots, i.e. the reference read a zero counter).
+//   min_kmer_count = c > 1     K1/K2 as above, then K3 once per counter level v = 0 .. c-1 over the occurrences that
+//                              won nothing at the levels below (the derivation is at resolve_kernel); level 0 leaves a
+//                              dense copy of every bucket for the later levels, what persists between batches is the
+//                              4-bit counter of every slot, valid <=> eligible at level c-1 and a win there.
 //
 // All run/chunk positions are exact (prefix sums of counts): memory use is deterministic and heavy
 // duplication (poly-G reads, adapters) only makes one bucket longer, never overflows anything.
