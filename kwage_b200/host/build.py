@@ -25,7 +25,7 @@ def build(force=False):
     from kwage_b200 import build as kbuild
     kbuild.build()
     os.makedirs(BIN_DIR, exist_ok=True)
-    flags = ["-O2", "-std=c++11", "-Wall", "-fPIC"]
+    flags = ["-O2", "-std=c++11", "-Wall", "-fPIC", "-pthread"]
     link = ["-L" + LIB_DIR, "-lkwage_cuda", "-lz", "-Wl,-rpath," + LIB_DIR, "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,$ORIGIN"]
     common = [os.path.join(HERE, s) for s in COMMON]
     targets = [

@@ -3,12 +3,14 @@
 // --device <n>.  Output assembly follows kwage.cpp:189-319 (results sorted by num_kmers_found,
 // command-line sequences first, then file records by id).
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <dirent.h>
 #include <sstream>
 #include <sys/stat.h>
+#include <thread>
 #include <zlib.h>
 
 #include "kwage_host.h"
@@ -105,7 +107,8 @@ int usage()
 		"\t[-t <search threshold>] (default is 1)\n"
 		"\t-d <database search path> (can be repeated)\n"
 		"\t[-i <input sequence file>] (can be repeated)\n"
-		"\t[--device <CUDA device>] (default is 0)\n"
+		"\t[--device <CUDA device>] (default is 0; can be repeated or a comma separated list: the database files are\n"
+		"\t\tshared out over the devices, one host thread per device, like the reference's OpenMP loop over files)\n"
 		"\t[--max-slab-gib <GiB>] (database files with equal Bloom parameters share one slab in HBM up to this size;\n"
 		"\t\t0 = one file at a time; default is 48)\n"
 		"\t[<DNA sequence>] (can be repeated)\n";
@@ -121,6 +124,7 @@ int main(int argc, char* argv[])
 		std::string output_file;
 		std::deque<std::string> db_paths, query_files, query_seq;
 		double max_slab_gib = 48.0;
+		std::vector<int> devices;
 		for (int i = 1; i < argc; ++i) {
 			const std::string a = argv[i];
 			if (a == "-o" && i + 1 < argc) output_file = argv[++i];
@@ -129,7 +133,11 @@ int main(int argc, char* argv[])
 			else if (a == "-t" && i + 1 < argc) opt.threshold = (float)std::atof(argv[++i]);
 			else if (a == "-d" && i + 1 < argc) db_paths.push_back(argv[++i]);
 			else if (a == "-i" && i + 1 < argc) query_files.push_back(argv[++i]);
-			else if (a == "--device" && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+			else if (a == "--device" && i + 1 < argc) {
+				std::stringstream list(argv[++i]);
+				std::string item;
+				while (std::getline(list, item, ',')) if (!item.empty()) devices.push_back(std::atoi(item.c_str()));
+			}
 			else if (a == "--max-slab-gib" && i + 1 < argc) max_slab_gib = std::atof(argv[++i]);
 			else if (a == "-h" || a == "-?") return usage();
 			else if (!a.empty() && a[0] == '-') { std::cerr << '"' << a << "\" is not a valid option!" << std::endl; return usage(); }
@@ -155,6 +163,7 @@ int main(int argc, char* argv[])
 		// consecutive files with equal Bloom parameters share one column slab in HBM (one pass of wide rows instead of
 		// one pass of 256-byte rows per file); the match set is the same either way
 		const uint64_t max_slab_bytes = (uint64_t)(max_slab_gib * 1073741824.0);
+		std::vector<std::vector<std::string> > groups;
 		for (size_t f = 0; f < subject_files.size();) {
 			std::vector<std::string> group(1, subject_files[f]);
 			uint64_t bytes = SubjectDatabase::slab_bytes(subject_files[f]);
@@ -164,10 +173,40 @@ int main(int argc, char* argv[])
 				bytes += SubjectDatabase::slab_bytes(subject_files[g]);
 				group.push_back(subject_files[g++]);
 			}
-			SubjectDatabase subject(group, opt.device);
-			subject.search(cmd_results, cmd_seqs, cmd_ids, opt);
-			subject.search(file_results, file_seqs, file_ids, opt);
+			groups.push_back(group);
 			f = g;
+		}
+		// one host thread per device takes slabs off a shared counter (the reference: one OpenMP thread per file,
+		// kwage.cpp:76-87); every thread collects its matches privately and they are merged afterwards
+		if (devices.empty()) devices.push_back(opt.device);
+		const size_t n_workers = std::min(devices.size(), groups.size());
+		std::vector<std::unordered_map<size_t, std::deque<MatchResult> > > w_cmd(n_workers), w_file(n_workers);
+		std::vector<std::string> w_error(n_workers);
+		std::atomic<size_t> next(0);
+		std::vector<std::thread> workers;
+		for (size_t w = 0; w < n_workers; ++w) {
+			workers.push_back(std::thread([&, w]() {
+				try {
+					SearchOptions o = opt;
+					o.device = devices[w];
+					for (size_t gi = next.fetch_add(1); gi < groups.size(); gi = next.fetch_add(1)) {
+						SubjectDatabase subject(groups[gi], o.device);
+						subject.search(w_cmd[w], cmd_seqs, cmd_ids, o);
+						subject.search(w_file[w], file_seqs, file_ids, o);
+					}
+				}
+				catch (const char* error) { w_error[w] = error; }
+				catch (const std::exception& error) { w_error[w] = error.what(); }
+				catch (...) { w_error[w] = "unhandled error"; }
+			}));
+		}
+		for (size_t w = 0; w < workers.size(); ++w) workers[w].join();
+		for (size_t w = 0; w < n_workers; ++w) {
+			if (!w_error[w].empty()) { std::cerr << "Caught the error " << w_error[w] << std::endl; return EXIT_FAILURE; }
+			for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = w_cmd[w].begin(); i != w_cmd[w].end(); ++i)
+				cmd_results[i->first].insert(cmd_results[i->first].end(), i->second.begin(), i->second.end());
+			for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = w_file[w].begin(); i != w_file[w].end(); ++i)
+				file_results[i->first].insert(file_results[i->first].end(), i->second.begin(), i->second.end());
 		}
 		for (std::unordered_map<size_t, std::deque<MatchResult> >::iterator i = cmd_results.begin(); i != cmd_results.end(); ++i)
 			std::sort(i->second.begin(), i->second.end());
