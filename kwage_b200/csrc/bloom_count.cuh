@@ -891,6 +891,14 @@ resolve_kernel(const ResolveParams P)
 			}
 
 			for (uint32_t r0 = 0; r0 < staged || r0 == 0; r0 += RS_ROUND) {
+				if (r0) {
+					// A run that overhung the previous window may have carried the staged records to their end: then no
+					// run starts in this window, nobody below sets the extent, and the PREVIOUS window would be resolved a
+					// second time (every record of the bucket one loss too many).  Found by the randomised soak
+					// (profiles/dbg/stress_levels.py); regression: tests/test_gpu_bloom.py::test_staged_records_end_in_an_overhang.
+					if (tid == 0) s_misc[1] = 0;
+					__syncthreads();
+				}
 				const bool mine = span && so >= r0 && so < r0 + RS_ROUND;
 				if (mine && (so + span >= r0 + RS_ROUND || so + span == staged)) s_misc[1] = so + span - r0;
 				if (staged == 0 && tid == 0) s_misc[1] = 0;

@@ -182,6 +182,24 @@ def test_counting_mode_many_tiles_per_bucket(k, lc, n_reads):
     ob.close()
 
 
+@pytest.mark.parametrize("n_reads", [2400, 2500, 2600, 2700])
+def test_staged_records_end_in_an_overhang(n_reads):
+    # lc = 21: 128 buckets, one run of ~64 records per (bucket, tile) -- about half of them "long" (read directly), half
+    # staged.  Around 184 tiles the staged half of a bucket just exceeds one staging window; when the run that overhangs the
+    # window is the last one, the second round has nothing to stage and must resolve nothing (it used to resolve the first
+    # window again: 576 k-mers lost on this input).
+    case = dict(kind="coverage", seed=884924425, genome=200000, n_reads=4000, read_len=150, num_bp=-1)
+    bases, offsets = S.make_bloom_reads(case)
+    for c in (1, 2):
+        ob = O.Builder(31, c, 21, 24)
+        ob.add_reads(bases, offsets[: n_reads + 1])
+        with capi.BloomBuilder(31, min_kmer_count=c, log2_count_len=21, log2_max_len=24) as b:
+            b.add_reads(bases, offsets[: n_reads + 1])
+            assert b.num_valid() == ob.num_valid()
+            assert np.array_equal(b.finalize(24, 3), ob.finalize(24, 3))
+        ob.close()
+
+
 def test_counting_mode_small_filter_heavy_shadowing():
     # many more k-mers than counting slots: most first occurrences are shadowed by earlier k-mers, so
     # the stream-order rule (minimum position per slot, displacement of later occurrences) decides almost
