@@ -895,7 +895,7 @@ resolve_kernel(const ResolveParams P)
 					// A run that overhung the previous window may have carried the staged records to their end: then no
 					// run starts in this window, nobody below sets the extent, and the PREVIOUS window would be resolved a
 					// second time (every record of the bucket one loss too many).  Found by the randomised soak
-					// (profiles/dbg/stress_levels.py); regression: tests/test_gpu_bloom.py::test_staged_records_end_in_an_overhang.
+					// (tests/soak/stress_levels.py); regression: tests/test_gpu_bloom.py::test_staged_records_end_in_an_overhang.
 					if (tid == 0) s_misc[1] = 0;
 					__syncthreads();
 				}

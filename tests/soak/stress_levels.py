@@ -3,8 +3,8 @@ counting-filter lengths, batch splits and input mixes, for a fixed wall-clock bu
 this pool, so repeated randomised parity is what stands in for racecheck."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from kwage_b200 import capi
 from oracle import oracle_py as O
 import synth_cases as S

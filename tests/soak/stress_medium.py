@@ -2,8 +2,8 @@
 (several run-table passes and staging rounds), two-level geometries with real chunk counts, thresholds 1..5."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from kwage_b200 import capi
 from oracle import oracle_py as O
 import synth_cases as S

@@ -1,8 +1,8 @@
 """Randomised soak of transposition (+ device crc32), column slabs and search against the oracle / zlib."""
 import sys, time, os, zlib
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from kwage_b200 import capi
 from oracle import oracle_py as O
 
