@@ -11,9 +11,9 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 150.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 t0 = time.time(); n = 0
 while time.time() - t0 < budget:
-    c = int(rng.choice([1, 1, 2, 5]))
-    lc = int(rng.choice([19, 20, 21, 22, 23, 24, 25, 27]))
-    n_reads = int(rng.choice([8000, 30000, 60000, 100000]))
+    c = int(rng.choice([1, 1, 2, 3, 5, 9]))
+    lc = int(rng.choice([19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 30]))
+    n_reads = int(rng.choice([8000, 30000, 60000, 100000, 250000]))
     read_len = int(rng.choice([100, 150]))
     cov = float(rng.choice([1.5, 6.0, 20.0]))
     seed = int(rng.integers(1, 1 << 30))
