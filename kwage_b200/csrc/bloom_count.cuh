@@ -714,7 +714,8 @@ __device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
 // Returns true iff the record became the holder of its slot (LEVELS only): only such records can be winners in the end,
 // which is what lets the settle pass look at a handful of records per thread instead of all of them.
 template <bool LEVELS>
-__device__ __forceinline__ bool resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* acct, const uint32_t* elig, uint32_t level, uint64_t rec)
+__device__ __forceinline__ bool resolve_record(uint32_t* s_tile, uint32_t* s_bm, uint32_t* acct, const uint32_t* elig, uint32_t level, uint64_t rec,
+	bool have_word = false, uint32_t word = 0u)        // have_word: the caller already fetched elig[pos >> 5]
 {
 	const uint32_t slot = (uint32_t)(rec >> 32) & (FINAL_SLOTS - 1);
 	const uint32_t lo = (uint32_t)rec;
@@ -725,7 +726,8 @@ __device__ __forceinline__ bool resolve_record(uint32_t* s_tile, uint32_t* s_bm,
 		// s_bm holds the bucket's 4-bit counters here (8 slots per word)
 		if (*reinterpret_cast<volatile uint32_t*>(&s_tile[slot]) < v) return false;
 		if (((s_bm[slot >> 3] >> ((slot & 7u) << 2)) & 15u) > level) return false;      // the slot is already above this level
-		if (elig && !((__ldg(&elig[pos >> 5]) >> (pos & 31u)) & 1u)) return false;
+		if (have_word) { if (!((word >> (pos & 31u)) & 1u)) return false; }
+		else if (elig && !((__ldg(&elig[pos >> 5]) >> (pos & 31u)) & 1u)) return false;
 		const uint32_t old = atomicMin(&s_tile[slot], v);
 		if (old > v) {
 			atomicAdd(&acct[pos >> 3], (1u + dbl) << ((pos & 7u) << 2));
@@ -1036,7 +1038,7 @@ resolve_dense_kernel(const ResolveParams P)
 	uint32_t* s_cn = reinterpret_cast<uint32_t*>(s_bar + 2);                            // FINAL_SLOTS / 8
 
 	const uint32_t tid = threadIdx.x;
-	if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init_fence(); }
+	if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init_fence(); }
 	{
 		const uint4 e4 = make_uint4(SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY, SLOT_EMPTY);
 #pragma unroll
@@ -1056,9 +1058,14 @@ resolve_dense_kernel(const ResolveParams P)
 			// (the previous bucket's accesses to shared memory ended at its last barrier)
 			bulk_wait_read();
 			fence_async_smem();
-			mbar_arrive_expect_tx(&s_bar[0], dlen * 8u + (uint32_t)(FINAL_SLOTS / 2));
-			bulk_g2s(s_stage, seg, dlen * 8u, &s_bar[0]);
-			bulk_g2s(s_cn, cn, (uint32_t)(FINAL_SLOTS / 2), &s_bar[0]);
+			// the first record of every thread arrives on its own barrier: the eligibility words of those records (the
+			// tile is empty, so every one of them is a would-be winner) are fetched while the rest is still on its way
+			const uint32_t n0 = min(dlen, (uint32_t)RS_THREADS);
+			mbar_arrive_expect_tx(&s_bar[0], n0 * 8u);
+			bulk_g2s(s_stage, seg, n0 * 8u, &s_bar[0]);
+			mbar_arrive_expect_tx(&s_bar[1], (dlen - n0) * 8u + (uint32_t)(FINAL_SLOTS / 2));
+			if (dlen > n0) bulk_g2s(s_stage + n0, seg + n0, (dlen - n0) * 8u, &s_bar[1]);
+			bulk_g2s(s_cn, cn, (uint32_t)(FINAL_SLOTS / 2), &s_bar[1]);
 		}
 		if (b + gridDim.x < P.n_buckets) {
 			const uint32_t bn = b + gridDim.x;
@@ -1070,9 +1077,14 @@ resolve_dense_kernel(const ResolveParams P)
 		if (dlen == 0u) continue;          // block-uniform: gathered by resolve_kernel<true> (or empty)
 
 		mbar_wait(&s_bar[0], parity);
+		const uint64_t rec0 = (tid < dlen) ? s_stage[tid] : REC_NULL;
+		uint32_t word0 = 0;
+		if ((uint32_t)(rec0 >> 32) != REC_NULL_HI) word0 = __ldg(&P.elig[((uint32_t)rec0 & REC_POS_MASK) >> 5]);
+		mbar_wait(&s_bar[1], parity);
 		parity ^= 1u;
-		uint32_t held = 0, q = 0;       // bit q <=> this thread's q-th record became its slot's holder (dlen <= 9 * RS_THREADS)
-		for (uint32_t e = tid; e < dlen; e += RS_THREADS, ++q) {
+		uint32_t held = 0, q = 1;       // bit q <=> this thread's q-th record became its slot's holder (dlen <= 9 * RS_THREADS)
+		if ((uint32_t)(rec0 >> 32) != REC_NULL_HI && resolve_record<true>(s_tile, s_cn, P.loss, P.elig, P.level, rec0, true, word0)) held |= 1u;
+		for (uint32_t e = tid + RS_THREADS; e < dlen; e += RS_THREADS, ++q) {
 			const uint64_t rec = s_stage[e];
 			if ((uint32_t)(rec >> 32) != REC_NULL_HI && resolve_record<true>(s_tile, s_cn, P.loss, P.elig, P.level, rec)) held |= 1u << q;
 		}
