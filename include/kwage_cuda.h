@@ -63,6 +63,10 @@ uint64_t kwg_launch_count(void);
  * of reproduced: with min_kmer_count == 15 such a double increment can take a 4-bit counter from
  * 14 to 16 = 0 in the reference; the library detects it and kwg_bloom_num_valid / kwg_bloom_finalize
  * return KWG_ERR_UNSUPPORTED.
+ * Device memory per handle (besides ~64 bytes per start position of the largest batch): min_kmer_count 1 keeps one bit per
+ * counting-filter slot (2^log2_count_len / 4 bytes); min_kmer_count > 1 keeps the reference's 4-bit counters
+ * (2^log2_count_len bytes) plus a dense copy of the current batch's touch records for the later counter levels
+ * (72 KiB per 2^15 slots: 4.5 GiB at log2_count_len 30, 18 GiB at 32; skipped if it cannot be allocated).
  *   log2_count_len : log2 of the counting-filter length, [18,32] (make_bloom.cpp:104-129)
  *   log2_max_len   : opt.max_log_2_filter_len, <= 32 (make_bloom.cpp:137-140)
  *
