@@ -13,6 +13,7 @@
 //
 // Only lengths that are multiples of 4 bytes at 4-byte aligned addresses are taken; the host layer keeps zlib for the rest.
 #include "common.cuh"
+#include "crc_tables.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -24,9 +25,7 @@ constexpr int CRC_THREADS = 256;
 constexpr int CRC_WPT = 16;                                   // 32-bit words per thread
 constexpr int CRC_TILE_WORDS = CRC_THREADS * CRC_WPT;         // 16 KiB
 constexpr int CRC_TILE_LOG2 = 8;                              // tile = 64 bytes * 2^8
-constexpr int CRC_LEVELS = 44;                                // shift matrices for 64 * 2^l bytes
 constexpr int CRC_FAN = 1024;                                 // registers merged per block of the combine kernel
-constexpr uint32_t CRC_POLY = 0xEDB88320u;
 
 struct CrcParams {
 	const uint8_t* base;
@@ -108,8 +107,6 @@ constexpr int CRC2_THREADS = 512;
 constexpr int CRC2_BYTES_PT = 256;
 constexpr int CRC2_TILE_BYTES = 32 * CRC2_BYTES_PT;             // one WARP per tile: 8 KiB = 64 * 2^7
 constexpr int CRC2_TILE_LOG2 = 7;
-constexpr int CRC2_SHIFT_LEVELS = 7;                            // byte-indexed shift tables for 64 * 2^l bytes, l = 0 .. 6
-constexpr size_t CRC_SHIFT_OFFSET = (size_t)4 * 256 + (size_t)(CRC_LEVELS + 10) * 32;      // where they start in the table buffer
 constexpr size_t CRC2_SMEM = ((size_t)4 * 256 * 32 + (size_t)CRC2_SHIFT_LEVELS * 4 * 256) * 4;
 
 __device__ __forceinline__ void ld_nc_v8(const void* p, uint32_t (&r)[8])
@@ -206,15 +203,6 @@ crc_combine_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __rest
 }
 
 // ---------------------------------------------------------------- host: tables
-static void gf2_square(uint32_t* sq, const uint32_t* mat)
-{
-	for (int n = 0; n < 32; ++n) {
-		uint32_t v = mat[n], r = 0;
-		for (int i = 0; v; ++i, v >>= 1) if (v & 1u) r ^= mat[i];
-		sq[n] = r;
-	}
-}
-
 static const uint32_t* crc_tables_dev(int device)
 {
 	static std::mutex mu;
@@ -223,33 +211,8 @@ static const uint32_t* crc_tables_dev(int device)
 	if ((int)per_device.size() <= device) per_device.resize(device + 1, nullptr);
 	if (per_device[device]) return per_device[device];
 
-	std::vector<uint32_t> h(CRC_SHIFT_OFFSET + (size_t)CRC2_SHIFT_LEVELS * 4 * 256, 0u);
-	for (uint32_t i = 0; i < 256; ++i) {
-		uint32_t c = i;
-		for (int k = 0; k < 8; ++k) c = (c & 1u) ? (CRC_POLY ^ (c >> 1)) : (c >> 1);
-		h[i] = c;
-	}
-	for (uint32_t i = 0; i < 256; ++i)
-		for (int t = 1; t < 4; ++t) h[t * 256 + i] = (h[(t - 1) * 256 + i] >> 8) ^ h[h[(t - 1) * 256 + i] & 255u];
-	// operator for one zero bit, squared up to one byte (3x), then to 64 bytes (6x): level 0
-	uint32_t a[32], b[32];
-	a[0] = CRC_POLY;
-	for (int n = 1; n < 32; ++n) a[n] = 1u << (n - 1);
-	for (int q = 0; q < 9; ++q) { gf2_square(b, a); for (int n = 0; n < 32; ++n) a[n] = b[n]; }
-	for (int l = 0; l < CRC_LEVELS + 10; ++l) {
-		for (int n = 0; n < 32; ++n) h[4 * 256 + l * 32 + n] = a[n];
-		gf2_square(b, a);
-		for (int n = 0; n < 32; ++n) a[n] = b[n];
-	}
-	// byte-indexed forms of the first shift matrices: entry [l][k][b] = matrix_l * (b << 8k)
-	for (int l = 0; l < CRC2_SHIFT_LEVELS; ++l)
-		for (int k = 0; k < 4; ++k)
-			for (uint32_t bb = 0; bb < 256; ++bb) {
-				const uint32_t* mat = &h[4 * 256 + l * 32];
-				uint32_t v = bb << (8 * k), r = 0;
-				for (int i = 0; v; ++i, v >>= 1) if (v & 1u) r ^= mat[i];
-				h[CRC_SHIFT_OFFSET + ((size_t)l * 4 + k) * 256 + bb] = r;
-			}
+	std::vector<uint32_t> h;
+	crc32_build_tables(h);          // crc_tables.h (also checked on the CPU: tests/test_host_emul.py)
 	uint32_t* d = nullptr;
 	if (cudaMalloc(&d, h.size() * sizeof(uint32_t)) != cudaSuccess) return nullptr;
 	if (cudaMemcpy(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }

@@ -26,8 +26,8 @@ def _built():
     kbuild.build()
     emul_so = os.path.join(ROOT, "tests", "host_emul", "libkwage_emul.so")
     src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
-    hdr = os.path.join(ROOT, "kwage_b200", "csrc", "bitops.cuh")
-    if (not os.path.exists(emul_so)) or os.path.getmtime(emul_so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "kwage_b200", "csrc", h) for h in ("bitops.cuh", "crc_tables.h")]
+    if (not os.path.exists(emul_so)) or os.path.getmtime(emul_so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", emul_so, src], check=True)
     yield

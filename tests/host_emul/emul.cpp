@@ -153,3 +153,102 @@ void emu_count128(const uint32_t* vecs /* n x 4 */, uint32_t n, uint32_t nsub, u
 uint64_t emu_synth_rnd(uint64_t seed, uint64_t stream, uint64_t ctr) { return synth_rnd(seed, stream, ctr); }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------- crc32
+// Mirrors crc32.cu on the host with the SAME tables (kwage_b200/csrc/crc_tables.h): tiles counted from the end of the
+// message (zero-prefixed when they stick out before byte 0), the running value xor-ed into the first word, a raw register per
+// 256-byte thread chunk taken as four interleaved 64-byte chains with the slice-by-4 tables (crc_tile256_kernel) or per
+// 64-byte chunk (crc_tile_kernel), and the pairwise merge raw(A||B) = x^(8|B|) * raw(A) xor raw(B) with the byte-indexed
+// shift tables up to a tile and the level matrices above (crc_combine_kernel, 1024 registers per step).
+#include "../../kwage_b200/csrc/crc_tables.h"
+
+namespace {
+
+struct CrcTables {
+	std::vector<uint32_t> h;
+	CrcTables() { kwg::crc32_build_tables(h); }
+	uint32_t step(uint32_t c, uint32_t w) const
+	{
+		const uint32_t x = c ^ w;
+		return h[768 + (x & 255u)] ^ h[512 + ((x >> 8) & 255u)] ^ h[256 + ((x >> 16) & 255u)] ^ h[x >> 24];
+	}
+	uint32_t shift_table(int l, uint32_t v) const
+	{
+		const uint32_t* t = &h[kwg::CRC_SHIFT_OFFSET + (size_t)l * 1024];
+		return t[v & 255u] ^ t[256 + ((v >> 8) & 255u)] ^ t[512 + ((v >> 16) & 255u)] ^ t[768 + (v >> 24)];
+	}
+	uint32_t shift_matrix(int l, uint32_t v) const { return kwg::crc_gf2_times_host(&h[4 * 256 + (size_t)l * 32], v); }
+};
+
+const CrcTables& crc_tables()
+{
+	static CrcTables t;
+	return t;
+}
+
+} // namespace
+
+extern "C" {
+
+// n_bytes % 4 == 0, n_bytes >= 4.  fast != 0: the 8 KiB-per-warp tiling of crc_tile256_kernel; else 16 KiB tiles of 64-byte chunks.
+uint32_t emu_crc32(const uint8_t* data, uint64_t n_bytes, uint32_t crc_in, int fast)
+{
+	const CrcTables& T = crc_tables();
+	const uint64_t W = n_bytes / 4;
+	auto word = [&](long long w) -> uint32_t {
+		if (w < 0) return 0u;
+		uint32_t v;
+		memcpy(&v, data + (uint64_t)w * 4, 4);
+		return w == 0 ? v ^ ~crc_in : v;
+	};
+	const int tile_log2 = fast ? 7 : 8;                         // tile = 64 bytes * 2^tile_log2
+	const uint64_t tile_words = (uint64_t)16 << tile_log2;
+	const uint64_t n_tiles = (W + tile_words - 1) / tile_words;
+	std::vector<uint32_t> regs(n_tiles);                        // element 0 = the END of the message
+	for (uint64_t t = 0; t < n_tiles; ++t) {
+		const long long start = (long long)W - (long long)(t + 1) * (long long)tile_words;
+		// registers of the 64-byte chunks of the tile, forward order
+		std::vector<uint32_t> c(tile_words / 16);
+		for (size_t i = 0; i < c.size(); ++i) {
+			uint32_t r = 0;
+			for (int j = 0; j < 16; ++j) r = T.step(r, word(start + (long long)i * 16 + j));
+			c[i] = r;
+		}
+		// merge neighbours level by level: the earlier half is shifted past the later one
+		for (int l = 0; l < tile_log2; ++l) {
+			std::vector<uint32_t> nx(c.size() / 2);
+			for (size_t i = 0; i < nx.size(); ++i)
+				nx[i] = (l < kwg::CRC2_SHIFT_LEVELS && fast ? T.shift_table(l, c[2 * i]) : T.shift_matrix(l, c[2 * i])) ^ c[2 * i + 1];
+			c.swap(nx);
+		}
+		regs[t] = c[0];
+	}
+	// crc_combine_kernel: groups of 1024 registers, ten levels per step; element i + stride lies earlier in the message
+	int level = tile_log2;
+	while (regs.size() > 1) {
+		std::vector<uint32_t> out((regs.size() + 1023) / 1024);
+		for (size_t b = 0; b < out.size(); ++b) {
+			uint32_t s[1024];
+			for (size_t i = 0; i < 1024; ++i) s[i] = (b * 1024 + i < regs.size()) ? regs[b * 1024 + i] : 0u;
+			for (int l = 0; l < 10; ++l) {
+				const size_t stride = (size_t)1 << l;
+				for (size_t i = 0; i < 1024; i += 2 * stride) s[i] ^= T.shift_matrix(level + l, s[i + stride]);
+			}
+			out[b] = s[0];
+		}
+		regs.swap(out);
+		level += 10;
+	}
+	return ~regs[0];
+}
+
+// the byte-indexed shift tables are the matrices: table_l(v) == M_l * v
+int emu_crc_shift_tables_agree(uint32_t v)
+{
+	const CrcTables& T = crc_tables();
+	for (int l = 0; l < kwg::CRC2_SHIFT_LEVELS; ++l)
+		if (T.shift_table(l, v) != T.shift_matrix(l, v)) return 0;
+	return 1;
+}
+
+} // extern "C"

@@ -94,3 +94,26 @@ def test_bitsliced_counters(E, n, nsub):
 def test_synth_generator_agrees(E):
     for seed, stream, ctr in [(0, 0, 0), (1, 2, 3), (12345, 999999, 1 << 40), (2 ** 64 - 1, 2 ** 63, 7)]:
         assert E.emu_synth_rnd(seed, stream, ctr) == O.lib().kwo_rnd(seed, stream, ctr) == int(S.rnd(seed, stream, ctr))
+
+
+# ---------------------------------------------------------------------------------------------- crc32
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("n_bytes", [4, 8, 60, 64, 68, 252, 256, 260, 8188, 8192, 8196, 16384, 16388, 3 * 16384 + 12,
+                                     1 << 20, (1 << 20) + 8, 1024 * 8192 + 4, 1025 * 16384 + 64])
+def test_crc32_tiling_tables_and_combine_equal_zlib(E, n_bytes, fast):
+    # the device algorithm of crc32.cu replayed on the host with the tables the kernels use (crc_tables.h)
+    import zlib
+    E.emu_crc32.restype = C.c_uint32
+    E.emu_crc32.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int]
+    rng = np.random.default_rng(n_bytes + fast)
+    a = rng.integers(0, 256, n_bytes, dtype=np.uint8)
+    for crc_in in (0, 0xDEADBEEF):
+        assert E.emu_crc32(p(a), n_bytes, crc_in, fast) == zlib.crc32(a.tobytes(), crc_in)
+    z = np.zeros(n_bytes, np.uint8)
+    assert E.emu_crc32(p(z), n_bytes, 0, fast) == zlib.crc32(z.tobytes())
+
+
+def test_crc32_shift_tables_are_the_matrices(E):
+    rng = np.random.default_rng(1)
+    for v in [0, 1, 0x80000000, 0xFFFFFFFF] + [int(x) for x in rng.integers(0, 1 << 32, 200, dtype=np.uint64)]:
+        assert E.emu_crc_shift_tables_agree(C.c_uint32(v)) == 1
