@@ -20,6 +20,9 @@ _lib = None
 def build():
     """Compile the C restatement and, when /root/reference is present, the reference itself."""
     subprocess.run(["make", "-s", "-C", HERE, "all"], check=True)
+    # the reference's host code with the build_db shim of INTEGRATION.md, linked against the product library (when built)
+    if os.path.exists(os.path.join(HERE, "..", "kwage_b200", "lib", "libkwage_cuda.so")):
+        subprocess.run(["make", "-s", "-C", HERE, "shim"], check=True)
 
 
 def lib():
