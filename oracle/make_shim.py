@@ -118,10 +118,108 @@ def patch_make_bloom(ref, out):
     open(out, "w").write(MB_PRELUDE + text)
 
 
+# ---- kwage.cpp: the body of search() -- k-mer extraction, the per-k-mer slice reads, AND /
+# count loops and the match decision -- becomes one kwg_search call against the file's slices resident in HBM (loaded once
+# per database file and thread); option parsing, FASTA iteration, the FilterInfo look-up, MatchResult, sorting and the
+# CSV / JSON writers are the reference's.
+KW_SIGNATURE = "const SearchOptions &m_opt)\n{"
+
+KW_BODY = r'''
+	// ---- kwage_b200 shim: this thread keeps the slices of the database file it is working on resident in HBM
+	static thread_local kwg_db_t* kwg_db = NULL;
+	static thread_local unsigned long int kwg_key[4] = {0, 0, 0, 0};
+	const unsigned long int key[4] = {(unsigned long int)m_header.crc32, m_info_start, (unsigned long int)m_header.num_filter,
+		(unsigned long int)m_header.log_2_filter_len};
+
+	if( (kwg_db == NULL) || (memcmp(key, kwg_key, sizeof(key)) != 0) ){
+
+		if(kwg_db != NULL){
+			kwg_db_unload(kwg_db);
+			kwg_db = NULL;
+		}
+
+		const size_t num_slice = size_t(1) << m_header.log_2_filter_len;
+		std::vector<unsigned char> slices(num_slice*m_slice_size);
+
+		m_fsubject.clear();
+		m_fsubject.seekg(m_bloom_start);
+		m_fsubject.read( (char*)slices.data(), slices.size() );
+
+		if(!m_fsubject){
+			throw __FILE__ ":search: Error reading slice from file (1)";
+		}
+
+		if(kwg_db_load(&kwg_db, 0, slices.data(), m_header.kmer_len, m_header.num_hash, m_header.log_2_filter_len,
+			m_header.num_filter, 0, m_header.num_filter) != KWG_OK){
+
+			cerr << "kwg_db_load: " << kwg_last_error() << endl;
+			throw __FILE__ ":search: kwg_db_load failed";
+		}
+
+		memcpy(kwg_key, key, sizeof(key));
+	}
+
+	const char* query_ptr = m_query.c_str();
+	const uint64_t query_len = m_query.size();
+	uint32_t num_query_kmer = 0;
+	kwg_hit_t* hits = NULL;
+	uint64_t num_hit = 0;
+
+	if(kwg_search_ptrs(kwg_db, &query_ptr, &query_len, 1, m_opt.threshold, &num_query_kmer, &hits, &num_hit) != KWG_OK){
+		throw __FILE__ ":search: kwg_search failed";
+	}
+
+	unordered_map< size_t, deque<MatchResult> >::iterator result_iter = m_search_results.end();
+
+	for(uint64_t h = 0;h < num_hit;++h){
+
+		// Read the Bloom filter info exactly like the reference does (kwage.cpp:505-515)
+		m_fsubject.clear();
+		m_fsubject.seekg( m_info_start + hits[h].filter*sizeof(unsigned long int) );
+
+		unsigned long int info_loc;
+
+		m_fsubject.read( (char*)&info_loc, sizeof(unsigned long int) );
+		m_fsubject.seekg(info_loc);
+
+		FilterInfo info;
+
+		binary_read(m_fsubject, info);
+
+		if( result_iter == m_search_results.end() ){
+
+			result_iter = m_search_results.find(m_query_id);
+
+			if( result_iter == m_search_results.end() ){
+				result_iter = m_search_results.insert( make_pair(m_query_id, deque<MatchResult>() ) ).first;
+			}
+		}
+
+		result_iter->second.push_back( MatchResult(hits[h].num_match, num_query_kmer, info) );
+	}
+
+	kwg_free_hits(hits);
+
+	return (num_hit > 0);
+}
+'''
+
+
+def patch_kwage(ref, out):
+    text = open(ref + "/kwage.cpp").read()
+    assert text.count(KW_SIGNATURE) == 1, "the definition of search() was not found where expected"
+    at = text.index(KW_SIGNATURE) + len(KW_SIGNATURE)
+    # search() is the last function of the file: everything after its opening brace is its body
+    assert "\nbool " not in text[at:] and "\nint " not in text[at:] and "\nvoid " not in text[at:]
+    open(out, "w").write('#include <string.h>\n#include <vector>\n#include "kwage_cuda.h"\n' + text[:at] + KW_BODY)
+
+
 def main():
     ref, out = sys.argv[1], sys.argv[2]
     if out.endswith("make_bloom_gpu.cpp"):
         return patch_make_bloom(ref, out)
+    if out.endswith("kwage_gpu.cpp"):
+        return patch_kwage(ref, out)
     text = open(ref + "/build_db.cpp").read()
     a, b = text.index(BEGIN), text.index(END)
     assert a < b and text.count(BEGIN) == 1 and text.count(END) == 1, "the reference's chunk loop was not found where expected"
