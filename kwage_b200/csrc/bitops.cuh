@@ -199,6 +199,15 @@ KWG_DEV void csa(uint4& s, uint4& carry, const uint4 a, const uint4 b)
 
 
 // ---- bit-sliced counters (search): 32 filter columns per word, plane i holds bit i of every count
+// A substream counts with 4 low + 6 upper planes, i.e. up to 1023: a segment hands it at most SC_SUB_CAP k-mers
+// (a multiple of the 16-k-mer Harley-Seal block), so a filter that holds EVERY k-mer of a long query cannot wrap.
+constexpr uint32_t SC_SUB_CAP = 1008;      // k-mers per substream per segment (<= 2^10 - 1)
+constexpr uint32_t SC_SEG_CAP = 32768;     // k-mers per segment (merged counts stay below 2^16)
+KWG_DEV uint32_t search_seg_cap(uint32_t nsub)
+{
+	const uint32_t c = nsub * SC_SUB_CAP;
+	return c < SC_SEG_CAP ? c : SC_SEG_CAP;
+}
 // total += x, where x has P planes and total has 16 (counts stay below 2^16 per segment)
 template <int P>
 KWG_DEV void bitsliced_add(uint32_t (&tot)[16], const uint32_t (&x)[P])

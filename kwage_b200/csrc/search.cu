@@ -99,11 +99,9 @@ query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ 
 constexpr int SC_WARPS = 8;
 constexpr int SC_THREADS = SC_WARPS * 32;
 constexpr int SC_LOW = 4;                  // ones, twos, fours, eights
-constexpr int SC_UP = 6;                   // 16s .. 512s  -> <= 1024 k-mers per substream per segment
+constexpr int SC_UP = 6;                   // 16s .. 512s  -> < 1024 k-mers per substream per segment (SC_SUB_CAP, bitops.cuh)
 constexpr int SC_PLANES = SC_LOW + SC_UP;
 constexpr int SC_TOT = 16;                 // planes of the merged per-segment total (< 65536)
-constexpr uint32_t SC_SUB_CAP = 1024;      // k-mers per substream per segment
-constexpr uint32_t SC_SEG_CAP = 32768;     // k-mers per segment (merged counts stay below 2^16)
 
 struct SearchParams {
 	const uint8_t* slab;          // rows of row_pitch bytes
@@ -139,7 +137,7 @@ search_count_kernel(const SearchParams P)
 	const bool active = col4 < P.vec_per_row;
 	const uint8_t* col_ptr = P.slab + (uint64_t)col4 * 16;
 	const uint32_t words_per_chunk = lpr * 4;               // 32-bit column words handled by this block
-	const uint32_t seg_cap = min(SC_SEG_CAP, nsub * SC_SUB_CAP);
+	const uint32_t seg_cap = search_seg_cap(nsub);
 
 	for (uint32_t seg0 = 0; seg0 == 0 || seg0 < n; seg0 += seg_cap) {
 		const uint32_t seg_n = (n > seg0) ? min(seg_cap, n - seg0) : 0u;

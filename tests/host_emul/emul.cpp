@@ -4,6 +4,7 @@
 // be checked bit-for-bit against the oracle without a GPU.  The loops below mirror how the kernels
 // drive those helpers (kmer_scan_kernel stages 1-2, transpose_kernel, search_count_kernel).
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../../kwage_b200/csrc/bitops.cuh"
@@ -91,64 +92,74 @@ void emu_transpose32(const uint32_t* in, uint32_t* out)
 // Mirrors search_count_kernel for one 128-column lane: `n` AND-ed match vectors (uint4 each) are
 // dealt round-robin to `nsub` substreams, each accumulates with the Harley-Seal block of 16, then
 // the substreams are merged bit-sliced and expanded.  counts: 128 uint32.
-void emu_count128(const uint32_t* vecs /* n x 4 */, uint32_t n, uint32_t nsub, uint32_t* counts)
+void emu_count128(const uint32_t* vecs_all /* n x 4 */, uint32_t n_all, uint32_t nsub, uint32_t* counts)
 {
+	// search_count_kernel: segments of search_seg_cap(nsub) k-mers, each counted by nsub substreams of 4 + 6 planes,
+	// merged bit-sliced and added to the counts of the segments before it
 	const int LOW = 4, UP = 6, PL = LOW + UP;
-	std::vector<uint32_t> planes((size_t)nsub * PL * 4, 0);
-	const uint32_t n_blk = (n + 16 * nsub - 1) / (16 * nsub);
-	for (uint32_t sub = 0; sub < nsub; ++sub) {
-		uint4 pl[PL];
-		for (int i = 0; i < PL; ++i) pl[i] = make_uint4(0, 0, 0, 0);
-		for (uint32_t blk = 0; blk < n_blk; ++blk) {
-			uint4 fA = make_uint4(0, 0, 0, 0), eA = make_uint4(0, 0, 0, 0);
-			for (int quad = 0; quad < 4; ++quad) {
-				uint4 v[4];
-				for (int u = 0; u < 4; ++u) {
-					const uint32_t i = (blk * 16 + quad * 4 + u) * nsub + sub;
-					v[u] = make_uint4(0, 0, 0, 0);
-					if (i < n) v[u] = make_uint4(vecs[4 * i], vecs[4 * i + 1], vecs[4 * i + 2], vecs[4 * i + 3]);
-				}
-				uint4 tA, tB, f;
-				csa(pl[0], tA, v[0], v[1]);
-				csa(pl[0], tB, v[2], v[3]);
-				csa(pl[1], f, tA, tB);
-				if (quad == 0 || quad == 2) fA = f;
-				else {
-					uint4 e;
-					csa(pl[2], e, fA, f);
-					if (quad == 1) eA = e;
+	const uint32_t seg_cap = search_seg_cap(nsub);
+	for (int i = 0; i < 128; ++i) counts[i] = 0;
+	for (uint32_t seg0 = 0; seg0 == 0 || seg0 < n_all; seg0 += seg_cap) {
+		const uint32_t n = (n_all > seg0) ? std::min(seg_cap, n_all - seg0) : 0u;
+		const uint32_t* vecs = vecs_all + (size_t)seg0 * 4;
+		std::vector<uint32_t> planes((size_t)nsub * PL * 4, 0);
+		const uint32_t n_blk = (n + 16 * nsub - 1) / (16 * nsub);
+		for (uint32_t sub = 0; sub < nsub; ++sub) {
+			uint4 pl[PL];
+			for (int i = 0; i < PL; ++i) pl[i] = make_uint4(0, 0, 0, 0);
+			for (uint32_t blk = 0; blk < n_blk; ++blk) {
+				uint4 fA = make_uint4(0, 0, 0, 0), eA = make_uint4(0, 0, 0, 0);
+				for (int quad = 0; quad < 4; ++quad) {
+					uint4 v[4];
+					for (int u = 0; u < 4; ++u) {
+						const uint32_t i = (blk * 16 + quad * 4 + u) * nsub + sub;
+						v[u] = make_uint4(0, 0, 0, 0);
+						if (i < n) v[u] = make_uint4(vecs[4 * i], vecs[4 * i + 1], vecs[4 * i + 2], vecs[4 * i + 3]);
+					}
+					uint4 tA, tB, f;
+					csa(pl[0], tA, v[0], v[1]);
+					csa(pl[0], tB, v[2], v[3]);
+					csa(pl[1], f, tA, tB);
+					if (quad == 0 || quad == 2) fA = f;
 					else {
-						uint4 c16;
-						csa(pl[3], c16, eA, e);
-						for (int up = LOW; up < PL; ++up) {
-							const uint4 t = and4(pl[up], c16);
-							pl[up].x ^= c16.x; pl[up].y ^= c16.y; pl[up].z ^= c16.z; pl[up].w ^= c16.w;
-							c16 = t;
+						uint4 e;
+						csa(pl[2], e, fA, f);
+						if (quad == 1) eA = e;
+						else {
+							uint4 c16;
+							csa(pl[3], c16, eA, e);
+							for (int up = LOW; up < PL; ++up) {
+								const uint4 t = and4(pl[up], c16);
+								pl[up].x ^= c16.x; pl[up].y ^= c16.y; pl[up].z ^= c16.z; pl[up].w ^= c16.w;
+								c16 = t;
+							}
 						}
 					}
 				}
 			}
+			for (int i = 0; i < PL; ++i) {
+				uint32_t* d = &planes[((size_t)sub * PL + i) * 4];
+				d[0] = pl[i].x; d[1] = pl[i].y; d[2] = pl[i].z; d[3] = pl[i].w;
+			}
 		}
-		for (int i = 0; i < PL; ++i) {
-			uint32_t* d = &planes[((size_t)sub * PL + i) * 4];
-			d[0] = pl[i].x; d[1] = pl[i].y; d[2] = pl[i].z; d[3] = pl[i].w;
-		}
-	}
-	for (uint32_t w = 0; w < 4; ++w) {
-		uint32_t tot[16];
-		for (int i = 0; i < 16; ++i) tot[i] = 0;
-		for (uint32_t s = 0; s < nsub; ++s) {
-			uint32_t x[PL];
-			for (int i = 0; i < PL; ++i) x[i] = planes[((size_t)s * PL + i) * 4 + w];
-			bitsliced_add<PL>(tot, x);
-		}
-		for (int nb = 0; nb < 8; ++nb) {
-			const uint4 c = expand_counts4(tot, nb);
-			uint32_t* o = counts + w * 32 + nb * 4;
-			o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w;
+		for (uint32_t w = 0; w < 4; ++w) {
+			uint32_t tot[16];
+			for (int i = 0; i < 16; ++i) tot[i] = 0;
+			for (uint32_t s = 0; s < nsub; ++s) {
+				uint32_t x[PL];
+				for (int i = 0; i < PL; ++i) x[i] = planes[((size_t)s * PL + i) * 4 + w];
+				bitsliced_add<PL>(tot, x);
+			}
+			for (int nb = 0; nb < 8; ++nb) {
+				const uint4 c = expand_counts4(tot, nb);
+				uint32_t* o = counts + w * 32 + nb * 4;
+				o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w;
+			}
 		}
 	}
 }
+
+uint32_t emu_seg_cap(uint32_t nsub) { return search_seg_cap(nsub); }
 
 uint64_t emu_synth_rnd(uint64_t seed, uint64_t stream, uint64_t ctr) { return synth_rnd(seed, stream, ctr); }
 

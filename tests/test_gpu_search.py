@@ -81,6 +81,29 @@ def test_search_long_query_many_kmers():
     assert nk[0] == n and n > 70000 and np.array_equal(counts[0], exp)
 
 
+@pytest.mark.parametrize("n_filters", [600, 2048, 4100])
+def test_search_filter_holding_every_kmer_of_a_long_query(n_filters):
+    # with more than 512 filters a substream got exactly 1024 k-mers per full segment and its 10-plane
+    # counter wrapped to 0 for a filter that matches all of them.  Planted columns: one all-ones filter per 128-column
+    # group boundary, the rest sparse; the oracle counts are the reference's (kwage.cpp:404-483).
+    L, h, k = 14, 2, 31
+    rng = np.random.default_rng(n_filters)
+    row = (n_filters + 7) // 8
+    slices = rng.integers(0, 256, ((1 << L), row), dtype=np.uint8) & rng.integers(0, 256, ((1 << L), row), dtype=np.uint8)
+    full = [0, 127, 128, 511, 512, n_filters - 1]
+    for f in full:
+        slices[:, f >> 3] |= np.uint8(1 << (f & 7))
+    seq = bytes(O.gen_reads(11, 0, 1, 45000)).decode()
+    with capi.Database.load(slices, k, h, L, n_filters) as db:
+        counts, nk = db.search_counts([seq])
+        hits, _ = db.search([seq], 1.0)
+    exp, n = O.search_counts(slices, n_filters, L, h, k, seq)
+    assert nk[0] == n and n > 40000
+    assert np.array_equal(counts[0], exp)
+    assert all(int(counts[0][f]) == n for f in full)
+    assert sorted(int(x) for x in hits["filter"]) == sorted(set(full))
+
+
 def test_search_column_slabs_equal_whole():
     # multi-GPU layout: every device holds a column slab; the concatenation of slab counts is the answer
     dbd = util.search_case_db("random_n257")

@@ -91,6 +91,19 @@ def test_bitsliced_counters(E, n, nsub):
     assert np.array_equal(counts.astype(np.uint64), exp.astype(np.uint64))
 
 
+@pytest.mark.parametrize("nsub", [8, 16, 32, 64, 256])
+def test_bitsliced_counters_cannot_wrap(E, nsub):
+    # a filter that holds EVERY k-mer of a long query used to wrap a substream's 10-plane counter (1024 -> 0)
+    cap = E.emu_seg_cap(C.c_uint32(nsub))
+    assert cap <= 32768 and cap // nsub <= 1023
+    for n in (cap - 1, cap, cap + 1, 2 * cap + 1, 40000):
+        vecs = np.full((n, 4), 0xFFFFFFFF, np.uint32)
+        vecs[:, 3] &= np.uint32(0x7FFFFFFF)          # one column that never matches
+        counts = np.zeros(128, np.uint32)
+        E.emu_count128(p(vecs), C.c_uint32(n), C.c_uint32(nsub), p(counts))
+        assert list(counts[:127]) == [n] * 127 and counts[127] == 0
+
+
 def test_synth_generator_agrees(E):
     for seed, stream, ctr in [(0, 0, 0), (1, 2, 3), (12345, 999999, 1 << 40), (2 ** 64 - 1, 2 ** 63, 7)]:
         assert E.emu_synth_rnd(seed, stream, ctr) == O.lib().kwo_rnd(seed, stream, ctr) == int(S.rnd(seed, stream, ctr))
