@@ -20,6 +20,7 @@
 //        table meet; a 4-bit wrap (only possible for c == 15) is detected and reported as an error.
 #include "common.cuh"
 #include "bloom_count.cuh"
+#include "bloom_first.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -191,10 +192,12 @@ __global__ void mark_read_starts_kernel(const uint64_t* __restrict__ offsets, ui
 template <int NH>
 __global__ void __launch_bounds__(256)
 insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint32_t k, uint32_t* __restrict__ filter,
-	uint32_t filter_mask, uint32_t win_id, uint32_t n_win)
+	uint32_t filter_mask, uint32_t win_id, uint32_t n_win, const uint32_t* __restrict__ invalid)
 {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+		// first-touch path: the list holds every occurrence; the few that read four non-zero counters are skipped
+		if (invalid && ((invalid[i >> 5] >> (i & 31u)) & 1u)) continue;
 		const uint64_t w = chunks[i >> LIST_CHUNK_LOG2][i & (LIST_CHUNK - 1)];
 		const uint64_t low = reverse_groups(w, k);
 		uint32_t h[NH];
@@ -240,6 +243,19 @@ struct kwg_bloom {
 	uint32_t* d_cfirst = nullptr; size_t cfirst_cap = 0;
 	unsigned long long* d_tot_rec = nullptr; size_t tot_rec_cap = 0;
 	uint32_t* d_tot_chk = nullptr; size_t tot_chk_cap = 0;
+	// min_count == 1, lc <= 30: page chains of the one-level partition (bloom_first.cuh)
+	bool use_ft = false;
+	uint8_t* d_ft_pool = nullptr;  size_t ft_pool_cap = 0;
+	uint32_t* d_ft_log = nullptr;  size_t ft_log_cap = 0;
+	uint32_t* d_ft_plist = nullptr; size_t ft_plist_cap = 0;
+	uint2* d_ft_info = nullptr;    size_t ft_info_cap = 0;
+	uint32_t* d_ft_npages = nullptr; size_t ft_npages_cap = 0;
+	uint32_t* d_ft_tiles = nullptr; size_t ft_tiles_cap = 0;
+	uint4* d_ft_hm = nullptr;      size_t ft_hm_cap = 0;
+	uint32_t* d_ft_meta = nullptr; size_t ft_meta_cap = 0;
+	uint2* d_ft_carry = nullptr;   size_t ft_carry_cap = 0;
+	uint32_t* d_inv = nullptr;     size_t inv_cap = 0;     // bit i: list entry i is an occurrence that read four non-zero counters
+	uint64_t n_list_host = 0;            // entries of the word list (first-touch path: every k-mer occurrence, valid or not)
 	uint64_t n_valid_host = 0;           // last value read from d_counter (saves a device round trip in finalize)
 	bool n_valid_known = false;
 	// host feed: bases stream in on a copy stream while the partition scan already runs on what has arrived
@@ -274,17 +290,19 @@ static int grow(void** p, size_t* cap, size_t need)
 	return KWG_OK;
 }
 
-// d_counter[0] = valid k-mers so far, d_counter[1] != 0: a 4-bit counter wrapped (min_kmer_count == 15 only)
+// d_counter[0] = valid k-mers so far, d_counter[1] != 0: a 4-bit counter wrapped (min_kmer_count == 15 only),
+// d_counter[2] = entries of the word list (first-touch path; elsewhere the list holds exactly the valid k-mers)
 static int read_counter(kwg_bloom* b, uint64_t* out)
 {
 	if (b->n_valid_known) { *out = b->n_valid_host; return KWG_OK; }
-	KWG_CUDA(cudaMemcpyAsync(b->h_counter, b->d_counter, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+	KWG_CUDA(cudaMemcpyAsync(b->h_counter, b->d_counter, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
 	KWG_CUDA(cudaStreamSynchronize(b->stream));
 	if (b->h_counter[1])
 		return fail(KWG_ERR_UNSUPPORTED, "a 4-bit counter of the counting filter wrapped from 15 to 0 (min_kmer_count 15 with both hashes of "
 			"a table on one slot, reference make_bloom.cpp:586-592); this order-dependent case is not reproduced on the device");
 	*out = *b->h_counter;
 	b->n_valid_host = *out;
+	b->n_list_host = b->use_ft ? b->h_counter[2] : *out;
 	b->n_valid_known = true;
 	return KWG_OK;
 }
@@ -358,6 +376,145 @@ static int count_kernels_init()
 	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes()));
 	KWG_CUDA(cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes(true)));
 	KWG_CUDA(cudaFuncSetAttribute(resolve_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes(true)));
+	KWG_CUDA(cudaFuncSetAttribute(ft_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_append_smem_bytes()));
+	KWG_CUDA(cudaFuncSetAttribute(ft_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_resolve_smem_bytes()));
+	return KWG_OK;
+}
+
+constexpr size_t FEED_CHUNK = 16u << 20;
+
+// min_kmer_count == 1, at most FT_MAX_BUCKETS buckets of 2^20 slots (lc <= 30): count / scan / hash by tile, append into
+// page chains, resolve bucket by bucket against a 1-bit-per-slot tile, mark the invalid occurrences (bloom_first.cuh).
+// The canonical words go straight into the accession's list (entries list_base + ordinal), there is no pass B.
+static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const char* h_feed, uint64_t list_base)
+{
+	const CountGeom& G = b->geom;
+	const uint32_t slot_bits = G.lc + 1;
+	const uint32_t n_buckets = slot_bits > (uint32_t)FT_BUCKET_LOG2 ? 1u << (slot_bits - FT_BUCKET_LOG2) : 1u;
+	const uint32_t bucket_words = (slot_bits > (uint32_t)FT_BUCKET_LOG2 ? 1u << FT_BUCKET_LOG2 : 1u << slot_bits) / 32;
+	const uint32_t sms = (uint32_t)sm_count(b->device);
+	const uint32_t n_tiles = (uint32_t)ceil_div(n_pos, HT_POS);
+	int rc;
+
+	// pieces: one, or one per piece of the host feed (at most FT_MAX_CHAINS / sms of them)
+	struct Piece { uint32_t tile0, n_tiles, grid, chain0; size_t feed_off, feed_len; };
+	std::vector<Piece> pieces;
+	if (!h_feed) {
+		pieces.push_back(Piece{0, n_tiles, 0, 0, 0, 0});
+	} else {
+		const size_t max_pieces = std::max<size_t>(1, (size_t)FT_MAX_CHAINS / sms);
+		const size_t chunk = std::max<size_t>(FEED_CHUNK, (size_t)round_up(ceil_div(S.n_bases, max_pieces), 1u << 20));
+		const size_t n_chunks = (size_t)ceil_div(S.n_bases, chunk);
+		uint32_t t_done = 0;
+		for (size_t c = 0; c < n_chunks; ++c) {
+			const size_t off = c * chunk, len = std::min<size_t>(chunk, (size_t)S.n_bases - off);
+			// a tile reads HT_LOAD bases from its first position
+			const uint32_t t_end = (c + 1 == n_chunks) ? n_tiles
+				: (uint32_t)std::min<uint64_t>(n_tiles, (off + len >= (size_t)HT_LOAD) ? (off + len - HT_LOAD) / HT_POS + 1 : 0);
+			pieces.push_back(Piece{t_done, t_end > t_done ? t_end - t_done : 0u, 0, 0, off, len});
+			t_done = std::max(t_done, t_end);
+		}
+	}
+	uint32_t n_chains = 0;
+	uint64_t max_per_cta = FT_SUB;                             // ordinals per append block, upper bound
+	for (Piece& L : pieces) {
+		if (L.n_tiles == 0) continue;
+		const uint64_t ords = (uint64_t)L.n_tiles * HT_POS;
+		L.grid = (uint32_t)std::min<uint64_t>(sms, ceil_div(ords, FT_SUB));
+		L.chain0 = n_chains;
+		n_chains += L.grid;
+		max_per_cta = std::max<uint64_t>(max_per_cta, round_up(ceil_div(ords, L.grid), FT_SUB));
+	}
+	if (n_chains > (uint32_t)FT_MAX_CHAINS) return fail(KWG_ERR_CUDA, "internal: too many partition chains");
+	const uint32_t max_chains = (uint32_t)round_up(std::max(n_chains, 1u), 32);
+
+	// page size: about four pages per chain, 4 .. 32 units; pool per chain: exact worst case
+	const uint64_t chain_units = max_per_cta * 4 / FT_UNIT / n_buckets;
+	uint32_t pu_log2 = 2;
+	while (pu_log2 < 5 && (8ull << pu_log2) <= chain_units) ++pu_log2;
+	const uint64_t ppc64 = ceil_div(max_per_cta * 4, (uint64_t)FT_UNIT << pu_log2) + 2ull * n_buckets + 2;
+	if (ppc64 * max_chains >= 0xFFFFFFFFull || ppc64 >= (1ull << FT_SEQ_BITS)) return fail(KWG_ERR_CUDA, "internal: page pool too large");
+	const uint32_t ppc = (uint32_t)ppc64;
+	const size_t page_bytes = (size_t)FT_UNIT_BYTES << pu_log2;
+	const size_t meta_words = 2 + 2 * pieces.size();
+	if ((rc = grow((void**)&b->d_ft_pool, &b->ft_pool_cap, (size_t)n_chains * ppc * page_bytes))) return rc;
+	if ((rc = grow((void**)&b->d_ft_log, &b->ft_log_cap, (size_t)n_chains * ppc * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_plist, &b->ft_plist_cap, (size_t)n_chains * ppc * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_info, &b->ft_info_cap, (size_t)n_buckets * max_chains * sizeof(uint2)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_npages, &b->ft_npages_cap, (size_t)n_chains * FT_MAX_BUCKETS * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_tiles, &b->ft_tiles_cap, (size_t)n_tiles * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_hm, &b->ft_hm_cap, (size_t)n_tiles * HT_POS * sizeof(uint4)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_meta, &b->ft_meta_cap, meta_words * sizeof(uint32_t)))) return rc;
+	if ((rc = grow((void**)&b->d_ft_carry, &b->ft_carry_cap, (size_t)sms * 2 * FR_CARRY * sizeof(uint2)))) return rc;
+	KWG_CUDA(cudaMemsetAsync(b->d_ft_meta, 0, meta_words * sizeof(uint32_t), b->stream));
+
+	FtTileParams T{};
+	T.bases = S.bases; T.n_bases = S.n_bases; T.start_mask = S.start_mask; T.k = S.k;
+	T.pos0 = pos0; T.n_pos = n_pos;
+	T.tile_cnt = b->d_ft_tiles;
+	T.count_mask = G.count_mask;
+	T.hm = b->d_ft_hm;
+	T.list_chunks = b->d_chunk_table;
+	T.list_base = list_base;
+	T.loss = b->d_loss;
+
+	FtAppendParams A{};
+	A.hm = b->d_ft_hm; A.meta = b->d_ft_meta;
+	A.lc = G.lc; A.n_buckets = n_buckets;
+	A.max_chains = max_chains; A.pu_log2 = pu_log2; A.ppc = ppc;
+	A.pool = b->d_ft_pool; A.page_log = b->d_ft_log; A.plist = b->d_ft_plist; A.npages = b->d_ft_npages; A.info = b->d_ft_info;
+
+	if (h_feed) {
+		if (!b->copy_stream) KWG_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+		while (b->feed_events.size() < pieces.size() + 1) {
+			cudaEvent_t e;
+			KWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			b->feed_events.push_back(e);
+		}
+		// the staging buffer may still be read by work queued earlier on the compute stream
+		KWG_CUDA(cudaEventRecord(b->feed_events[pieces.size()], b->stream));
+		KWG_CUDA(cudaStreamWaitEvent(b->copy_stream, b->feed_events[pieces.size()], 0));
+	}
+	for (size_t l = 0; l < pieces.size(); ++l) {
+		const Piece& L = pieces[l];
+		if (h_feed) {
+			KWG_CUDA(cudaMemcpyAsync(const_cast<char*>(S.bases) + L.feed_off, h_feed + L.feed_off, L.feed_len, cudaMemcpyHostToDevice, b->copy_stream));
+			KWG_CUDA(cudaEventRecord(b->feed_events[l], b->copy_stream));
+			KWG_CUDA(cudaStreamWaitEvent(b->stream, b->feed_events[l], 0));
+		}
+		if (L.n_tiles == 0) continue;
+		T.tile0 = L.tile0;
+		b->timers.begin(KWG_T_SCAN_A, b->stream);
+		ft_count_kernel<<<L.n_tiles, HT_THREADS, 0, b->stream>>>(T);
+		KWG_LAUNCHED();
+		ft_scan_kernel<<<1, 1024, 0, b->stream>>>(b->d_ft_tiles, L.tile0, L.n_tiles, b->d_ft_meta, (uint32_t)l);
+		KWG_LAUNCHED();
+		ft_hash_kernel<<<L.n_tiles, HT_THREADS, 0, b->stream>>>(T);
+		b->timers.end(b->stream);
+		KWG_LAUNCHED();
+		A.piece = (uint32_t)l; A.chain0 = L.chain0;
+		b->timers.begin(KWG_T_REGROUP, b->stream);
+		ft_append_kernel<<<L.grid, FT_THREADS, ft_append_smem_bytes(), b->stream>>>(A);
+		b->timers.end(b->stream);
+		KWG_LAUNCHED();
+	}
+
+	FtResolveParams K3{};
+	K3.pool = b->d_ft_pool; K3.plist = b->d_ft_plist; K3.info = b->d_ft_info;
+	K3.n_chains = n_chains; K3.max_chains = max_chains; K3.n_buckets = n_buckets; K3.pu_log2 = pu_log2;
+	K3.bucket_words = bucket_words;
+	K3.touched = b->d_touched;
+	K3.have_prior = b->touched_dirty ? 1u : 0u;
+	K3.loss = b->d_loss;
+	K3.carry_scratch = b->d_ft_carry;
+	b->timers.begin(KWG_T_RESOLVE, b->stream);
+	ft_resolve_kernel<<<std::min(n_buckets, sms), FR_THREADS, ft_resolve_smem_bytes(), b->stream>>>(K3);
+	b->timers.end(b->stream);
+	KWG_LAUNCHED();
+	b->timers.begin(KWG_T_SCAN_B, b->stream);
+	ft_finish_kernel<<<(unsigned)ceil_div(ceil_div(n_pos, 8), 256), 256, 0, b->stream>>>(b->d_loss, b->d_ft_meta, list_base, b->d_inv, b->d_counter);
+	b->timers.end(b->stream);
+	KWG_LAUNCHED();
 	return KWG_OK;
 }
 
@@ -365,8 +522,6 @@ static int count_kernels_init()
 // partition (K1) -> [regroup (K2)] -> resolve (K3) -> pass B (valid-word list).
 // h_feed != NULL: the bases of this (single) sub-batch are still on the host at h_feed; they are copied in
 // FEED_CHUNK pieces on the copy stream and the partition scan is launched piece by piece behind them.
-constexpr size_t FEED_CHUNK = 16u << 20;
-
 static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const char* h_feed)
 {
 	const CountGeom& G = b->geom;
@@ -379,15 +534,36 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	uint64_t n_valid = 0;
 	rc = read_counter(b, &n_valid);
 	if (rc) return rc;
-	rc = ensure_list_capacity(b, n_valid + n_pos);
+	rc = ensure_list_capacity(b, b->n_list_host + n_pos);
 	if (rc) return rc;
 
-	const size_t loss_words = (size_t)(n_tiles * PT_POS / 8);
+	const size_t loss_words = (size_t)(round_up(n_pos, 8192) / 8);
 	if ((rc = grow((void**)&b->d_loss, &b->loss_cap, loss_words * sizeof(uint32_t)))) return rc;
+	KWG_CUDA(cudaMemsetAsync(b->d_loss, 0, loss_words * sizeof(uint32_t), b->stream));
+	if (b->use_ft) {
+		// the invalid bitmap grows with the list (kept contiguous: it is 1/64 of the list)
+		const uint64_t list_base = b->n_list_host;
+		const size_t inv_need = (size_t)round_up(ceil_div(list_base + n_pos, 8), 256);
+		if (inv_need > b->inv_cap) {
+			uint32_t* n = nullptr;
+			const size_t want = round_up(inv_need + inv_need / 2, 256);
+			KWG_CUDA(cudaMalloc(&n, want));
+			KWG_CUDA(cudaMemsetAsync(n, 0, want, b->stream));
+			if (b->d_inv) {
+				KWG_CUDA(cudaMemcpyAsync(n, b->d_inv, b->inv_cap, cudaMemcpyDeviceToDevice, b->stream));
+				KWG_CUDA(cudaStreamSynchronize(b->stream));
+				KWG_CUDA(cudaFree(b->d_inv));
+			}
+			b->d_inv = n; b->inv_cap = want;
+		}
+		if ((rc = count_first_touch(b, S, pos0, n_pos, h_feed, list_base))) return rc;
+		b->touched_dirty = true;
+		b->n_valid_known = false;
+		return KWG_OK;
+	}
 	if ((rc = grow((void**)&b->d_rec1, &b->rec1_cap, (size_t)n_tiles * PT_REC * sizeof(uint64_t)))) return rc;
 	if ((rc = grow((void**)&b->d_offs1, &b->offs1_cap, (size_t)(F1 + 1) * ntp * sizeof(uint16_t)))) return rc;
 	if (b->min_count > 1 && (rc = grow((void**)&b->d_elig, &b->elig_cap, loss_words / 4 * sizeof(uint32_t)))) return rc;
-	KWG_CUDA(cudaMemsetAsync(b->d_loss, 0, loss_words * sizeof(uint32_t), b->stream));
 
 	PartParams K1{};
 	K1.bases = S.bases; K1.n_bases = S.n_bases; K1.start_mask = S.start_mask; K1.k = S.k;
@@ -575,10 +751,10 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 		return KWG_OK;
 	}
 
-	// counting mode: sub-batches of at most 2^28 start positions (a record carries a 28-bit position)
-	for (uint64_t pos0 = 0; pos0 < n_bases; pos0 += MAX_COUNT_POS) {
-		const uint64_t n_pos = std::min<uint64_t>(MAX_COUNT_POS, n_bases - pos0);
-		rc = count_sub_batch(b, P, pos0, n_pos, (n_bases <= MAX_COUNT_POS) ? h_feed : nullptr);
+	// counting mode: sub-batches of just under 2^28 start positions (a record carries a 28-bit position)
+	for (uint64_t pos0 = 0; pos0 < n_bases; pos0 += FT_MAX_POS) {
+		const uint64_t n_pos = std::min<uint64_t>(FT_MAX_POS, n_bases - pos0);
+		rc = count_sub_batch(b, P, pos0, n_pos, (n_bases <= FT_MAX_POS) ? h_feed : nullptr);
 		if (rc) return rc;
 	}
 	return KWG_OK;
@@ -593,9 +769,9 @@ static int bloom_alloc_common(kwg_bloom* b)
 		fprintf(stderr, "[kwg] L2 fetch granularity = %zu\n", v);
 	}
 	KWG_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-	KWG_CUDA(cudaMalloc(&b->d_counter, 2 * sizeof(unsigned long long)));
-	KWG_CUDA(cudaMallocHost(&b->h_counter, 2 * sizeof(unsigned long long)));
-	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, 2 * sizeof(unsigned long long), b->stream));
+	KWG_CUDA(cudaMalloc(&b->d_counter, 3 * sizeof(unsigned long long)));
+	KWG_CUDA(cudaMallocHost(&b->h_counter, 3 * sizeof(unsigned long long)));
+	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, 3 * sizeof(unsigned long long), b->stream));
 	return KWG_OK;
 }
 
@@ -610,6 +786,8 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
 	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_meta);
 	cudaFree(b->d_cfirst); cudaFree(b->d_loss); cudaFree(b->d_tot_rec); cudaFree(b->d_tot_chk);
+	cudaFree(b->d_ft_pool); cudaFree(b->d_ft_log); cudaFree(b->d_ft_plist); cudaFree(b->d_ft_info); cudaFree(b->d_ft_npages);
+	cudaFree(b->d_ft_tiles); cudaFree(b->d_ft_hm); cudaFree(b->d_ft_meta); cudaFree(b->d_ft_carry); cudaFree(b->d_inv);
 	for (cudaEvent_t e : b->feed_events) cudaEventDestroy(e);
 	if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
 	for (uint64_t* c : b->chunks) cudaFree(c);
@@ -643,6 +821,8 @@ int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t 
 	rc = bloom_alloc_common(b);
 	if (rc == KWG_OK) {
 		b->geom = count_geometry(b->lc);
+		// the one-level partition covers up to 2048 buckets of 2^20 slots; KWG_COUNT_TWO_LEVEL=1 keeps the first design (A/B runs)
+		b->use_ft = min_kmer_count == 1 && b->lc + 1 <= (uint32_t)FT_BUCKET_LOG2 + 11 && !getenv("KWG_COUNT_TWO_LEVEL");
 		rc = count_kernels_init();
 		if (rc == KWG_OK) {
 			// two tables of 2^lc slots: one bit each (min count 1: the first batch after create/reset writes every word
@@ -695,9 +875,11 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
 	int rc = select_device(b->device);
 	if (rc) return rc;
-	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, 2 * sizeof(unsigned long long), b->stream));
+	KWG_CUDA(cudaMemsetAsync(b->d_counter, 0, 3 * sizeof(unsigned long long), b->stream));
 	b->n_valid_host = 0;
+	b->n_list_host = 0;
 	b->n_valid_known = true;
+	if (b->d_inv) KWG_CUDA(cudaMemsetAsync(b->d_inv, 0, b->inv_cap, b->stream));
 	if (b->raw) {
 		KWG_CUDA(cudaMemsetAsync(b->d_filter, 0, (size_t)1 << (b->raw_L - 3), b->stream));
 	} else {
@@ -749,7 +931,7 @@ int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offse
 			rc = grow((void**)&b->d_offsets, &b->offsets_cap, (r1 - r0 + 1) * sizeof(uint64_t));
 			if (rc) return rc;
 			KWG_CUDA(cudaMemcpyAsync(b->d_offsets, offsets + r0, (r1 - r0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
-			const bool feed = !b->raw && nb <= MAX_COUNT_POS && nb > FEED_CHUNK;
+			const bool feed = !b->raw && nb <= FT_MAX_POS && nb > FEED_CHUNK;
 			if (!feed) KWG_CUDA(cudaMemcpyAsync(b->d_bases, bases + off0, nb, cudaMemcpyHostToDevice, b->stream));
 			rc = add_batch_dev(b, b->d_bases, b->d_offsets, r1 - r0, off0, nb, feed ? bases + off0 : nullptr);
 			if (rc) return rc;
@@ -787,12 +969,13 @@ int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 	if (rc) return rc;
 	const size_t bytes = (size_t)1 << (log2_len - 3);
 	KWG_CUDA(cudaMemsetAsync(d_out_bits, 0, bytes, b->stream));
-	if (n_valid) {
+	const uint64_t n_list = b->n_list_host;
+	if (n_list) {
 		const uint32_t mask = (log2_len >= 32) ? 0xFFFFFFFFu : ((1u << log2_len) - 1u);
-		const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n_valid, 256), (uint64_t)sm_count(b->device) * 16);
+		const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n_list, 256), (uint64_t)sm_count(b->device) * 16);
 		uint32_t* f = reinterpret_cast<uint32_t*>(d_out_bits);
 		b->timers.begin(KWG_T_INSERT, b->stream);
-#define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_valid, b->k, f, mask, w, n_win); break;
+#define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_list, b->k, f, mask, w, n_win, b->use_ft ? b->d_inv : nullptr); break;
 		const uint32_t n_win = (log2_len > WINDOW_LOG2 && !getenv("KWG_NO_WINDOWS")) ? 1u << (log2_len - WINDOW_LOG2) : 1u;
 		for (uint32_t w = 0; w < n_win; ++w) {
 			switch (num_hash) {
