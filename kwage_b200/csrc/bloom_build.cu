@@ -249,7 +249,6 @@ struct kwg_bloom {
 	uint32_t* d_ft_log = nullptr;  size_t ft_log_cap = 0;
 	uint32_t* d_ft_plist = nullptr; size_t ft_plist_cap = 0;
 	uint2* d_ft_info = nullptr;    size_t ft_info_cap = 0;
-	uint32_t* d_ft_npages = nullptr; size_t ft_npages_cap = 0;
 	uint32_t* d_ft_tiles = nullptr; size_t ft_tiles_cap = 0;
 	uint4* d_ft_hm = nullptr;      size_t ft_hm_cap = 0;
 	uint32_t* d_ft_meta = nullptr; size_t ft_meta_cap = 0;
@@ -432,6 +431,9 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	const uint64_t chain_units = max_per_cta * 4 / FT_UNIT / n_buckets;
 	uint32_t pu_log2 = 2;
 	while (pu_log2 < 5 && (8ull << pu_log2) <= chain_units) ++pu_log2;
+	// a chain's pages are counted in 16 bits: even if one bucket took every record of a block's stretch
+	while (pu_log2 < 5 && ceil_div(max_per_cta * 4, (uint64_t)FT_UNIT << pu_log2) + 1 > 0xFFFFull) ++pu_log2;
+	if (ceil_div(max_per_cta * 4, (uint64_t)FT_UNIT << pu_log2) + 1 > 0xFFFFull) return fail(KWG_ERR_CUDA, "internal: partition stretch too long");
 	const uint64_t ppc64 = ceil_div(max_per_cta * 4, (uint64_t)FT_UNIT << pu_log2) + 2ull * n_buckets + 2;
 	if (ppc64 * max_chains >= 0xFFFFFFFFull || ppc64 >= (1ull << FT_SEQ_BITS)) return fail(KWG_ERR_CUDA, "internal: page pool too large");
 	const uint32_t ppc = (uint32_t)ppc64;
@@ -441,7 +443,6 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	if ((rc = grow((void**)&b->d_ft_log, &b->ft_log_cap, (size_t)n_chains * ppc * sizeof(uint32_t)))) return rc;
 	if ((rc = grow((void**)&b->d_ft_plist, &b->ft_plist_cap, (size_t)n_chains * ppc * sizeof(uint32_t)))) return rc;
 	if ((rc = grow((void**)&b->d_ft_info, &b->ft_info_cap, (size_t)n_buckets * max_chains * sizeof(uint2)))) return rc;
-	if ((rc = grow((void**)&b->d_ft_npages, &b->ft_npages_cap, (size_t)n_chains * FT_MAX_BUCKETS * sizeof(uint32_t)))) return rc;
 	if ((rc = grow((void**)&b->d_ft_tiles, &b->ft_tiles_cap, (size_t)n_tiles * sizeof(uint32_t)))) return rc;
 	if ((rc = grow((void**)&b->d_ft_hm, &b->ft_hm_cap, (size_t)n_tiles * HT_POS * sizeof(uint4)))) return rc;
 	if ((rc = grow((void**)&b->d_ft_meta, &b->ft_meta_cap, meta_words * sizeof(uint32_t)))) return rc;
@@ -462,7 +463,7 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	A.hm = b->d_ft_hm; A.meta = b->d_ft_meta;
 	A.lc = G.lc; A.n_buckets = n_buckets;
 	A.max_chains = max_chains; A.pu_log2 = pu_log2; A.ppc = ppc;
-	A.pool = b->d_ft_pool; A.page_log = b->d_ft_log; A.plist = b->d_ft_plist; A.npages = b->d_ft_npages; A.info = b->d_ft_info;
+	A.pool = b->d_ft_pool; A.page_log = b->d_ft_log; A.plist = b->d_ft_plist; A.info = b->d_ft_info;
 
 	if (h_feed) {
 		if (!b->copy_stream) KWG_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
@@ -786,7 +787,7 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_rec1); cudaFree(b->d_rec2); cudaFree(b->d_offs1); cudaFree(b->d_offs2);
 	cudaFree(b->d_cnt1); cudaFree(b->d_base2); cudaFree(b->d_cbase); cudaFree(b->d_chunk_rec); cudaFree(b->d_chunk_meta);
 	cudaFree(b->d_cfirst); cudaFree(b->d_loss); cudaFree(b->d_tot_rec); cudaFree(b->d_tot_chk);
-	cudaFree(b->d_ft_pool); cudaFree(b->d_ft_log); cudaFree(b->d_ft_plist); cudaFree(b->d_ft_info); cudaFree(b->d_ft_npages);
+	cudaFree(b->d_ft_pool); cudaFree(b->d_ft_log); cudaFree(b->d_ft_plist); cudaFree(b->d_ft_info);
 	cudaFree(b->d_ft_tiles); cudaFree(b->d_ft_hm); cudaFree(b->d_ft_meta); cudaFree(b->d_ft_carry); cudaFree(b->d_inv);
 	for (cudaEvent_t e : b->feed_events) cudaEventDestroy(e);
 	if (b->copy_stream) cudaStreamDestroy(b->copy_stream);

@@ -45,7 +45,9 @@ namespace kwg {
 
 constexpr int FT_THREADS = 1024;
 constexpr int FT_SUB_LOG2 = 10;
-constexpr int FT_SUB = 1 << FT_SUB_LOG2;          // ordinals per append round (one per thread)
+constexpr int FT_SUB = 1 << FT_SUB_LOG2;          // ordinals per append round (one per thread): the resolver's ordering unit
+constexpr int FT_PER = FT_SUB / FT_THREADS;       // ordinals per thread and round
+constexpr int FT_REC = 4 * FT_PER;                // touches per thread and round
 constexpr int FT_BUCKET_LOG2 = 20;                // slots per bucket
 constexpr int FT_MAX_BUCKETS = 2048;
 constexpr int FT_RING = 16;                       // records staged per bucket
@@ -234,20 +236,19 @@ struct FtAppendParams {
 	uint8_t* pool;               // [chain][ppc] pages of (48 << pu_log2) bytes
 	uint32_t* page_log;          // [chain][ppc] bucket << 20 | page number within (chain, bucket), in allocation order
 	uint32_t* plist;             // [chain][ppc] page ids sorted by bucket, each bucket's pages in order
-	uint32_t* npages;            // [chain][FT_MAX_BUCKETS] pages of every bucket of the chain (scratch of the block)
 	uint2* info;                 // [bucket][max_chains]: x = plist index of the chain's first page, y = units in the chain
 };
 
 static inline size_t ft_append_smem_bytes()
 {
-	return (size_t)FT_MAX_BUCKETS * FT_RING_BYTES + (size_t)FT_MAX_BUCKETS * (4 + 4 + 2 + 2) + 64;
+	return (size_t)FT_MAX_BUCKETS * FT_RING_BYTES + (size_t)FT_MAX_BUCKETS * (4 + 4 + 2 + 2 + 2) + 64;
 }
 
 constexpr uint32_t FT_DIFF_MASK = 0x7FFFFu;      // (records appended - 8 * units flushed) is taken modulo 2^19
 
 // Everything of bucket b that makes whole units goes to the bucket's page chain.  One thread per bucket and round.
 __device__ __forceinline__ void ft_flush_bucket(const FtAppendParams& P, uint8_t* s_ring, const uint32_t* s_head, uint32_t* s_page,
-	uint16_t* s_tailu, uint32_t* s_next_page, uint32_t chain, uint32_t b, bool pad_rest)
+	uint16_t* s_tailu, uint16_t* s_npg, uint32_t* s_next_page, uint32_t chain, uint32_t b, bool pad_rest)
 {
 	const uint32_t pu = 1u << P.pu_log2;
 	const uint32_t head = s_head[b];
@@ -268,9 +269,8 @@ __device__ __forceinline__ void ft_flush_bucket(const FtAppendParams& P, uint8_t
 	do {
 		if (fill == pu) {
 			page = atomicAdd(s_next_page, 1u);
-			uint32_t* np = P.npages + (size_t)chain * FT_MAX_BUCKETS + b;
-			const uint32_t seq = __ldcg(np);
-			__stcg(np, seq + 1u);
+			const uint32_t seq = s_npg[b];                   // (the host sizes the pages so that a chain has fewer than 2^16 of them)
+			s_npg[b] = (uint16_t)(seq + 1u);
 			P.page_log[(uint64_t)chain * P.ppc + page] = (b << FT_SEQ_BITS) | seq;
 			fill = 0;
 		}
@@ -295,7 +295,8 @@ ft_append_kernel(const FtAppendParams P)
 	uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw + (size_t)FT_MAX_BUCKETS * FT_RING_BYTES);   // records appended (free running)
 	uint32_t* s_page = s_head + FT_MAX_BUCKETS;                                        // page << 6 | units in it
 	uint16_t* s_tailu = reinterpret_cast<uint16_t*>(s_page + FT_MAX_BUCKETS);          // units flushed (mod 2^16)
-	uint16_t* s_items = s_tailu + FT_MAX_BUCKETS;                                      // buckets with a whole unit this round
+	uint16_t* s_npg = s_tailu + FT_MAX_BUCKETS;                                        // pages of the bucket so far
+	uint16_t* s_items = s_npg + FT_MAX_BUCKETS;                                        // buckets with a whole unit this round
 	uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_items + FT_MAX_BUCKETS);          // [0] next page of the pool, [1..2] item counts by round parity
 
 	const uint32_t tid = threadIdx.x;
@@ -304,8 +305,7 @@ ft_append_kernel(const FtAppendParams P)
 	const uint32_t nb = P.n_buckets;
 
 	for (uint32_t b = tid; b < (uint32_t)FT_MAX_BUCKETS; b += FT_THREADS) {
-		s_head[b] = 0; s_page[b] = pu; s_tailu[b] = 0;
-		P.npages[(size_t)chain * FT_MAX_BUCKETS + b] = 0;
+		s_head[b] = 0; s_page[b] = pu; s_tailu[b] = 0; s_npg[b] = 0;
 	}
 	if (tid < 3) s_misc[tid] = 0;
 	__syncthreads();
@@ -317,46 +317,80 @@ ft_append_kernel(const FtAppendParams P)
 	const uint32_t o_end = ord0 + min(n_ok, (blockIdx.x + 1) * per);
 	uint32_t round = 0;
 
-	uint4 v_next = make_uint4(0u, 0u, 0u, 0u);
-	{
-		const uint32_t o = (o_begin & ~(uint32_t)(FT_SUB - 1)) + tid;
-		if (o >= o_begin && o < o_end) v_next = ld_nc_v4(P.hm + o);
+	const uint32_t lane = tid & 31u;
+	uint4 v_next[FT_PER];
+#pragma unroll
+	for (int i = 0; i < FT_PER; ++i) {
+		const uint32_t o = (o_begin & ~(uint32_t)(FT_SUB - 1)) + i * FT_THREADS + tid;
+		v_next[i] = make_uint4(FT_TWIN, FT_TWIN, FT_TWIN, FT_TWIN);
+		if (o >= o_begin && o < o_end) v_next[i] = ld_nc_v4(P.hm + o);
 	}
 #pragma unroll 1
 	for (uint32_t a = o_begin & ~(uint32_t)(FT_SUB - 1); a < o_end; a += FT_SUB) {
-		const uint32_t o = a + tid;
-		uint32_t bkt[4], rlo[4], rhi = 0, pend = 0;
-		const uint4 v = v_next;
-		if (o + FT_SUB < o_end) v_next = ld_nc_v4(P.hm + o + FT_SUB);        // the next round's hashes travel during this one
-		if (o >= o_begin && o < o_end) {
-			const uint32_t hmv[4] = {v.x, v.y, v.z, v.w};
-			rhi = o >> 12;
+		// a touch is kept as its hash (FT_TWIN: nothing to append); bucket and record word are derived when needed
+		uint32_t hm[FT_REC], pend = 0;
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				if (hmv[j] != FT_TWIN) pend |= 1u << j;
-				const uint32_t slot = ((uint32_t)(j >> 1) << P.lc) | hmv[j];          // lc <= 30
-				bkt[j] = (slot >> FT_BUCKET_LOG2) & (nb - 1u);
-				rlo[j] = (slot & ((1u << FT_BUCKET_LOG2) - 1u)) | ((o & 0xFFFu) << FT_BUCKET_LOG2);
-			}
+		for (int i = 0; i < FT_PER; ++i) {
+			const uint32_t o = a + i * FT_THREADS + tid;
+			const uint4 v = v_next[i];
+			hm[4 * i] = v.x; hm[4 * i + 1] = v.y; hm[4 * i + 2] = v.z; hm[4 * i + 3] = v.w;
+			// the next round's hashes travel during this one
+			v_next[i] = make_uint4(FT_TWIN, FT_TWIN, FT_TWIN, FT_TWIN);
+			if (o + FT_SUB < o_end) v_next[i] = ld_nc_v4(P.hm + o + FT_SUB);
 		}
+#pragma unroll
+		for (int j = 0; j < FT_REC; ++j) pend |= (hm[j] != FT_TWIN) ? 1u << j : 0u;
+#define FT_SLOT(j) ((((uint32_t)(((j) >> 1) & 1)) << P.lc) | hm[j])
+#define FT_BKT(j) ((FT_SLOT(j) >> FT_BUCKET_LOG2) & (nb - 1u))
 		// append what fits into the rings; the append that completes a bucket's first whole unit of the round puts the
 		// bucket on the flush list; the list is flushed one bucket per thread; again if a ring was full
 		while (true) {
 			uint32_t* items_n = &s_misc[1 + (round & 1u)];
+			// (the ring counters first, then the stores: independent shared-memory operations in flight together)
+			uint32_t old[FT_REC], tl[FT_REC];
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
+			for (int j = 0; j < FT_REC; ++j) {
+				old[j] = 0; tl[j] = 0;
+				if ((pend >> j) & 1u) { const uint32_t b = FT_BKT(j); old[j] = atomicAdd(&s_head[b], 1u); tl[j] = s_tailu[b]; }
+			}
+			uint32_t pushm = 0;
+#pragma unroll
+			for (int j = 0; j < FT_REC; ++j) {
 				if ((pend >> j) & 1u) {
-					const uint32_t b = bkt[j];
-					const uint32_t old = atomicAdd(&s_head[b], 1u);
-					const uint32_t d = (old - ((uint32_t)s_tailu[b] << 3)) & FT_DIFF_MASK;
+					const uint32_t slot = FT_SLOT(j), b = (slot >> FT_BUCKET_LOG2) & (nb - 1u);
+					const uint32_t d = (old[j] - (tl[j] << 3)) & FT_DIFF_MASK;
 					if (d < (uint32_t)FT_RING) {
+						const uint32_t o = a + (j >> 2) * FT_THREADS + tid;
 						uint8_t* r = s_ring + (size_t)b * FT_RING_BYTES;
-						reinterpret_cast<uint32_t*>(r)[old & 15u] = rlo[j];
-						reinterpret_cast<uint16_t*>(r + 64)[old & 15u] = (uint16_t)rhi;
+						reinterpret_cast<uint32_t*>(r)[old[j] & 15u] = (slot & ((1u << FT_BUCKET_LOG2) - 1u)) | ((o & 0xFFFu) << FT_BUCKET_LOG2);
+						reinterpret_cast<uint16_t*>(r + 64)[old[j] & 15u] = (uint16_t)(o >> 12);
 						pend &= ~(1u << j);
-						if (d == (uint32_t)FT_UNIT - 1u) s_items[atomicAdd(items_n, 1u)] = (uint16_t)b;
+						if (d == (uint32_t)FT_UNIT - 1u) pushm |= 1u << j;
 					} else {
 						atomicSub(&s_head[b], 1u);
+					}
+				}
+			}
+			// flush list: one counter update per warp
+			{
+				const uint32_t mine = __popc(pushm);
+				uint32_t inc = mine;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+					if (lane >= (uint32_t)o) inc += y;
+				}
+				const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+				if (total) {
+					uint32_t base = 0;
+					if (lane == 31) base = atomicAdd(items_n, total);
+					base = __shfl_sync(0xFFFFFFFFu, base, 31) + inc - mine;
+					for (uint32_t m = pushm; m; m &= m - 1u) {
+						const int j = __ffs(m) - 1;
+						uint32_t b = 0;
+#pragma unroll
+						for (int jj = 0; jj < FT_REC; ++jj) if (jj == j) b = FT_BKT(jj);
+						s_items[base++] = (uint16_t)b;
 					}
 				}
 			}
@@ -364,24 +398,25 @@ ft_append_kernel(const FtAppendParams P)
 			const uint32_t n_items = *items_n;
 			if (tid == 0) s_misc[1 + ((round + 1u) & 1u)] = 0;
 			for (uint32_t i = tid; i < n_items; i += FT_THREADS)
-				ft_flush_bucket(P, s_ring, s_head, s_page, s_tailu, &s_misc[0], chain, s_items[i], false);
+				ft_flush_bucket(P, s_ring, s_head, s_page, s_tailu, s_npg, &s_misc[0], chain, s_items[i], false);
 			++round;
 			if (!__syncthreads_or(pend != 0u)) break;
 		}
+#undef FT_SLOT
+#undef FT_BKT
 	}
 
 	// ---- end of the range: pad and flush what is left in the rings
 	__syncthreads();
 	for (uint32_t b = tid; b < nb; b += FT_THREADS)
-		ft_flush_bucket(P, s_ring, s_head, s_page, s_tailu, &s_misc[0], chain, b, true);
+		ft_flush_bucket(P, s_ring, s_head, s_page, s_tailu, s_npg, &s_misc[0], chain, b, true);
 	__syncthreads();
 
 	// ---- page lists: prefix sum of the pages per bucket, then every logged page finds its place
 	uint32_t* s_first = reinterpret_cast<uint32_t*>(s_ring);            // the rings are free now
 	uint32_t* s_warp = s_first + FT_MAX_BUCKETS;
 	{
-		const uint32_t* np = P.npages + (size_t)chain * FT_MAX_BUCKETS;
-		const uint32_t c0 = __ldcg(np + 2 * tid), c1 = __ldcg(np + 2 * tid + 1);
+		const uint32_t c0 = s_npg[2 * tid], c1 = s_npg[2 * tid + 1];
 		uint32_t total;
 		const uint32_t ex = block_exclusive_scan_1024(c0 + c1, total, s_warp);
 		s_first[2 * tid] = ex;
@@ -471,7 +506,7 @@ ft_resolve_kernel(const FtResolveParams P)
 	uint32_t* s_list = s_pages + FR_PAGES + 1;                                          // [2][4][FR_CONF]: late slot, late ord, claimer slot, claimer ord (8-byte aligned)
 	uint32_t* s_filt = s_list + 2 * 4 * FR_CONF;                                        // [2][FR_FILT_WORDS]
 	uint32_t* s_warp = s_filt + 2 * FR_FILT_WORDS;                                      // 32
-	uint32_t* s_misc = s_warp + 32;                                                     // per parity: [0] late, [1] claimers listed, [2] carry, [3] tail tile
+	uint32_t* s_misc = s_warp + 32;                                                     // per parity: [0] late, [1] claimers listed, [2] carry, [3] tail tile; [8] round to skip, [9] round carried
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t pu = 1u << P.pu_log2;
@@ -488,7 +523,7 @@ ft_resolve_kernel(const FtResolveParams P)
 			for (uint32_t i = tid; i < bw / 4; i += FR_THREADS) reinterpret_cast<uint4*>(s_bm)[i] = make_uint4(0u, 0u, 0u, 0u);
 		}
 		for (uint32_t i = tid; i < (uint32_t)(2 * FR_FILT_WORDS); i += FR_THREADS) s_filt[i] = 0;
-		if (tid < 8) s_misc[tid] = (tid == 3 || tid == 7) ? FR_NO_TILE : 0u;
+		if (tid < 10) s_misc[tid] = (tid == 3 || tid == 7 || tid >= 8) ? FR_NO_TILE : 0u;
 		// ---- chain table: where every chain's units (and pages) start in the bucket's flat numbering
 		{
 			uint2 inf = make_uint2(0u, 0u);
@@ -559,10 +594,31 @@ ft_resolve_kernel(const FtResolveParams P)
 			const uint32_t par = w & 1u, nxt = par ^ 1u;
 			uint32_t* mi = s_misc + 4 * par;
 			uint32_t* mn = s_misc + 4 * nxt;
-			const uint32_t n_carry = mi[2];
+			uint32_t n_carry = mi[2];
 			if (n_carry > (uint32_t)FR_CARRY) __trap();        // cannot happen: a round is 1024 ordinals of 4 touches
-			// a carry of more than 1024 records: this window takes no new units, only the first 1024 of the carry
+			// A carry of more than 1024 records: this window takes no new units.  The records of one round are in no order, so
+			// the WHOLE round must be settled together: what the units in flight hold of it joins the carry first (and the
+			// next window skips those records), then the eight slots of the unit that is not taken hold the carried round.
 			const bool carry_only = n_carry > (uint32_t)FR_CARRY_SMEM;
+			const uint32_t skip_tile = carry_only ? FR_NO_TILE : s_misc[8];
+			if (carry_only) {
+				const uint32_t x_tile = s_misc[9];
+				const uint32_t lo8[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+				const uint32_t hi4[4] = {f2.x, f2.y, f2.z, f2.w};
+#pragma unroll
+				for (int q = 0; q < FR_OWN; ++q) {
+					const uint32_t lo = lo8[q], hi = (q & 1) ? (hi4[q >> 1] >> 16) : (hi4[q >> 1] & 0xFFFFu);
+					if (((((hi << 12) | (lo >> FT_BUCKET_LOG2))) >> FT_SUB_LOG2) == x_tile) {
+						const uint32_t at = atomicAdd(&mi[2], 1u);
+						if (at < (uint32_t)FR_CARRY_SMEM) { s_clo[par * FR_CARRY_SMEM + at] = lo; s_chi[par * FR_CARRY_SMEM + at] = (uint16_t)hi; }
+						else if (at < (uint32_t)FR_CARRY) __stcg(&g_carry[par * FR_CARRY + at], make_uint2(lo, hi));
+					}
+				}
+				if (tid == 0) s_misc[8] = x_tile;
+				__syncthreads();
+				n_carry = mi[2];
+				if (n_carry > (uint32_t)FR_CARRY) __trap();
+			}
 			const uint32_t tail_tile = carry_only ? FR_NO_TILE : mi[3];
 			const bool more = !carry_only && u0 + FR_WIN_UNITS < n_units;
 
@@ -597,21 +653,25 @@ ft_resolve_kernel(const FtResolveParams P)
 			if (more) fetch(u0 + FR_WIN_UNITS);
 
 			uint32_t cand = 0;           // bit q: record q takes part and its slot was untouched before this window
-			uint32_t bmw[FR_SLOTS];
 #pragma unroll
-			for (int q = 0; q < FR_SLOTS; ++q) bmw[q] = s_bm[(rl[q] & ((1u << FT_BUCKET_LOG2) - 1u)) >> 5];
+			for (int q0 = 0; q0 < FR_SLOTS; q0 += 5) {
+				uint32_t bmw[5];             // (several bitmap words first, then the decisions: loads in flight together)
 #pragma unroll
-			for (int q = 0; q < FR_SLOTS; ++q) {
-				const uint32_t lo = rl[q], hi = FR_HI(rh, q);
-				const uint32_t ord = (hi << 12) | (lo >> FT_BUCKET_LOG2);
-				if ((ord >> FT_SUB_LOG2) == tail_tile) {
-					// the rest of the window's last round waits for the next window (in any order: it has none)
-					const uint32_t at = atomicAdd(&mn[2], 1u);
-					if (at < (uint32_t)FR_CARRY_SMEM) { s_clo[nxt * FR_CARRY_SMEM + at] = lo; s_chi[nxt * FR_CARRY_SMEM + at] = (uint16_t)hi; }
-					else if (at < (uint32_t)FR_CARRY) __stcg(&g_carry[nxt * FR_CARRY + at], make_uint2(lo, hi));
-				} else if (ord != FT_NULL_ORD) {
-					if ((bmw[q] >> (lo & 31u)) & 1u) ft_charge_loss(P, ord);
-					else cand |= 1u << q;
+				for (int q = q0; q < q0 + 5 && q < FR_SLOTS; ++q) bmw[q - q0] = s_bm[(rl[q] & ((1u << FT_BUCKET_LOG2) - 1u)) >> 5];
+#pragma unroll
+				for (int q = q0; q < q0 + 5 && q < FR_SLOTS; ++q) {
+					const uint32_t lo = rl[q], hi = FR_HI(rh, q);
+					const uint32_t ord = (hi << 12) | (lo >> FT_BUCKET_LOG2);
+					if ((ord >> FT_SUB_LOG2) == skip_tile) continue;      // settled with its round by the window before
+					if ((ord >> FT_SUB_LOG2) == tail_tile) {
+						// the rest of the window's last round waits for the next window (in any order: it has none)
+						const uint32_t at = atomicAdd(&mn[2], 1u);
+						if (at < (uint32_t)FR_CARRY_SMEM) { s_clo[nxt * FR_CARRY_SMEM + at] = lo; s_chi[nxt * FR_CARRY_SMEM + at] = (uint16_t)hi; }
+						else if (at < (uint32_t)FR_CARRY) __stcg(&g_carry[nxt * FR_CARRY + at], make_uint2(lo, hi));
+					} else if (ord != FT_NULL_ORD) {
+						if ((bmw[q - q0] >> (lo & 31u)) & 1u) ft_charge_loss(P, ord);
+						else cand |= 1u << q;
+					}
 				}
 			}
 			__syncthreads();                                                            // B1
@@ -623,11 +683,20 @@ ft_resolve_kernel(const FtResolveParams P)
 			uint32_t* c_slot = l_pos + FR_CONF;
 			uint32_t* c_pos = c_slot + FR_CONF;
 			uint32_t* filt = s_filt + par * FR_FILT_WORDS;
+			// (several claims first, then their outcomes: independent shared-memory atomics in flight together)
 #pragma unroll
-			for (int q = 0; q < FR_SLOTS; ++q) {
-				if ((cand >> q) & 1u) {
+			for (int q0 = 0; q0 < FR_SLOTS; q0 += 5) {
+				uint32_t seen[5];
+#pragma unroll
+				for (int q = q0; q < q0 + 5 && q < FR_SLOTS; ++q) {
+					const uint32_t slot = rl[q] & ((1u << FT_BUCKET_LOG2) - 1u);
+					seen[q - q0] = 0;
+					if ((cand >> q) & 1u) seen[q - q0] = atomicOr(&s_bm[slot >> 5], 1u << (slot & 31u));
+				}
+#pragma unroll
+				for (int q = q0; q < q0 + 5 && q < FR_SLOTS; ++q) {
 					const uint32_t slot = rl[q] & ((1u << FT_BUCKET_LOG2) - 1u), bit = 1u << (slot & 31u);
-					if (atomicOr(&s_bm[slot >> 5], bit) & bit) {
+					if (((cand >> q) & 1u) && (seen[q - q0] & bit)) {
 						late |= 1u << q;
 						const uint32_t c = atomicAdd(&mi[0], 1u);
 						if (c < (uint32_t)FR_CONF) { l_slot[c] = slot; l_pos[c] = FR_POS(rl, rh, q); }
@@ -640,36 +709,33 @@ ft_resolve_kernel(const FtResolveParams P)
 			// ---- P3a
 			if (n_late && n_late <= (uint32_t)FR_CONF) {
 				const uint32_t claim = cand & ~late;
+				uint32_t fw[FR_SLOTS];
+#pragma unroll
+				for (int q = 0; q < FR_SLOTS; ++q) fw[q] = filt[((rl[q] & ((1u << FT_BUCKET_LOG2) - 1u)) >> 5) & (FR_FILT_WORDS - 1)];
 #pragma unroll
 				for (int q = 0; q < FR_SLOTS; ++q) {
-					if ((claim >> q) & 1u) {
-						const uint32_t slot = rl[q] & ((1u << FT_BUCKET_LOG2) - 1u);
-						if ((filt[(slot >> 5) & (FR_FILT_WORDS - 1)] >> (slot & 31u)) & 1u) {
-							const uint32_t c = atomicAdd(&mi[1], 1u);
-							if (c < (uint32_t)FR_CONF) { c_slot[c] = slot; c_pos[c] = FR_POS(rl, rh, q); }
-						}
+					if (((claim >> q) & 1u) && ((fw[q] >> (rl[q] & 31u)) & 1u)) {
+						const uint32_t c = atomicAdd(&mi[1], 1u);
+						if (c < (uint32_t)FR_CONF) { c_slot[c] = rl[q] & ((1u << FT_BUCKET_LOG2) - 1u); c_pos[c] = FR_POS(rl, rh, q); }
 					}
 				}
 			}
 			// housekeeping for the next window: its lists, filter and tail tile; the carry buffer this window read is free again
-			if (tid == 0) { mn[0] = 0; mn[1] = 0; mi[2] = 0; }
+			if (tid == 0) { mn[0] = 0; mn[1] = 0; mi[2] = 0; if (!carry_only) { s_misc[8] = FR_NO_TILE; s_misc[9] = tail_tile; } }
 			if (tid < (uint32_t)FR_FILT_WORDS) s_filt[nxt * FR_FILT_WORDS + tid] = 0;
 			if (more) publish_tail(u0 + FR_WIN_UNITS, nxt);
 			__syncthreads();                                                            // B3
 			const uint32_t n_claim = mi[1];
 			if (n_late && n_late <= (uint32_t)FR_CONF && n_claim <= (uint32_t)FR_CONF) {
-				// ---- P3b: one thread per listed record
-				if (tid < n_late) {
-					const uint32_t slot = l_slot[tid], pos = l_pos[tid];
+				// ---- P3b: a warp per listed record i, its lanes over the listed records c: i loses to an earlier c on its slot
+				// (a claimer can only lose to a late contender: there is one claimer per slot)
+				const uint32_t n_all = n_late + n_claim;
+				for (uint32_t i = tid >> 5; i < n_all; i += FR_THREADS / 32) {
+					const uint32_t si = (i < n_late) ? l_slot[i] : c_slot[i - n_late], pi = (i < n_late) ? l_pos[i] : c_pos[i - n_late];
 					bool lose = false;
-					for (uint32_t c = 0; c < n_late; ++c) lose = lose || (l_slot[c] == slot && l_pos[c] < pos);
-					for (uint32_t c = 0; c < n_claim; ++c) lose = lose || (c_slot[c] == slot && c_pos[c] < pos);
-					if (lose) ft_charge_loss(P, pos);
-				} else if (tid >= (uint32_t)FR_CONF && tid - FR_CONF < n_claim) {
-					const uint32_t slot = c_slot[tid - FR_CONF], pos = c_pos[tid - FR_CONF];
-					bool lose = false;
-					for (uint32_t c = 0; c < n_late; ++c) lose = lose || (l_slot[c] == slot && l_pos[c] < pos);
-					if (lose) ft_charge_loss(P, pos);
+					for (uint32_t c = tid & 31u; c < n_late; c += 32) lose = lose || (l_slot[c] == si && l_pos[c] < pi);
+					if (i < n_late) for (uint32_t c = tid & 31u; c < n_claim; c += 32) lose = lose || (c_slot[c] == si && c_pos[c] < pi);
+					if (__any_sync(0xFFFFFFFFu, lose) && (tid & 31u) == 0) ft_charge_loss(P, pi);
 				}
 			} else if (n_late) {
 				// ---- thousands of records on a few slots (low-complexity reads): min-reduction rounds over all the
