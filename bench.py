@@ -564,16 +564,29 @@ def stage_search(D, args, windows):
     qb, qo = h_q.numpy(), h_qo.numpy().view(np.uint64)
     n_hits = [0]
 
-    from kwage_b200 import sharding
+    # the one collective of the path, inside the product: kwg_search_gather = per-slab search + one NCCL exchange of the
+    # compacted hit lists (HBM to HBM over NVLink) + merge on rank 0 with global column indices
+    comm = None
+    if D.enabled:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if D.rank == 0:
+            uid = torch.tensor(list(capi.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        D.dist.broadcast(uid, src=0)
+        comm = capi.Comm.create(dev, D.world, D.rank, bytes(uid.cpu().numpy().tobytes()))
+    h_nk = torch.empty(nq, dtype=torch.int32).pin_memory()
 
     def step_host(i):
-        hits, nk = db.search_flat(qb, qo, 0.5)
-        # the one collective of the path: per-slab hit lists -> rank 0 (NCCL gather over NVLink)
-        merged = sharding.gather_hits(hits, D.rank * F, D.dist if D.enabled else None, dst=0, device="cuda")
-        if merged is not None:
-            n_hits[0] = len(merged)
+        if comm is not None:
+            n = db.search_gather_ptr(comm, h_q.data_ptr(), h_qo.data_ptr(), nq, 0.5, D.rank * F, h_nk.data_ptr(), root=0)
+            if D.rank == 0:
+                n_hits[0] = n
+        else:
+            hits, nk = db.search_flat(qb, qo, 0.5)
+            n_hits[0] = len(hits)
 
     sec_e2e = timed(D, db.stream(), step_host, steps, 1, windows)
+    if comm is not None:
+        comm.close()
     db.close()
     del slab, d_counts
     torch.cuda.empty_cache()

@@ -203,6 +203,37 @@ int kwg_search_counts_dev(kwg_db_t* db, const char* d_bases, const uint64_t* d_o
 	uint64_t n_bases, uint32_t* d_n_query_kmers, uint32_t* d_counts, uint64_t count_pitch);
 int kwg_db_sync(kwg_db_t* db);
 void kwg_free_hits(kwg_hit_t* hits);
+/* kwg_search works through the queries in batches so that its per-(query, filter) counts stay below this many bytes
+ * (default 1 GiB); the reference streams one query at a time (kwage.cpp:116-148). */
+int kwg_db_set_count_budget(kwg_db_t* db, uint64_t bytes);
+/* kwg_search that leaves the hit list in HBM (owned by the handle, valid until its next search): *d_hits is a DEVICE pointer.
+ * filter0 is added to every filter index (the slab's first column in the whole database). */
+int kwg_search_hits_dev(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
+	uint32_t* n_query_kmers, uint32_t filter0, const kwg_hit_t** d_hits, uint64_t* n_hits);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU search: every device holds a column slab of the database (the reference's unit is the database file,
+ * one OpenMP thread each: kwage.cpp:76-87) and searches all the queries; the per-slab hit lists are gathered on the
+ * root with one exchange over NCCL and merged into kwg_search's (query, filter) order with global filter indices --
+ * what the reference's critical section kwage.cpp:154-177 does with its thread-local maps.
+ * One kwg_comm_t per device; either one per process (kwg_comm_create with an id made by rank 0 and handed to the other
+ * ranks by the host's own means: MPI, torch.distributed, a file) or all of them in one process (kwg_comm_create_all,
+ * then one host thread per device).  NCCL is loaded at run time (libnccl.so.2); without it these calls fail with
+ * KWG_ERR_CUDA and nothing else in the library is affected.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kwg_comm kwg_comm_t;
+#define KWG_COMM_ID_BYTES 128
+int kwg_comm_get_unique_id(uint8_t* id /* KWG_COMM_ID_BYTES */);
+int kwg_comm_create(kwg_comm_t** out, int device, int n_ranks, int rank, const uint8_t* id);
+int kwg_comm_create_all(kwg_comm_t** out /* n */, int n, const int* devices);
+void kwg_comm_destroy(kwg_comm_t* c);
+/* Collective: every rank calls it with the same queries and threshold and its own slab (filter0 = first column of the
+ * slab).  On the root *hits / *n_hits receive the merged list (release with kwg_free_hits); elsewhere *n_hits = 0. */
+int kwg_search_gather(kwg_db_t* db, kwg_comm_t* comm, int root, const char* bases, const uint64_t* offsets, uint32_t n_queries,
+	float threshold, uint32_t filter0, uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits);
+/* The merge step on its own (host only): n_lists lists laid end to end, each ordered by (query, filter), list r holding
+ * the columns before those of list r + 1; out receives them ordered by (query, filter). */
+void kwg_merge_hits(const kwg_hit_t* lists, const uint64_t* list_len, uint32_t n_lists, uint32_t n_queries, kwg_hit_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * Device-side synthetic inputs for benchmarks (same generators as oracle/kwage_oracle.c).

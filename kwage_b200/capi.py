@@ -28,6 +28,8 @@ EXPORTS = [
     "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev", "kwg_host_alloc", "kwg_host_free",
     "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_upload_columns", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
+    "kwg_db_set_count_budget", "kwg_search_hits_dev",
+    "kwg_comm_get_unique_id", "kwg_comm_create", "kwg_comm_create_all", "kwg_comm_destroy", "kwg_search_gather", "kwg_merge_hits",
     "kwg_synth_reads_dev", "kwg_synth_filter_bits_dev", "kwg_synth_plant_dev",
     "kwg_bloom_set_timing", "kwg_bloom_get_timing", "kwg_db_set_timing", "kwg_db_get_timing",
 ]
@@ -96,6 +98,16 @@ def lib():
     L.kwg_search_counts.argtypes = [vp, vp, vp, u32, vp, vp]
     L.kwg_search_counts_dev.argtypes = [vp, vp, vp, u32, u64, vp, vp, u64]
     L.kwg_db_sync.argtypes = [vp]
+    L.kwg_db_set_count_budget.argtypes = [vp, u64]
+    L.kwg_search_hits_dev.argtypes = [vp, vp, vp, u32, f32, vp, u32, pvp, C.POINTER(u64)]
+    L.kwg_comm_get_unique_id.argtypes = [vp]
+    L.kwg_comm_create.argtypes = [pvp, i32, i32, i32, vp]
+    L.kwg_comm_create_all.argtypes = [pvp, i32, vp]
+    L.kwg_comm_destroy.argtypes = [vp]
+    L.kwg_comm_destroy.restype = None
+    L.kwg_search_gather.argtypes = [vp, vp, i32, vp, vp, u32, f32, u32, vp, C.POINTER(C.POINTER(Hit)), C.POINTER(u64)]
+    L.kwg_merge_hits.argtypes = [vp, vp, u32, u32, vp]
+    L.kwg_merge_hits.restype = None
     L.kwg_db_stream.argtypes = [vp, pvp]
     L.kwg_free_hits.argtypes = [C.POINTER(Hit)]
     L.kwg_free_hits.restype = None
@@ -355,6 +367,50 @@ class Database:
                 lib().kwg_free_hits(hp)
         return hits, nk[:nq]
 
+    def set_count_budget(self, n_bytes):
+        check(lib().kwg_db_set_count_budget(self.h, int(n_bytes)))
+
+    def search_hits_dev(self, bases, offsets, threshold, filter0=0):
+        """kwg_search_hits_dev: -> (device pointer of the hit list, number of hits, n_query_kmers)"""
+        bases = _as_bases(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nq = len(offsets) - 1
+        nk = np.zeros(max(nq, 1), dtype=np.uint32)
+        dp = C.c_void_p()
+        nh = C.c_uint64(0)
+        check(lib().kwg_search_hits_dev(self.h, _np_ptr(bases), _np_ptr(offsets), nq, C.c_float(threshold), _np_ptr(nk), int(filter0),
+                                        C.byref(dp), C.byref(nh)))
+        return dp.value or 0, nh.value, nk[:nq]
+
+    def search_gather(self, comm, bases, offsets, threshold, filter0, root=0):
+        """kwg_search_gather (collective over `comm`): merged hits with global filter indices on the root, an empty
+        array elsewhere; plus n_query_kmers."""
+        bases = _as_bases(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nq = len(offsets) - 1
+        nk = np.zeros(max(nq, 1), dtype=np.uint32)
+        hp = C.POINTER(Hit)()
+        nh = C.c_uint64(0)
+        check(lib().kwg_search_gather(self.h, comm.h, int(root), _np_ptr(bases), _np_ptr(offsets), nq, C.c_float(threshold), int(filter0),
+                                      _np_ptr(nk), C.byref(hp), C.byref(nh)))
+        try:
+            hits = np.frombuffer(C.string_at(hp, nh.value * C.sizeof(Hit)), dtype=HIT_DTYPE).copy() if nh.value else np.zeros(0, dtype=HIT_DTYPE)
+        finally:
+            if nh.value:
+                lib().kwg_free_hits(hp)
+        return hits, nk[:nq]
+
+    def search_gather_ptr(self, comm, bases_ptr, offsets_ptr, n_queries, threshold, filter0, nk_ptr, root=0):
+        """Same with raw host pointers (benchmarks); returns the number of hits delivered to this rank."""
+        hp = C.POINTER(Hit)()
+        nh = C.c_uint64(0)
+        check(lib().kwg_search_gather(self.h, comm.h, int(root), bases_ptr, offsets_ptr, int(n_queries), C.c_float(threshold), int(filter0),
+                                      nk_ptr, C.byref(hp), C.byref(nh)))
+        n = nh.value
+        if n:
+            lib().kwg_free_hits(hp)
+        return n
+
     def search_ptrs(self, queries, threshold):
         """Same through kwg_search_ptrs (one pointer per query)."""
         arrs = [_as_bases(q) for q in queries]
@@ -421,6 +477,50 @@ class Database:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """kwg_comm_t: the NCCL communicator behind kwg_search_gather (one per device)."""
+
+    def __init__(self, h, rank, n_ranks):
+        self.h, self.rank, self.n_ranks = h, rank, n_ranks
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().kwg_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, device, n_ranks, rank, uid):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        check(lib().kwg_comm_create(C.byref(h), device, n_ranks, rank, buf))
+        return cls(h, rank, n_ranks)
+
+    @classmethod
+    def create_all(cls, devices):
+        n = len(devices)
+        hs = (C.c_void_p * n)()
+        devs = (C.c_int * n)(*devices)
+        check(lib().kwg_comm_create_all(hs, n, devs))
+        return [cls(C.c_void_p(hs[i]), i, n) for i in range(n)]
+
+    def close(self):
+        if self.h:
+            lib().kwg_comm_destroy(self.h)
+            self.h = None
+
+
+def merge_hits(lists, n_queries):
+    """kwg_merge_hits: per-slab hit arrays (each ordered by (query, filter), slabs in column order, global filter
+    indices) -> one array ordered by (query, filter)."""
+    lens = np.array([len(x) for x in lists], dtype=np.uint64)
+    flat = np.concatenate([np.asarray(x, dtype=HIT_DTYPE) for x in lists]) if len(lists) else np.zeros(0, dtype=HIT_DTYPE)
+    out = np.zeros(len(flat), dtype=HIT_DTYPE)
+    if len(flat):
+        lib().kwg_merge_hits(_np_ptr(flat), _np_ptr(lens), len(lists), int(n_queries), _np_ptr(out))
+    return out
 
 
 def synth_reads_dev(seed, first_read, n_reads, read_len, d_bases_ptr, d_offsets_ptr=0, *, device=0, stream=0):

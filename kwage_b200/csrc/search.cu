@@ -13,6 +13,9 @@
 //                        489-503) and compact (query, filter, num_match) in (query, filter) order.
 #include "common.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is loaded with dlopen
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -246,7 +249,7 @@ template <int PASS>
 __global__ void __launch_bounds__(256)
 hits_kernel(const uint32_t* __restrict__ counts, uint64_t count_pitch, uint32_t n_filters, const uint32_t* __restrict__ n_kmers,
 	uint32_t n_queries, float threshold, uint32_t* __restrict__ hit_count, const uint64_t* __restrict__ hit_base,
-	kwg_hit_t* __restrict__ hits)
+	kwg_hit_t* __restrict__ hits, uint32_t query0, uint32_t filter0)
 {
 	const uint32_t q = (blockIdx.x * 256 + threadIdx.x) >> 5;
 	const uint32_t lane = threadIdx.x & 31;
@@ -268,13 +271,41 @@ hits_kernel(const uint32_t* __restrict__ counts, uint64_t count_pitch, uint32_t 
 		const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
 		if (PASS == 1 && hit) {
 			kwg_hit_t h;
-			h.query = q; h.filter = f; h.num_match = complete ? n : cnt;   // kwage.cpp:519-520
+			h.query = query0 + q; h.filter = filter0 + f; h.num_match = complete ? n : cnt;   // kwage.cpp:519-520
 			hits[at + __popc(m & ((1u << lane) - 1u))] = h;
 		}
 		at += __popc(m);
 		total += __popc(m);
 	}
 	if (PASS == 0 && lane == 0) hit_count[q] = total;
+}
+
+// exclusive prefix of the per-query hit counts (one block): hit_base[q] = *total + sum of the counts before q; *total advances
+__global__ void __launch_bounds__(1024)
+hit_scan_kernel(const uint32_t* __restrict__ hit_count, uint32_t n_queries, uint64_t* __restrict__ hit_base, unsigned long long* __restrict__ total)
+{
+	__shared__ unsigned long long s_w[32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned long long carry = *total;
+	for (uint32_t q0 = 0; q0 < n_queries; q0 += 1024) {
+		const uint32_t q = q0 + tid;
+		const unsigned long long c = (q < n_queries) ? hit_count[q] : 0ull;
+		unsigned long long inc = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+			if (lane >= (uint32_t)o) inc += y;
+		}
+		__syncthreads();
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		unsigned long long base = 0, tot = 0;
+		for (int w = 0; w < 32; ++w) { if ((uint32_t)w < warp) base += s_w[w]; tot += s_w[w]; }
+		if (q < n_queries) hit_base[q] = carry + base + inc - c;
+		carry += tot;
+	}
+	__syncthreads();
+	if (tid == 0) *total = carry;
 }
 
 } // namespace kwg
@@ -300,6 +331,9 @@ struct kwg_db {
 	uint32_t* d_hit_count = nullptr;  size_t hit_count_cap = 0;
 	uint64_t* d_hit_base = nullptr;   size_t hit_base_cap = 0;
 	kwg_hit_t* d_hits = nullptr;      size_t hits_cap = 0;
+	unsigned long long* d_hit_total = nullptr;          // running length of d_hits
+	unsigned long long* h_hit_total = nullptr;          // pinned
+	uint64_t count_budget = 1ull << 30;                 // bytes of per-(query, filter) counts held at a time (kwg_search batches its queries)
 	KernelTimers timers;
 };
 
@@ -417,6 +451,8 @@ void kwg_db_unload(kwg_db_t* db)
 	if (db->owns_slab) cudaFree(db->slab);
 	cudaFree(db->d_bases); cudaFree(db->d_offsets); cudaFree(db->d_table); cudaFree(db->d_kmers); cudaFree(db->d_rows);
 	cudaFree(db->d_nk); cudaFree(db->d_counts); cudaFree(db->d_hit_count); cudaFree(db->d_hit_base); cudaFree(db->d_hits);
+	cudaFree(db->d_hit_total);
+	if (db->h_hit_total) cudaFreeHost(db->h_hit_total);
 	if (db->stream) cudaStreamDestroy(db->stream);
 	delete db;
 }
@@ -586,6 +622,77 @@ int kwg_search_counts(kwg_db_t* db, const char* bases, const uint64_t* offsets, 
 	return KWG_OK;
 }
 
+// Queries [q0, q1) that fit the handle's budget for the per-(query, filter) counts and the 2^31-base staging limit.
+static uint32_t next_query_batch(const kwg_db* db, const uint64_t* offsets, uint32_t q0, uint32_t n_queries, uint64_t pitch)
+{
+	const uint64_t max_q = std::max<uint64_t>(1, db->count_budget / (pitch * sizeof(uint32_t)));
+	uint32_t q1 = (uint32_t)std::min<uint64_t>(n_queries, (uint64_t)q0 + max_q);
+	while (q1 > q0 + 1 && offsets[q1] - offsets[q0] > (1ull << 30)) q1 = q0 + (q1 - q0) / 2;
+	return q1;
+}
+
+// Shared by kwg_search and kwg_search_hits_dev: the hits of all the queries, compacted on the device in (query, filter)
+// order into db->d_hits; queries go through in batches so that counts and scratch stay within the handle's budget
+// (the reference streams one query at a time, kwage.cpp:116-148); filter indices are offset by filter0.
+static int search_hits_device(kwg_db* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
+	uint32_t* n_query_kmers, uint32_t filter0, uint64_t* total_out)
+{
+	int rc;
+	const uint64_t pitch = round_up(db->n_filters, 4);
+	if (!db->d_hit_total) {
+		KWG_CUDA(cudaMalloc(&db->d_hit_total, sizeof(unsigned long long)));
+		KWG_CUDA(cudaMallocHost(&db->h_hit_total, sizeof(unsigned long long)));
+	}
+	KWG_CUDA(cudaMemsetAsync(db->d_hit_total, 0, sizeof(unsigned long long), db->stream));
+	uint64_t total = 0;
+	for (uint32_t q0 = 0; q0 < n_queries;) {
+		const uint32_t q1 = next_query_batch(db, offsets, q0, n_queries, pitch);
+		const uint32_t nq = q1 - q0;
+		uint64_t n_bases = 0;
+		uint32_t max_len = 0;
+		if ((rc = stage_queries(db, bases, offsets + q0, nq, &n_bases, &max_len))) return rc;
+		if ((rc = grow_db((void**)&db->d_counts, &db->counts_cap, (size_t)nq * pitch * sizeof(uint32_t)))) return rc;
+		if ((rc = grow_db((void**)&db->d_hit_count, &db->hit_count_cap, (size_t)nq * sizeof(uint32_t)))) return rc;
+		if ((rc = grow_db((void**)&db->d_hit_base, &db->hit_base_cap, (size_t)nq * sizeof(uint64_t)))) return rc;
+		if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, nq, n_bases, max_len, db->d_nk, db->d_counts, pitch))) return rc;
+
+		const unsigned hgrid = (unsigned)ceil_div((uint64_t)nq * 32, 256);
+		db->timers.begin(KWG_T_HITS, db->stream);
+		hits_kernel<0><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, nq, threshold,
+			db->d_hit_count, nullptr, nullptr, 0, 0);
+		KWG_LAUNCHED();
+		hit_scan_kernel<<<1, 1024, 0, db->stream>>>(db->d_hit_count, nq, db->d_hit_base, db->d_hit_total);
+		db->timers.end(db->stream);
+		KWG_LAUNCHED();
+		KWG_CUDA(cudaMemcpyAsync(db->h_hit_total, db->d_hit_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+		if (n_query_kmers)
+			KWG_CUDA(cudaMemcpyAsync(n_query_kmers + q0, db->d_nk, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+		KWG_CUDA(cudaStreamSynchronize(db->stream));
+		const uint64_t new_total = *db->h_hit_total;
+		if (new_total > total) {
+			if (new_total * sizeof(kwg_hit_t) > db->hits_cap) {
+				// grow, keeping the hits of the batches before
+				kwg_hit_t* n = nullptr;
+				const size_t want = round_up(new_total * sizeof(kwg_hit_t) * 3 / 2, 256);
+				KWG_CUDA(cudaMalloc(&n, want));
+				if (total) KWG_CUDA(cudaMemcpyAsync(n, db->d_hits, total * sizeof(kwg_hit_t), cudaMemcpyDeviceToDevice, db->stream));
+				KWG_CUDA(cudaStreamSynchronize(db->stream));
+				if (db->d_hits) KWG_CUDA(cudaFree(db->d_hits));
+				db->d_hits = n; db->hits_cap = want;
+			}
+			db->timers.begin(KWG_T_HITS, db->stream);
+			hits_kernel<1><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, nq, threshold,
+				db->d_hit_count, db->d_hit_base, db->d_hits, q0, filter0);
+			db->timers.end(db->stream);
+			KWG_LAUNCHED();
+		}
+		total = new_total;
+		q0 = q1;
+	}
+	*total_out = total;
+	return KWG_OK;
+}
+
 int kwg_search(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
 	uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits)
 {
@@ -595,48 +702,43 @@ int kwg_search(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_
 	if (n_queries == 0) return KWG_OK;
 	int rc = select_device(db->device);
 	if (rc) return rc;
-	uint64_t n_bases = 0;
-	uint32_t max_len = 0;
-	if ((rc = stage_queries(db, bases, offsets, n_queries, &n_bases, &max_len))) return rc;
-	const uint64_t pitch = round_up(db->n_filters, 4);
-	if ((rc = grow_db((void**)&db->d_counts, &db->counts_cap, (size_t)n_queries * pitch * sizeof(uint32_t)))) return rc;
-	if ((rc = grow_db((void**)&db->d_hit_count, &db->hit_count_cap, (size_t)n_queries * sizeof(uint32_t)))) return rc;
-	if ((rc = grow_db((void**)&db->d_hit_base, &db->hit_base_cap, (size_t)n_queries * sizeof(uint64_t)))) return rc;
-	if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, n_queries, n_bases, max_len, db->d_nk, db->d_counts, pitch))) return rc;
-
-	const unsigned hgrid = (unsigned)ceil_div((uint64_t)n_queries * 32, 256);
-	db->timers.begin(KWG_T_HITS, db->stream);
-	hits_kernel<0><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, n_queries, threshold,
-		db->d_hit_count, nullptr, nullptr);
-	db->timers.end(db->stream);
-	KWG_LAUNCHED();
-	std::vector<uint32_t> hc(n_queries);
-	KWG_CUDA(cudaMemcpyAsync(hc.data(), db->d_hit_count, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
-	if (n_query_kmers)
-		KWG_CUDA(cudaMemcpyAsync(n_query_kmers, db->d_nk, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
-	KWG_CUDA(cudaStreamSynchronize(db->stream));
-	std::vector<uint64_t> base(n_queries);
 	uint64_t total = 0;
-	for (uint32_t q = 0; q < n_queries; ++q) { base[q] = total; total += hc[q]; }
+	if ((rc = search_hits_device(db, bases, offsets, n_queries, threshold, n_query_kmers, 0, &total))) return rc;
 	if (total == 0) return KWG_OK;
-	if ((rc = grow_db((void**)&db->d_hits, &db->hits_cap, (size_t)total * sizeof(kwg_hit_t)))) return rc;
 	kwg_hit_t* h = (kwg_hit_t*)std::malloc((size_t)total * sizeof(kwg_hit_t));
 	if (!h) return fail(KWG_ERR_NO_MEMORY, "host allocation of the hit list failed");
-	cudaError_t e = cudaMemcpyAsync(db->d_hit_base, base.data(), (size_t)n_queries * sizeof(uint64_t), cudaMemcpyHostToDevice, db->stream);
-	if (e == cudaSuccess) {
-		hits_kernel<1><<<hgrid, 256, 0, db->stream>>>(db->d_counts, pitch, db->n_filters, db->d_nk, n_queries, threshold,
-			db->d_hit_count, db->d_hit_base, db->d_hits);
-		g_launches.fetch_add(1);
-		e = cudaGetLastError();
-	}
-	if (e == cudaSuccess) e = cudaMemcpyAsync(h, db->d_hits, (size_t)total * sizeof(kwg_hit_t), cudaMemcpyDeviceToHost, db->stream);
+	cudaError_t e = cudaMemcpyAsync(h, db->d_hits, (size_t)total * sizeof(kwg_hit_t), cudaMemcpyDeviceToHost, db->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
 	if (e != cudaSuccess) {
 		std::free(h);
-		return fail(KWG_ERR_CUDA, std::string("hit compaction: ") + cudaGetErrorString(e));
+		return fail(KWG_ERR_CUDA, std::string("hit list copy: ") + cudaGetErrorString(e));
 	}
 	*hits = h;
 	*n_hits = total;
+	return KWG_OK;
+}
+
+int kwg_search_hits_dev(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
+	uint32_t* n_query_kmers, uint32_t filter0, const kwg_hit_t** d_hits, uint64_t* n_hits)
+{
+	if (!db || !bases || !offsets || !d_hits || !n_hits) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*d_hits = nullptr; *n_hits = 0;
+	if (!(threshold > 0.0f && threshold <= 1.0f)) return fail(KWG_ERR_INVALID_ARG, "threshold must be in (0,1] (reference options.cpp:186-191)");
+	if (n_queries == 0) return KWG_OK;
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	uint64_t total = 0;
+	if ((rc = search_hits_device(db, bases, offsets, n_queries, threshold, n_query_kmers, filter0, &total))) return rc;
+	*d_hits = db->d_hits;
+	*n_hits = total;
+	return KWG_OK;
+}
+
+int kwg_db_set_count_budget(kwg_db_t* db, uint64_t bytes)
+{
+	if (!db) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	if (bytes < 4096) return fail(KWG_ERR_INVALID_ARG, "budget too small");
+	db->count_budget = bytes;
 	return KWG_OK;
 }
 
@@ -650,6 +752,198 @@ int kwg_search_ptrs(kwg_db_t* db, const char* const* queries, const uint64_t* qu
 	for (uint32_t q = 0; q < n_queries; ++q)
 		if (query_len[q]) std::memcpy(flat.data() + offsets[q], queries[q], (size_t)query_len[q]);
 	return kwg_search(db, flat.data(), offsets.data(), n_queries, threshold, n_query_kmers, hits, n_hits);
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU gather
+// The one exchange of the path: every device holds a column slab, searches all the queries, and the
+// compacted hit lists -- a few KB -- travel to the root over NCCL (NVLink): one all-gather of the list lengths, one
+// grouped send/recv of the lists themselves straight from HBM, one counting sort by query on the root's host.
+// NCCL is loaded at run time (dlopen of libnccl.so.2: the one the process already has, e.g. PyTorch's, else the
+// system's), so the library has no link-time dependency on it and single-GPU users never touch it.
+namespace {
+struct NcclApi {
+	void* lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	std::string error;
+};
+
+NcclApi& nccl_api()
+{
+	static NcclApi api = [] {
+		NcclApi a;
+		a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!a.lib) { a.error = std::string("libnccl.so.2 could not be loaded: ") + dlerror(); return a; }
+#define KWG_SYM(field, name) \
+		*reinterpret_cast<void**>(&a.field) = dlsym(a.lib, name); \
+		if (!a.field && a.error.empty()) a.error = std::string("libnccl.so.2 lacks ") + name;
+		KWG_SYM(GetUniqueId, "ncclGetUniqueId") KWG_SYM(CommInitRank, "ncclCommInitRank") KWG_SYM(CommInitAll, "ncclCommInitAll")
+		KWG_SYM(CommDestroy, "ncclCommDestroy") KWG_SYM(AllGather, "ncclAllGather") KWG_SYM(Send, "ncclSend") KWG_SYM(Recv, "ncclRecv")
+		KWG_SYM(GroupStart, "ncclGroupStart") KWG_SYM(GroupEnd, "ncclGroupEnd") KWG_SYM(GetErrorString, "ncclGetErrorString")
+#undef KWG_SYM
+		return a;
+	}();
+	return api;
+}
+} // namespace
+
+#define KWG_NCCL(expr)                                                                                   \
+	do {                                                                                                 \
+		ncclResult_t _r = (expr);                                                                        \
+		if (_r != ncclSuccess) return fail(KWG_ERR_CUDA, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
+	} while (0)
+
+struct kwg_comm {
+	ncclComm_t comm = nullptr;
+	int device = 0, rank = 0, n_ranks = 1;
+	unsigned long long* d_totals = nullptr;       // [n_ranks + 1]: every rank's list length; [n_ranks] = this rank's
+	unsigned long long* h_totals = nullptr;       // pinned
+	kwg_hit_t* d_gathered = nullptr; size_t gathered_cap = 0;
+};
+
+static int comm_finish(kwg_comm* c)
+{
+	int rc = select_device(c->device);
+	if (rc) return rc;
+	KWG_CUDA(cudaMalloc(&c->d_totals, (size_t)(c->n_ranks + 1) * sizeof(unsigned long long)));
+	KWG_CUDA(cudaMallocHost(&c->h_totals, (size_t)(c->n_ranks + 1) * sizeof(unsigned long long)));
+	return KWG_OK;
+}
+
+void kwg_merge_hits(const kwg_hit_t* lists, const uint64_t* list_len, uint32_t n_lists, uint32_t n_queries, kwg_hit_t* out)
+{
+	// counting sort by query, stable over (list, position): lists are ordered by (query, filter) and list r holds the
+	// columns before those of list r + 1, so the result is ordered by (query, filter) -- kwg_search's order
+	std::vector<uint64_t> at((size_t)n_queries + 1, 0);
+	uint64_t total = 0;
+	for (uint32_t r = 0; r < n_lists; ++r) total += list_len[r];
+	for (uint64_t i = 0; i < total; ++i) ++at[(size_t)lists[i].query + 1];
+	for (uint32_t q = 0; q < n_queries; ++q) at[q + 1] += at[q];
+	for (uint64_t i = 0; i < total; ++i) out[at[lists[i].query]++] = lists[i];
+}
+
+int kwg_comm_get_unique_id(uint8_t* id)
+{
+	if (!id) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	NcclApi& N = nccl_api();
+	if (!N.error.empty()) return fail(KWG_ERR_CUDA, N.error);
+	ncclUniqueId u;
+	KWG_NCCL(N.GetUniqueId(&u));
+	static_assert(sizeof(u) == KWG_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+	std::memcpy(id, &u, sizeof(u));
+	return KWG_OK;
+}
+
+int kwg_comm_create(kwg_comm_t** out, int device, int n_ranks, int rank, const uint8_t* id)
+{
+	if (!out || !id) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*out = nullptr;
+	if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(KWG_ERR_INVALID_ARG, "bad rank");
+	NcclApi& N = nccl_api();
+	if (!N.error.empty()) return fail(KWG_ERR_CUDA, N.error);
+	int rc = select_device(device);
+	if (rc) return rc;
+	kwg_comm* c = new kwg_comm();
+	c->device = device; c->rank = rank; c->n_ranks = n_ranks;
+	ncclUniqueId u;
+	std::memcpy(&u, id, sizeof(u));
+	ncclResult_t r = N.CommInitRank(&c->comm, n_ranks, u, rank);
+	if (r != ncclSuccess) { delete c; return fail(KWG_ERR_CUDA, std::string("ncclCommInitRank: ") + N.GetErrorString(r)); }
+	rc = comm_finish(c);
+	if (rc) { kwg_comm_destroy(c); return rc; }
+	*out = c;
+	return KWG_OK;
+}
+
+int kwg_comm_create_all(kwg_comm_t** out, int n, const int* devices)
+{
+	if (!out || !devices || n < 1) return fail(KWG_ERR_INVALID_ARG, "bad argument");
+	NcclApi& N = nccl_api();
+	if (!N.error.empty()) return fail(KWG_ERR_CUDA, N.error);
+	std::vector<ncclComm_t> comms((size_t)n);
+	KWG_NCCL(N.CommInitAll(comms.data(), n, devices));
+	for (int i = 0; i < n; ++i) {
+		kwg_comm* c = new kwg_comm();
+		c->comm = comms[(size_t)i]; c->device = devices[i]; c->rank = i; c->n_ranks = n;
+		out[i] = c;
+		int rc = comm_finish(c);
+		if (rc) return rc;
+	}
+	return KWG_OK;
+}
+
+void kwg_comm_destroy(kwg_comm_t* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->comm) nccl_api().CommDestroy(c->comm);
+	cudaFree(c->d_totals);
+	if (c->h_totals) cudaFreeHost(c->h_totals);
+	cudaFree(c->d_gathered);
+	delete c;
+}
+
+int kwg_search_gather(kwg_db_t* db, kwg_comm_t* c, int root, const char* bases, const uint64_t* offsets, uint32_t n_queries,
+	float threshold, uint32_t filter0, uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits)
+{
+	if (!db || !c || !bases || !offsets || !hits || !n_hits) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
+	*hits = nullptr; *n_hits = 0;
+	if (root < 0 || root >= c->n_ranks) return fail(KWG_ERR_INVALID_ARG, "bad root");
+	if (c->device != db->device) return fail(KWG_ERR_INVALID_ARG, "communicator and database are on different devices");
+	if (!(threshold > 0.0f && threshold <= 1.0f)) return fail(KWG_ERR_INVALID_ARG, "threshold must be in (0,1] (reference options.cpp:186-191)");
+	NcclApi& N = nccl_api();
+	int rc = select_device(db->device);
+	if (rc) return rc;
+	uint64_t mine = 0;
+	if (n_queries && (rc = search_hits_device(db, bases, offsets, n_queries, threshold, n_query_kmers, filter0, &mine))) return rc;
+	const int W = c->n_ranks;
+	// list lengths of all ranks
+	c->h_totals[W] = mine;
+	KWG_CUDA(cudaMemcpyAsync(c->d_totals + W, c->h_totals + W, sizeof(unsigned long long), cudaMemcpyHostToDevice, db->stream));
+	KWG_NCCL(N.AllGather(c->d_totals + W, c->d_totals, 1, ncclUint64, c->comm, db->stream));
+	KWG_CUDA(cudaMemcpyAsync(c->h_totals, c->d_totals, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	uint64_t total = 0;
+	std::vector<uint64_t> len((size_t)W), off((size_t)W);
+	for (int r = 0; r < W; ++r) { len[(size_t)r] = c->h_totals[r]; off[(size_t)r] = total; total += len[(size_t)r]; }
+	if (c->rank == root && total * sizeof(kwg_hit_t) > c->gathered_cap) {
+		if (c->d_gathered) KWG_CUDA(cudaFree(c->d_gathered));
+		c->d_gathered = nullptr; c->gathered_cap = 0;
+		const size_t want = round_up(total * sizeof(kwg_hit_t) * 3 / 2, 256);
+		KWG_CUDA(cudaMalloc(&c->d_gathered, want));
+		c->gathered_cap = want;
+	}
+	// the lists themselves, HBM to HBM (3 words per hit)
+	KWG_NCCL(N.GroupStart());
+	if (c->rank == root) {
+		for (int r = 0; r < W; ++r)
+			if (r != root && len[(size_t)r]) KWG_NCCL(N.Recv(c->d_gathered + off[(size_t)r], len[(size_t)r] * 3, ncclUint32, r, c->comm, db->stream));
+	} else if (mine) {
+		KWG_NCCL(N.Send(db->d_hits, mine * 3, ncclUint32, root, c->comm, db->stream));
+	}
+	KWG_NCCL(N.GroupEnd());
+	if (c->rank != root || total == 0) {
+		KWG_CUDA(cudaStreamSynchronize(db->stream));      // the list may be overwritten by the next call
+		return KWG_OK;
+	}
+	if (mine) KWG_CUDA(cudaMemcpyAsync(c->d_gathered + off[(size_t)root], db->d_hits, mine * sizeof(kwg_hit_t), cudaMemcpyDeviceToDevice, db->stream));
+	std::vector<kwg_hit_t> flat((size_t)total);
+	KWG_CUDA(cudaMemcpyAsync(flat.data(), c->d_gathered, total * sizeof(kwg_hit_t), cudaMemcpyDeviceToHost, db->stream));
+	KWG_CUDA(cudaStreamSynchronize(db->stream));
+	kwg_hit_t* h = (kwg_hit_t*)std::malloc((size_t)total * sizeof(kwg_hit_t));
+	if (!h) return fail(KWG_ERR_NO_MEMORY, "host allocation of the hit list failed");
+	kwg_merge_hits(flat.data(), len.data(), (uint32_t)W, n_queries, h);
+	*hits = h;
+	*n_hits = total;
+	return KWG_OK;
 }
 
 void kwg_free_hits(kwg_hit_t* hits) { std::free(hits); }

@@ -466,6 +466,7 @@ bool SubjectDatabase::search(std::unordered_map<size_t, std::deque<MatchResult> 
 	const std::vector<size_t>& query_ids, const SearchOptions& opt)
 {
 	if (queries.empty()) return false;
+	if (queries.size() > 0xFFFFFFFFull) throw __FILE__ ":search: more than 2^32 queries in one call (split the query set)";
 	std::vector<const char*> ptrs(queries.size());
 	std::vector<uint64_t> lens(queries.size());
 	for (size_t i = 0; i < queries.size(); ++i) { ptrs[i] = queries[i].data(); lens[i] = queries[i].size(); }

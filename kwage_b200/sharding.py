@@ -2,7 +2,9 @@
 
 The path shards without any data-path collective except one: construction by accession, transposition
 and search by filter-column slab; search gathers the per-slab hit lists on one rank.
-The functions are backend-agnostic (nccl on the GPUs, gloo in the CPU tests)."""
+On the GPUs that exchange is the library's own kwg_search_gather (NCCL inside the C ABI, capi.Database.search_gather);
+gather_hits below is the same exchange over any torch.distributed backend (gloo in the CPU tests) with the library's
+merge step (kwg_merge_hits)."""
 import numpy as np
 
 from .capi import HIT_DTYPE
@@ -56,8 +58,9 @@ def gather_hits(hits, col_begin, dist=None, dst=0, device="cpu"):
         if rank != dst:
             return None
         merged = np.concatenate([b[: int(s.item())].cpu().numpy() for b, s in zip(bufs, sizes)], axis=0)
-    order = np.lexsort((merged[:, 1], merged[:, 0]))
-    merged = merged[order]
     out = np.zeros(merged.shape[0], dtype=HIT_DTYPE)
     out["query"], out["filter"], out["num_match"] = merged[:, 0], merged[:, 1], merged[:, 2]
-    return out
+    # rank-major concatenation of (query, filter)-ordered slab lists -> (query, filter) order: the library's merge
+    from .capi import merge_hits
+    n_queries = int(out["query"].max()) + 1 if len(out) else 0
+    return merge_hits([out], n_queries)

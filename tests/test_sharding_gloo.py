@@ -89,6 +89,21 @@ def test_gather_hits_world2_gloo():
 
 
 def test_gather_hits_single_process():
-    hits = np.array([(1, 5, 9), (0, 7, 3), (0, 2, 4)], dtype=HIT_DTYPE)
+    hits = np.array([(0, 2, 4), (0, 7, 3), (1, 5, 9)], dtype=HIT_DTYPE)         # kwg_search's order: (query, filter)
     out = sharding.gather_hits(hits, 128)
     assert [(int(x["query"]), int(x["filter"])) for x in out] == [(0, 130), (0, 135), (1, 133)]
+
+
+def test_merge_hits_is_the_order_of_one_search_over_all_columns():
+    # kwg_merge_hits (the root's step of kwg_search_gather): per-slab lists, each in (query, filter) order, slabs in column
+    # order -> the list one search over the whole database returns (reference: kwage.cpp:154-177 merges thread-local maps)
+    from kwage_b200 import capi
+    rng = np.random.default_rng(5)
+    n_q, slabs = 40, [(0, 128), (128, 384), (384, 400), (400, 1000)]
+    whole = sorted({(int(rng.integers(0, n_q)), int(rng.integers(0, 1000))) for _ in range(3000)})
+    whole = np.array([(q, f, (q * 31 + f) % 97) for q, f in whole], dtype=HIT_DTYPE)
+    lists = [whole[(whole["filter"] >= a) & (whole["filter"] < b)] for a, b in slabs]
+    assert all(len(x) for x in lists)
+    merged = capi.merge_hits(lists, n_q)
+    assert np.array_equal(merged, whole)
+    assert len(capi.merge_hits([np.zeros(0, HIT_DTYPE), np.zeros(0, HIT_DTYPE)], 5)) == 0
