@@ -42,14 +42,20 @@ def env_int(name, default):
         return default
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the
-# default workload (profiles/r1c_ncu_full_construct.md, r1d_ncu_full_transpose_search.md); reported as roofline.traffic
-# when the workload matches
-NCU_TRAFFIC = {
-    "partition_scan": 3.987e9, "regroup": 7.728e9, "resolve": 6.529e9, "scan_pass_b": 1.147e9, "insert_words": 4.995e9,
-    "transpose_kernel": 6.868e10, "search_count_kernel": 3.026e10,
-}
-NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_construct.md, profiles/r1d_ncu_full_transpose_search.md"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the `ncu --set full` captures of the
+# default workload.  profiles/ncu_traffic.json is written by `profiles/extract_ncu.py traffic <reports>` and carries the
+# commit the captures were taken at; roofline.traffic is reported only when the workload matches the captured one.
+def ncu_traffic():
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("kernels", {}), "profiles/ncu_traffic.json (captured at commit %s: %s)" % (d.get("commit", "?"), ", ".join(d.get("reports", [])))
+    except Exception:
+        return {}, None
+
+
+NCU_TRAFFIC, NCU_TRAFFIC_SOURCE = ncu_traffic()
 
 
 def measured_peaks():
@@ -181,6 +187,54 @@ def timed(D, stream_ptr, fn, steps, warmup, windows):
     return D.max_over_ranks(e0.elapsed_time(e1) / 1e3)
 
 
+def run_concurrent(D, dev, handles, step, per_worker, warm, windows):
+    """step(w, i) on one host thread per handle (its own stream), `warm` untimed then `per_worker` timed calls each.
+    Returns the device time from the earliest start to the latest end over the handles' streams, max over ranks."""
+    torch = D.torch
+
+    def run(n, base):
+        def loop(w):
+            torch.cuda.set_device(dev)
+            for i in range(n):
+                step(w, base + i)
+        ts = [threading.Thread(target=loop, args=(w,)) for w in range(len(handles))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    if warm:
+        run(warm, 0)
+    D.barrier()
+    streams = [torch.cuda.ExternalStream(hd.stream()) for hd in handles]
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in handles]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in handles]
+    w0 = time.time()
+    for e, st in zip(ev0, streams):
+        e.record(st)
+    run(per_worker, warm)
+    for e, st in zip(ev1, streams):
+        e.record(st)
+    D.barrier()
+    windows.append((w0, time.time()))
+    return D.max_over_ranks(max(a.elapsed_time(z) for a in ev0 for z in ev1) / 1e3)
+
+
+def pack_2na_torch(torch, d_ascii, n_bases):
+    """bench input preparation only: ASCII bases on the device -> pinned host 2na bytes (kwg_bloom_add_packed's format)"""
+    x = d_ascii[:n_bases].to(torch.int32)
+    c = ((x >> 1) & 3)
+    c = c ^ (c >> 1)                                   # A:0 C:1 G:2 T:3
+    pad = (-n_bases) % 4
+    if pad:
+        c = torch.cat([c, torch.zeros(pad, dtype=torch.int32, device=c.device)])
+    c = c.view(-1, 4)
+    packed = ((c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]).to(torch.uint8)
+    h = torch.empty(packed.numel(), dtype=torch.uint8).pin_memory()
+    h.copy_(packed)
+    return h
+
+
 # ---------------------------------------------------------------------------------------------- construction
 def stage_construct(D, args, windows):
     import numpy as np
@@ -222,22 +276,48 @@ def stage_construct(D, args, windows):
         b.finalize_dev(L, h, d_out.data_ptr())
         state.update(n_valid=n_valid, L=L, h=h)
 
-    # value: inputs resident in HBM
+    # per-kernel times and the latency of one accession: one handle, one stream, inputs resident in HBM
     for i in range(args.warmup):
         step_dev(i)
     b.sync()
     b.set_timing(True)
     b.get_timing()
     launches0 = capi.launch_count()
-    sec = timed(D, b.stream(), step_dev, args.steps, 0, windows)
+    sec_single = timed(D, b.stream(), step_dev, args.steps, 0, windows)
     launches = capi.launch_count() - launches0
     ms, nl = b.get_timing()
     b.set_timing(False)
+
+    # value: whole-job throughput with inputs resident in HBM.  A job is many accessions (the reference runs one MPI
+    # worker per accession, many per node): IN_FLIGHT host threads, each with its own handle and stream, build whole
+    # accessions one after the other, so that the kernels of one accession that leave SM resources unused (the
+    # issue-bound hash pass, the L2-atomic-bound insert) run beside another accession's.
+    in_flight = max(1, args.in_flight)
+    vb = [b] + [capi.BloomBuilder(K, device=dev, min_kmer_count=args.min_kmer_count, log2_count_len=lc, log2_max_len=LMAX)
+                for _ in range(in_flight - 1)]
+    d_outs = [d_out] + [torch.empty((1 << LMAX) // 8, dtype=torch.uint8, device="cuda") for _ in range(in_flight - 1)]
+
+    def step_dev_w(w, i):
+        bw = vb[w]
+        bw.reset()
+        bw.add_reads_dev(d_bases[i % pool].data_ptr(), d_offsets.data_ptr(), n_reads, n_bases)
+        n_valid = bw.num_valid()
+        L, h = H.optimal_bloom_param(K, n_valid, P_FALSE, LMIN, LMAX)
+        bw.finalize_dev(L, h, d_outs[w].data_ptr())
+        bw.sync()
+
+    value_steps_per_worker = max(2, (args.steps + in_flight - 1) // in_flight)
+    sec = run_concurrent(D, dev, vb, lambda w, i: step_dev_w(w, w + i * in_flight), value_steps_per_worker, 2, windows)
+    value_steps = value_steps_per_worker * in_flight
+    for bw in vb[1:]:
+        bw.close()
+    del d_outs
 
     # e2e: pinned host buffers through the host-pointer C-ABI calls.  E2E_WORKERS host threads per GPU, each with
     # its own handle, stream and buffers and each building whole accessions (the reference's model: one MPI worker
     # per accession, many workers per node), so that one accession's H2D / D2H overlaps the other's kernels.
     n_workers = max(1, args.e2e_workers)
+    use_ft = args.min_kmer_count == 1 and lc <= 30
     h_offsets = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
     h_offsets.copy_(d_offsets)
     builders = [b] + [capi.BloomBuilder(K, device=dev, min_kmer_count=args.min_kmer_count, log2_count_len=lc, log2_max_len=LMAX)
@@ -250,7 +330,7 @@ def stage_construct(D, args, windows):
         h_out.append(torch.empty((1 << state["L"]) // 8, dtype=torch.uint8).pin_memory())
     torch.cuda.synchronize()
 
-    def step_host(w):
+    def step_host(w, i):
         bw = builders[w]
         bw.reset()
         bw.add_reads_ptr(h_bases[w].data_ptr(), h_offsets.data_ptr(), n_reads)
@@ -258,38 +338,30 @@ def stage_construct(D, args, windows):
         L, h = H.optimal_bloom_param(K, n_valid, P_FALSE, LMIN, LMAX)
         bw.finalize_crc_ptr(L, h, h_out[w].data_ptr())      # bits + their crc32, what make_bloom_filter writes into the .bloom file
 
-    def run_workers(per_worker):
-        def loop(w):
-            torch.cuda.set_device(dev)
-            for _ in range(per_worker):
-                step_host(w)
-        ts = [threading.Thread(target=loop, args=(w,)) for w in range(n_workers)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-
     per_worker = max(1, (args.steps + n_workers - 1) // n_workers)
-    run_workers(1)                                       # warm-up (allocations of the extra handles)
-    D.barrier()
-    streams = [torch.cuda.ExternalStream(bw.stream()) for bw in builders]
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in builders]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in builders]
-    w0 = time.time()
-    for e, st in zip(ev0, streams):
-        e.record(st)
-    run_workers(per_worker)
-    for e, st in zip(ev1, streams):
-        e.record(st)
-    D.barrier()
-    windows.append((w0, time.time()))
-    # device time from the earliest start to the latest end over the workers' streams
-    sec_e2e = D.max_over_ranks(max(a.elapsed_time(z) for a in ev0 for z in ev1) / 1e3)
+    sec_e2e = run_concurrent(D, dev, builders, step_host, per_worker, 1, windows)
     e2e_steps = per_worker * n_workers
-    crc = None
-    if D.rank == 0:
-        import zlib
-        crc = zlib.crc32(h_out[0].numpy().tobytes()) & 0xFFFFFFFF
+    import zlib
+    crc_ascii = zlib.crc32(h_out[0].numpy().tobytes()) & 0xFFFFFFFF
+
+    # the same through kwg_bloom_add_packed: the host holds the reads 2-bit packed (NCBI 2na, what the SRA stores), a
+    # quarter of the bytes cross PCIe
+    h_packed = [pack_2na_torch(torch, d_bases[w % pool], n_bases) for w in range(n_workers)]
+    torch.cuda.synchronize()
+
+    def step_host_packed(w, i):
+        bw = builders[w]
+        bw.reset()
+        bw.add_packed_ptr(h_packed[w].data_ptr(), 0, h_offsets.data_ptr(), n_reads)
+        n_valid = bw.num_valid()
+        L, h = H.optimal_bloom_param(K, n_valid, P_FALSE, LMIN, LMAX)
+        bw.finalize_crc_ptr(L, h, h_out[w].data_ptr())
+        state["n_valid_packed"] = n_valid
+
+    sec_e2e_packed = run_concurrent(D, dev, builders, step_host_packed, per_worker, 1, windows)
+    if (zlib.crc32(h_out[0].numpy().tobytes()) & 0xFFFFFFFF) != crc_ascii:
+        raise SystemExit("bench: the packed-input arm built a different filter than the ASCII arm")
+    crc = crc_ascii
     for bw in builders:
         bw.close()
     del d_bases, d_out
@@ -298,22 +370,37 @@ def stage_construct(D, args, windows):
     n = D.world
     peak, peak_src = measured_peaks()
     # Algorithmic HBM bytes per k-mer occurrence of each kernel of the counting pipeline.
-    # A touch record is 8 bytes, four per k-mer: the partition scan writes them once, regroup reads and
-    # re-writes them once, resolve reads them once; everything else is small next to that.
     ascii_b = READ_LEN / (READ_LEN - K + 1) * (1 + 1 / 8)            # bases + read-start bitmap
     touched_b = (2 << lc) / 8 / kmers                                # touched bitmap written once per batch
-    alg = {
-        "partition_scan": ("partition_scan_kernel (encode + 4 hashes + tile-local counting sort)", capi.T_SCAN_A, ascii_b + 32.0),
-        "regroup": ("regroup_kernel (bulk-copy gather + level-2 counting sort)", capi.T_REGROUP, 64.0 + 2 * 257 * 2 / 8192 * 32),
-        "resolve": ("resolve_kernel (first-touch atomicMin in shared memory)", capi.T_RESOLVE, 32.0 + touched_b + 0.5) if args.min_kmer_count == 1 else
-                   # one launch per counter level: records read once per level (+ the dense copy written by level 0), the 4-bit
-                   # counters (2^lc bytes) read and written once per level
-                   ("resolve_kernel<levels> + resolve_dense_kernel x%d levels" % args.min_kmer_count, capi.T_RESOLVE,
-                    32.0 * (args.min_kmer_count + 1) + 2.0 * args.min_kmer_count * (1 << lc) / kmers),
-        "scan_pass_b": ("kmer_scan_kernel<PASS_B> (valid-word list)", capi.T_SCAN_B, ascii_b + 0.5 + 8.0),
-        "insert_words": ("insert_words_kernel (final filter, L2-resident red.or)", capi.T_INSERT, 8.0 + (1 << state["L"]) / 8 / kmers),
-    }
-    step_ms = sec / args.steps * 1e3
+    if use_ft:
+        # first-touch path (bloom_first.cuh): the four counting hashes of an occurrence are written once (16 B) and read
+        # once, its four 6-byte touch records are written once and read once, its canonical word (8 B) is written once
+        # and read once by the insert
+        alg = {
+            "hash": ("ft_count_kernel + ft_scan_kernel + ft_hash_kernel (encode, canonical k-mer, 4 hashes by dense ordinal)", capi.T_SCAN_A,
+                     2 * ascii_b + 16.0 + 8.0),
+            "append": ("ft_append_kernel (one-level partition: ring-buffered append into page chains)", capi.T_REGROUP, 16.0 + 24.0),
+            "resolve": ("ft_resolve_kernel (stream-ordered first touch against a 1-bit-per-slot tile in shared memory)", capi.T_RESOLVE,
+                        24.0 + touched_b + 0.5),
+            "finish": ("ft_finish_kernel (invalid bitmap + valid count)", capi.T_SCAN_B, 0.5),
+            "insert_words": ("insert_words_kernel (final filter, L2-resident red.or)", capi.T_INSERT, 8.0 + (1 << state["L"]) / 8 / kmers),
+        }
+    else:
+        # two-level radix partition (bloom_count.cuh): a touch record is 8 bytes, four per k-mer: the partition scan writes
+        # them once, regroup reads and re-writes them once, resolve reads them once; everything else is small next to that.
+        alg = {
+            "partition_scan": ("partition_scan_kernel (encode + 4 hashes + tile-local counting sort)", capi.T_SCAN_A, ascii_b + 32.0),
+            "regroup": ("regroup_kernel (bulk-copy gather + level-2 counting sort)", capi.T_REGROUP, 64.0 + 2 * 257 * 2 / 8192 * 32),
+            "resolve": ("resolve_kernel (first-touch atomicMin in shared memory)", capi.T_RESOLVE, 32.0 + touched_b + 0.5) if args.min_kmer_count == 1 else
+                       # one launch per counter level: records read once per level (+ the dense copy written by level 0), the 4-bit
+                       # counters (2^lc bytes) read and written once per level
+                       ("resolve_kernel<levels> + resolve_dense_kernel x%d levels" % args.min_kmer_count, capi.T_RESOLVE,
+                        32.0 * (args.min_kmer_count + 1) + 2.0 * args.min_kmer_count * (1 << lc) / kmers),
+            "scan_pass_b": ("kmer_scan_kernel<PASS_B> (valid-word list)", capi.T_SCAN_B, ascii_b + 0.5 + 8.0),
+            "insert_words": ("insert_words_kernel (final filter, L2-resident red.or)", capi.T_INSERT, 8.0 + (1 << state["L"]) / 8 / kmers),
+        }
+    single_ms = sec_single / args.steps * 1e3
+    step_ms = sec / value_steps * 1e3
     per_kernel = {}
     for name, (desc, idx, bpk) in alg.items():
         t = ms[idx] / max(int(nl[idx]), 1) / 1e3 if nl[idx] else 0.0
@@ -326,22 +413,33 @@ def stage_construct(D, args, windows):
     achieved = per_kernel[dom]["achieved_gbs"]
     kernels = {k: v["ms_per_step"] for k, v in per_kernel.items()}
     return {
-        "value": n * kmers * args.steps / sec,
+        "value": n * kmers * value_steps / sec,
         "ms_per_step": step_ms,
+        "accessions_in_flight": in_flight,
+        "single_stream": {"value": n * kmers * args.steps / sec_single, "ms_per_step": single_ms,
+                          "note": "one handle, one stream, one accession at a time (the latency of an accession; the per-kernel times below are taken here)"},
         "e2e": {"value": n * kmers * e2e_steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
                 "d2h_bytes_per_step": (1 << state["L"]) // 8 + 8, "ms_per_step": sec_e2e / e2e_steps * 1e3, "steps": e2e_steps,
                 "workers_per_gpu": n_workers,
+                "packed_input": {"value": n * kmers * e2e_steps / sec_e2e_packed, "ms_per_step": sec_e2e_packed / e2e_steps * 1e3,
+                                 "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1),
+                                 "how": "the same through kwg_bloom_add_packed (2-bit NCBI 2na input, no N mask needed for this input)"},
                 "how": "%d host threads per GPU, one accession at a time each through kwg_bloom_add_reads/num_valid/finalize with pinned "
                        "host buffers; device time from the first start to the last end over their streams" % n_workers},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC.get(dom) if (n_reads == 1000000 and args.min_kmer_count == 1) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
+                     "traffic": NCU_TRAFFIC.get({"hash": "ft_hash_kernel", "append": "ft_append_kernel", "resolve": "ft_resolve_kernel"}.get(dom, dom + "_kernel"))
+                     if (n_reads == 1000000 and args.min_kmer_count == 1 and use_ft) else None,
+                     "traffic_source": NCU_TRAFFIC_SOURCE,
                      "algorithmic_bytes": kmers * per_kernel[dom]["algorithmic_bytes_per_kmer"], "peak_source": peak_src,
                      "algorithmic_bytes_per_kmer": per_kernel[dom]["algorithmic_bytes_per_kmer"],
-                     "kernel_ms": per_kernel[dom]["ms_per_step"], "share_of_step": per_kernel[dom]["ms_per_step"] / step_ms,
+                     "kernel_ms": per_kernel[dom]["ms_per_step"], "share_of_step": per_kernel[dom]["ms_per_step"] / single_ms,
                      "pipeline_algorithmic_bytes_per_kmer": round(sum(v[2] for v in alg.values()), 2),
-                     "pipeline_achieved_gbs": round(kmers * sum(v[2] for v in alg.values()) / (step_ms / 1e3) / 1e9, 1)},
+                     "pipeline_achieved_gbs": round(kmers * sum(v[2] for v in alg.values()) / (step_ms / 1e3) / 1e9, 1),
+                     "note": "achieved = algorithmic bytes of this kernel / its mean duration (CUDA events on the handle's stream, single-stream pass); "
+                             "the first-touch pipeline moves 103 B per k-mer occurrence where round 1's radix pipeline moved 155 B, so the same "
+                             "time reads as a lower fraction: compare ms_per_step"},
         "kernel_ms_per_step": kernels,
         "kernels": per_kernel,
         "result": {"num_valid_kmers": state["n_valid"], "log2_filter_len": state["L"], "num_hash": state["h"], "log2_counting_filter_len": lc,
@@ -403,7 +501,7 @@ def stage_transpose(D, args, windows):
             "e2e": {"value": n * nf * cbits * 2 / sec_e2e, "unit": "bits/s", "h2d_bytes_per_step": nf * cbits // 8, "d2h_bytes_per_step": nf * cbits // 8,
                     "workload": "kwg_transpose, 2048 filters x 2^22 slices per call (the reference's chunk)"},
             "roofline": {"bound": "hbm", "kernel": "transpose_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC["transpose_kernel"] if (n_filters, L) == (4096, 26) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "traffic": NCU_TRAFFIC.get("transpose_kernel") if (n_filters, L) == (4096, 26) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
                          "algorithmic_bytes": 2 * bits // 8, "peak_source": peak_src},
             "gpu_launches": int(capi.launch_count() - launches0)}
 
@@ -444,18 +542,36 @@ def stage_construct_raw(D, args, windows):
     b.set_timing(False)
     t_scan = float(ms[capi.T_SCAN_A]) / steps / 1e3
 
-    h_bases = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
-    h_bases.copy_(d_bases[0][:n_bases])
+    # e2e: two host threads per GPU, each with its own handle: one accession's D2H rides beside the other's H2D
+    n_workers = 2
+    rb = [b] + [capi.BloomBuilder(K, device=dev, raw_num_hash=h, raw_log2_len=L) for _ in range(n_workers - 1)]
     h_offsets = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
     h_offsets.copy_(d_offsets)
-    h_out = torch.empty((1 << L) // 8, dtype=torch.uint8).pin_memory()
+    h_bases, h_packed, h_out = [], [], []
+    for w in range(n_workers):
+        hb = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
+        hb.copy_(d_bases[w % pool][:n_bases])
+        h_bases.append(hb)
+        h_packed.append(pack_2na_torch(torch, d_bases[w % pool], n_bases))
+        h_out.append(torch.empty((1 << L) // 8, dtype=torch.uint8).pin_memory())
+    torch.cuda.synchronize()
 
-    def step_host(i):
-        b.reset()
-        b.add_reads_ptr(h_bases.data_ptr(), h_offsets.data_ptr(), n_reads)
-        b.finalize_crc_ptr(L, h, h_out.data_ptr())
+    def step_host(w, i):
+        rb[w].reset()
+        rb[w].add_reads_ptr(h_bases[w].data_ptr(), h_offsets.data_ptr(), n_reads)
+        rb[w].finalize_crc_ptr(L, h, h_out[w].data_ptr())
 
-    sec_e2e = timed(D, b.stream(), step_host, steps, 1, windows)
+    def step_host_packed(w, i):
+        rb[w].reset()
+        rb[w].add_packed_ptr(h_packed[w].data_ptr(), 0, h_offsets.data_ptr(), n_reads)
+        rb[w].finalize_crc_ptr(L, h, h_out[w].data_ptr())
+
+    per_worker = max(3, (steps + n_workers - 1) // n_workers)
+    e2e_steps = per_worker * n_workers
+    sec_e2e = run_concurrent(D, dev, rb, step_host, per_worker, 1, windows)
+    sec_e2e_packed = run_concurrent(D, dev, rb, step_host_packed, per_worker, 1, windows)
+    for x in rb[1:]:
+        x.close()
     b.close()
     del d_bases, d_out
     torch.cuda.empty_cache()
@@ -466,8 +582,10 @@ def stage_construct_raw(D, args, windows):
     alg = n_bases * (1 + 1 / 8) + 2 * (1 << L) / 8
     return {"metric": "Bloom k-mer inserts/s (raw mode)", "value": n * kmers * steps / sec, "unit": "kmer_inserts/s", "ms_per_step": sec / steps * 1e3,
             "config": {"reads_per_accession": n_reads, "kmer_len": K, "num_hash": h, "log2_filter_len": L},
-            "e2e": {"value": n * kmers * steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
-                    "d2h_bytes_per_step": (1 << L) // 8 + 4, "ms_per_step": sec_e2e / steps * 1e3},
+            "e2e": {"value": n * kmers * e2e_steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
+                    "d2h_bytes_per_step": (1 << L) // 8 + 4, "ms_per_step": sec_e2e / e2e_steps * 1e3, "workers_per_gpu": n_workers,
+                    "packed_input": {"value": n * kmers * e2e_steps / sec_e2e_packed, "ms_per_step": sec_e2e_packed / e2e_steps * 1e3,
+                                     "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1)}},
             "gpu_launches": int(launches),
             "l2_atomics_per_s": kmers * h / t_scan if t_scan > 0 else None,
             "roofline": {"bound": "hbm", "kernel": "kmer_scan_kernel<RAW,3> (bound by L2 atomics and integer issue, not by HBM: see l2_atomics_per_s)",
@@ -602,7 +720,7 @@ def stage_search(D, args, windows):
                     "threshold": 0.5, "hits": n_hits[0], "hits_expected_at_least": n * n_planted * len(plant_cols),
                     "planted": "%d of %d queries carry %d bp whose k-mers are inserted into columns %s of every slab" % (n_planted, nq, PLANT, plant_cols)},
             "roofline": {"bound": "hbm", "kernel": "search_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC["search_count_kernel"] if (F, L, nq, qlen) == (8192, 26, 10000, 1000) else None,
+                         "traffic": NCU_TRAFFIC.get("search_count_kernel") if (F, L, nq, qlen) == (8192, 26, 10000, 1000) else None,
                          "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": t_k * 1e3, "share_of_step": t_k * 1e3 / (sec / steps * 1e3),
                          "algorithmic_bytes": alg_bytes},
             "kernel_ms_per_step": {"query_kmers": float(ms[capi.T_AUX]) / steps, "search_count": float(ms[capi.T_SEARCH]) / steps},
@@ -683,7 +801,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--stages", default="construct,construct_c5,construct_raw,crc32,transpose,search")
-    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (handles) per GPU in the construct e2e arm")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (handles) per GPU in the construct e2e arm")
+    ap.add_argument("--in-flight", type=int, default=1, help="accessions in flight per GPU (handles, streams) in the device-resident construct arm")
     ap.add_argument("--reads", type=int, default=1000000, help="reads per accession (step)")
     ap.add_argument("--min-kmer-count", type=int, default=1, help="counting-filter threshold (reference default 5; needs --coverage)")
     ap.add_argument("--coverage", type=float, default=0.0, help=">0: reads are sampled from a random genome at this coverage")
@@ -714,6 +833,16 @@ def main():
         budget_s = 150.0 / max(args.steps + args.warmup, 1)
         reads = int(min(args.reads, max(20000, budget_s * 0.9e6 / (READ_LEN - K + 1))))
         rate, desc, kind, cores, step_s = reference_construct(n_proc, reads, args.steps, args.warmup)
+        # the workload this arm actually ran: a bounded sample of the GPU arm's accession
+        config = dict(config)
+        config["workload"] = ("bounded sample of configs[1]: each step = %d processes x 1 accession of %d synthetic %d bp reads (%.3g k-mer occurrences "
+                              "each; the GPU arm's accession has %d reads), k=%d, counting filter with min_kmer_count=%d, p=%.2f, L in [%d,%d]; the "
+                              "reference's make_bloom_filter is single-threaded, one process per accession on every host core" % (
+                                  cores, reads, READ_LEN, reads * (READ_LEN - K + 1), args.reads, K, args.min_kmer_count, P_FALSE, LMIN, LMAX))
+        config["reads_per_accession"] = reads
+        config["full_workload_reads_per_accession"] = args.reads
+        config["parallelism"] = "accession-per-process x%d host processes" % cores
+        config["l2_policy"] = "n/a (CPU)"
         line = {"impl": "reference", "metric": "Bloom k-mer inserts/s", "value": rate, "unit": "kmer_inserts/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,

@@ -88,6 +88,16 @@ int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offse
 int kwg_bloom_add_reads_dev(kwg_bloom_t* b, const char* d_bases, const uint64_t* d_offsets,
 	uint64_t n_reads, uint64_t n_bases);
 
+/* The same reads 2-bit packed, as the SRA stores them (NCBI 2na): four bases per byte, the first in bits 7..6, A=0 C=1
+ * G=2 T=3 (the reference's own code order, word.h:19); base i of the call is in byte i/4.  bad_mask (may be NULL: every
+ * base is one of ACGT) has bit i%8 of byte i/8 set where base i is anything else (N, IUPAC codes: word.h:98-100 breaks
+ * the k-mer there); 2-byte aligned.  offsets are in bases, as above: reads need not start on byte boundaries.  A
+ * quarter of the PCIe traffic of the ASCII call (plus 1/8 byte per base when there is a mask) for hosts that hold packed
+ * reads or pack them on their parser threads (make_bloom.cpp:194-300 is the loop this feeds). */
+int kwg_bloom_add_packed(kwg_bloom_t* b, const uint8_t* packed, const uint8_t* bad_mask, const uint64_t* offsets, uint64_t n_reads);
+int kwg_bloom_add_packed_dev(kwg_bloom_t* b, const uint8_t* d_packed, const uint8_t* d_bad_mask, const uint64_t* d_offsets,
+	uint64_t n_reads, uint64_t n_bases);
+
 /* Counting mode: number of "valid" k-mers so far == BloomProgress::num_kmer (make_bloom.cpp:563).
  * Raw mode: number of k-mer occurrences inserted.  Synchronises the handle's stream. */
 int kwg_bloom_num_valid(kwg_bloom_t* b, uint64_t* n);
@@ -131,6 +141,18 @@ int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitc
 int kwg_transpose_crc(int device, const uint8_t* const* filter_chunks, uint32_t n_filters,
 	uint64_t chunk_bits, uint8_t* dest, uint32_t* filter_crc, uint32_t* dest_crc);
 
+/* ------------------------------------------------------------------------------------------
+ * Column concatenation of database files: the body of merge_database_files()'s chunk loop, merge_db.cpp:489-584 (the
+ * copy of source 1's slice and the bit-by-bit move of source 2's behind it, 533-566).  File handling, the running
+ * crc32_z values (519-520, 576, 586) and the FilterInfo sections stay on host.
+ *   src1, src2 : n_slices slices of ceil(n1/8) resp. ceil(n2/8) bytes (the files' slice layout, kwage.h:30-72)
+ *   n_dst1     : filters of destination 1 = n1 + the leading (n_dst1 - n1) columns of source 2; the other columns of
+ *                source 2 (has_remainder, merge_db.cpp:330) go to dst2, which may be NULL when there are none
+ *   dst1, dst2 : n_slices slices of ceil(n_dst1/8) resp. ceil((n1 + n2 - n_dst1)/8) bytes, fully overwritten
+ * ------------------------------------------------------------------------------------------ */
+int kwg_merge_slices(int device, const uint8_t* src1, uint32_t n1, const uint8_t* src2, uint32_t n2, uint64_t n_slices,
+	uint32_t n_dst1, uint8_t* dst1, uint8_t* dst2);
+
 /* Page-locked host memory for the staging buffers of the calls above (filter chunks, slices, read batches): the
  * library's copies then run at PCIe rate and overlap with its kernels.  Optional: any host pointer works. */
 void* kwg_host_alloc(uint64_t bytes);
@@ -170,12 +192,17 @@ int kwg_db_load(kwg_db_t** out, int device, const uint8_t* slices, uint32_t kmer
 int kwg_db_alloc(kwg_db_t** out, int device, uint32_t kmer_len, uint32_t num_hash, uint32_t log2_len,
 	uint32_t n_filters_total, uint32_t col_begin, uint32_t col_end);
 int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
+/* The same without waiting for the copy: `rows` must stay untouched until kwg_db_sync(db) (or the next synchronous call on
+ * this handle) returns.  With two page-locked buffers (kwg_host_alloc) the host reads piece n + 1 of the file while piece n
+ * travels: what SubjectDatabase does for the slice regions the reference seeks through on every query (kwage.cpp:404-483). */
+int kwg_db_upload_rows_async(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
 /* Several database files as one column slab (the reference keeps <= 2048 filters per file: 256-byte rows; wide rows gather
  * at three times the HBM rate).  After kwg_db_alloc(n_filters_total = sum of the files' filters, 0, n_filters_total):
  * rows [row_begin, row_begin + n_rows) of a file with n_cols filters -- n_rows * ceil(n_cols/8) host bytes, exactly the
  * file's slice region -- go to the columns [col_begin, col_begin + n_cols) of the slab; any bit offset.  Each column range
  * may be written once (bits are OR-ed into the zero-initialised slab).  Hits then carry slab column indices. */
 int kwg_db_upload_columns(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
+int kwg_db_upload_columns_async(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows);
 
 /* Use slices that are already in HBM (e.g. written by kwg_transpose_dev); row k at
  * d_slices + k*row_pitch, row_pitch % 16 == 0, bits >= n_filters in a row must be zero.

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libkwage_cuda.so")
-SOURCES = ["api.cu", "bloom_build.cu", "transpose.cu", "search.cu", "synth.cu", "crc32.cu"]
+SOURCES = ["api.cu", "bloom_build.cu", "transpose.cu", "search.cu", "synth.cu", "crc32.cu", "merge.cu"]
 HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
     [os.path.join(ROOT, "include", "kwage_cuda.h"), os.path.abspath(__file__)]
 

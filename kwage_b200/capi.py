@@ -23,9 +23,11 @@ KWG_ERR_STATE = -5
 EXPORTS = [
     "kwg_last_error", "kwg_version", "kwg_device_count", "kwg_launch_count",
     "kwg_bloom_create", "kwg_bloom_create_raw", "kwg_bloom_add_reads", "kwg_bloom_add_reads_dev",
+    "kwg_bloom_add_packed", "kwg_bloom_add_packed_dev",
     "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_finalize_crc", "kwg_bloom_reset",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
     "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev", "kwg_host_alloc", "kwg_host_free",
+    "kwg_merge_slices", "kwg_db_upload_rows_async", "kwg_db_upload_columns_async",
     "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_upload_columns", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
     "kwg_db_set_count_budget", "kwg_search_hits_dev",
@@ -69,6 +71,8 @@ def lib():
     L.kwg_bloom_create_raw.argtypes = [pvp, i32, u32, u32, u32]
     L.kwg_bloom_add_reads.argtypes = [vp, vp, vp, u64]
     L.kwg_bloom_add_reads_dev.argtypes = [vp, vp, vp, u64, u64]
+    L.kwg_bloom_add_packed.argtypes = [vp, vp, vp, vp, u64]
+    L.kwg_bloom_add_packed_dev.argtypes = [vp, vp, vp, vp, u64, u64]
     L.kwg_bloom_num_valid.argtypes = [vp, C.POINTER(u64)]
     L.kwg_bloom_finalize.argtypes = [vp, u32, u32, vp]
     L.kwg_bloom_finalize_dev.argtypes = [vp, u32, u32, vp]
@@ -90,6 +94,9 @@ def lib():
     L.kwg_db_alloc.argtypes = [pvp, i32, u32, u32, u32, u32, u32, u32]
     L.kwg_db_upload_rows.argtypes = [vp, u64, u64, vp]
     L.kwg_db_upload_columns.argtypes = [vp, u32, u32, u64, u64, vp]
+    L.kwg_db_upload_rows_async.argtypes = [vp, u64, u64, vp]
+    L.kwg_db_upload_columns_async.argtypes = [vp, u32, u32, u64, u64, vp]
+    L.kwg_merge_slices.argtypes = [i32, vp, u32, vp, u32, u64, u32, vp, vp]
     L.kwg_db_attach_dev.argtypes = [pvp, i32, vp, u64, u32, u32, u32, u32]
     L.kwg_db_unload.argtypes = [vp]
     L.kwg_db_unload.restype = None
@@ -162,6 +169,28 @@ def flatten(seqs):
     return np.ascontiguousarray(bases, dtype=np.uint8), offsets
 
 
+def pack_2na(bases):
+    """ASCII bases -> (NCBI 2na bytes, not-a-base mask or None): the input format of kwg_bloom_add_packed.  Test and
+    bench helper (numpy); a host that feeds the library packs on its parser threads (kwage_b200/host/stages.cpp)."""
+    b = _as_bases(bases)
+    n = len(b)
+    u = b & 0xDF
+    code = np.zeros(n, dtype=np.uint8)
+    code[u == ord("C")] = 1
+    code[u == ord("G")] = 2
+    code[u == ord("T")] = 3
+    bad = ~((u == ord("A")) | (u == ord("C")) | (u == ord("G")) | (u == ord("T")))
+    pad = (-n) % 4
+    c4 = np.concatenate([code, np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
+    packed = ((c4[:, 0] << 6) | (c4[:, 1] << 4) | (c4[:, 2] << 2) | c4[:, 3]).astype(np.uint8)
+    mask = None
+    if bad.any():
+        mask = np.packbits(bad, bitorder="little")
+        if len(mask) % 2:
+            mask = np.concatenate([mask, np.zeros(1, dtype=np.uint8)])
+    return np.ascontiguousarray(packed), mask
+
+
 class BloomBuilder:
     """kwg_bloom_t: streaming construction of one Bloom filter (one accession)."""
 
@@ -179,6 +208,22 @@ class BloomBuilder:
         bases = _as_bases(bases)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         check(lib().kwg_bloom_add_reads(self.h, _np_ptr(bases), _np_ptr(offsets), len(offsets) - 1))
+
+    def add_packed(self, packed, bad_mask, offsets):
+        """2na bytes + optional not-a-base mask (pack_2na) + offsets in bases"""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if bad_mask is not None:
+            bad_mask = np.ascontiguousarray(bad_mask, dtype=np.uint8)
+        check(lib().kwg_bloom_add_packed(self.h, _np_ptr(packed), _np_ptr(bad_mask) if bad_mask is not None else None,
+                                         _np_ptr(offsets), len(offsets) - 1))
+
+    def add_packed_ptr(self, packed_ptr, bad_ptr, offsets_ptr, n_reads):
+        check(lib().kwg_bloom_add_packed(self.h, C.c_void_p(packed_ptr), C.c_void_p(bad_ptr) if bad_ptr else None, C.c_void_p(offsets_ptr), n_reads))
+
+    def add_packed_dev(self, d_packed_ptr, d_bad_ptr, d_offsets_ptr, n_reads, n_bases):
+        check(lib().kwg_bloom_add_packed_dev(self.h, C.c_void_p(d_packed_ptr), C.c_void_p(d_bad_ptr) if d_bad_ptr else None,
+                                             C.c_void_p(d_offsets_ptr), n_reads, n_bases))
 
     def add_reads_ptr(self, bases_ptr, offsets_ptr, n_reads):
         """Host pointers (e.g. pinned torch tensors): no numpy conversion."""

@@ -46,8 +46,7 @@ constexpr uint32_t WINDOW_LOG2 = 29;
 enum ScanMode { MODE_RAW = 0, MODE_PASS_B = 2 };
 
 struct ScanParams {
-	const char* bases;           // device, 16-byte aligned
-	uint64_t n_bases;
+	BaseSource src;              // device, 16-byte aligned
 	const uint32_t* start_mask;  // bit p set <=> a read starts at base p
 	uint32_t k;
 	// raw
@@ -84,24 +83,14 @@ kmer_scan_kernel(const ScanParams P)
 	// ---- stage 1: 128-bit coalesced loads of the tile (+halo), encode, park in shared memory
 	for (uint32_t v = tid; v < TILE_VEC; v += SCAN_THREADS) {
 		const uint64_t g = t0 + (uint64_t)v * 16;
-		uint32_t codes = 0, bad16 = 0xFFFFu;
-		if (g + 16 <= P.n_bases) {
-			encode16(ld_nc_v4(P.bases + g), codes, bad16);
-		} else if (g < P.n_bases) {
-			// ragged end of the batch: bytes past n_bases behave like separators
-			uint32_t w[4] = {0, 0, 0, 0};
-			for (uint32_t j = 0; j < 16; ++j) {
-				const uint32_t b = (g + j < P.n_bases) ? (uint8_t)P.bases[g + j] : (uint32_t)'N';
-				w[j >> 2] |= b << (8 * (j & 3));
-			}
-			encode16(make_uint4(w[0], w[1], w[2], w[3]), codes, bad16);
-		}
+		uint32_t codes, bad16;
+		load_group16(P.src, g, codes, bad16);         // (the ragged end of the batch reads as separators)
 		s_codes[v] = codes;
 		reinterpret_cast<uint16_t*>(s_bad)[v] = (uint16_t)bad16;
 	}
 	for (uint32_t v = tid; v < TILE_LOAD / 32 + 1; v += SCAN_THREADS) {
 		const uint64_t w = (t0 >> 5) + v;
-		s_start[v] = (w * 32 < P.n_bases) ? P.start_mask[w] : 0u;
+		s_start[v] = (w * 32 < P.src.n_bases) ? P.start_mask[w] : 0u;
 	}
 	if (tid == 0) {
 		s_codes[TILE_VEC] = 0; s_codes[TILE_VEC + 1] = 0;
@@ -111,6 +100,7 @@ kmer_scan_kernel(const ScanParams P)
 	__syncthreads();
 
 	unsigned long long raw_local = 0;
+	const uint64_t pol_keep = l2_policy_evict_last();     // raw mode: the filter asks to stay in the L2
 
 	// ---- stage 2: one k-mer start position per thread per iteration
 #pragma unroll 1
@@ -194,18 +184,21 @@ __global__ void __launch_bounds__(256)
 insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint32_t k, uint32_t* __restrict__ filter,
 	uint32_t filter_mask, uint32_t win_id, uint32_t n_win, const uint32_t* __restrict__ invalid)
 {
+	// the word list streams through once (evict first) and must not push the filter out of the L2, where the red.or
+	// of a filter of up to 2^29 bits are served (evict last)
+	const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
 		// first-touch path: the list holds every occurrence; the few that read four non-zero counters are skipped
 		if (invalid && ((invalid[i >> 5] >> (i & 31u)) & 1u)) continue;
-		const uint64_t w = chunks[i >> LIST_CHUNK_LOG2][i & (LIST_CHUNK - 1)];
+		const uint64_t w = ld_nc_u64_hint(&chunks[i >> LIST_CHUNK_LOG2][i & (LIST_CHUNK - 1)], pol_stream);
 		const uint64_t low = reverse_groups(w, k);
 		uint32_t h[NH];
 		murmur3_multi<NH>(low, k, h);
 #pragma unroll
 		for (int s = 0; s < NH; ++s) {
 			const uint32_t bit = h[s] & filter_mask;
-			if (n_win == 1 || (bit >> WINDOW_LOG2) == win_id) atomicOr(filter + (bit >> 5), 1u << (bit & 31));
+			if (n_win == 1 || (bit >> WINDOW_LOG2) == win_id) red_or_hint(filter + (bit >> 5), 1u << (bit & 31), pol_keep);
 		}
 	}
 }
@@ -273,6 +266,8 @@ struct kwg_bloom {
 	size_t offsets_cap = 0;
 	uint32_t* d_start = nullptr;
 	size_t start_cap = 0;
+	uint16_t* d_bad = nullptr;    // packed input: not-a-base mask of the batch
+	size_t bad_cap = 0;
 	uint32_t* d_crc_ws = nullptr; size_t crc_ws_cap = 0;   // kwg_bloom_finalize_crc
 	uint32_t* h_crc = nullptr;                             // pinned
 	KernelTimers timers;
@@ -380,12 +375,78 @@ static int count_kernels_init()
 	return KWG_OK;
 }
 
-constexpr size_t FEED_CHUNK = 16u << 20;
+constexpr size_t FEED_CHUNK = 16u << 20;          // bases per piece of the host feed
+
+// Bases that are still on the host when the first kernel is launched: they are copied piece by piece on the copy
+// stream and the scan is launched piece by piece behind them, so that the H2D copy hides behind the kernels.
+struct HostFeed {
+	const char* h_bases = nullptr;     // what goes to BaseSource::bases (ASCII: one byte per base, packed: four bases per byte)
+	const uint16_t* h_bad = nullptr;   // packed: the not-a-base mask (NULL: none)
+	uint32_t lead = 0;                 // packed: the first `lead` (< 16) bases belong to the batch before and must not count
+};
+struct FeedPiece { uint32_t tile0, n_tiles; size_t off, len; };   // tiles of the scan that may run once bases [off, off + len) have arrived
+
+// pieces of about `chunk` bases; a tile of `pos` start positions reads `load` bases from its first position
+static std::vector<FeedPiece> feed_plan(uint64_t n_bases, size_t chunk, uint32_t pos, uint32_t load, uint32_t n_tiles)
+{
+	std::vector<FeedPiece> pieces;
+	const size_t n_chunks = (size_t)ceil_div(n_bases, chunk);
+	uint32_t t_done = 0;
+	for (size_t c = 0; c < n_chunks; ++c) {
+		const size_t off = c * chunk, len = std::min<size_t>(chunk, (size_t)n_bases - off);
+		const uint32_t t_end = (c + 1 == n_chunks) ? n_tiles
+			: (uint32_t)std::min<uint64_t>(n_tiles, (off + len >= (size_t)load) ? (off + len - load) / pos + 1 : 0);
+		pieces.push_back(FeedPiece{t_done, t_end > t_done ? t_end - t_done : 0u, off, len});
+		t_done = std::max(t_done, t_end);
+	}
+	return pieces;
+}
+
+// packed input: the not-a-base mask of the batch (the caller's, or zeros) with the lead-in blanked
+static int stage_mask(const BaseSource& S, const HostFeed& F, cudaStream_t st)
+{
+	if (!S.packed || !S.bad_mask) return KWG_OK;
+	uint16_t* d = const_cast<uint16_t*>(S.bad_mask);
+	const size_t bytes = (size_t)ceil_div(S.n_bases, 8);
+	if (F.h_bad) KWG_CUDA(cudaMemcpyAsync(d, F.h_bad, bytes, cudaMemcpyHostToDevice, st));
+	else KWG_CUDA(cudaMemsetAsync(d, 0, round_up(bytes, 2), st));
+	if (F.lead) {
+		// (two bytes from pageable memory: staged by the runtime before the call returns)
+		const uint16_t w0 = (uint16_t)((F.h_bad ? F.h_bad[0] : 0u) | ((1u << F.lead) - 1u));
+		KWG_CUDA(cudaMemcpyAsync(d, &w0, sizeof(w0), cudaMemcpyHostToDevice, st));
+	}
+	return KWG_OK;
+}
+
+static int feed_begin(kwg_bloom* b, size_t n_pieces, const BaseSource& S, const HostFeed& F)
+{
+	if (!b->copy_stream) KWG_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+	while (b->feed_events.size() < n_pieces + 1) {
+		cudaEvent_t e;
+		KWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		b->feed_events.push_back(e);
+	}
+	// the staging buffer may still be read by work queued earlier on the compute stream
+	KWG_CUDA(cudaEventRecord(b->feed_events[n_pieces], b->stream));
+	KWG_CUDA(cudaStreamWaitEvent(b->copy_stream, b->feed_events[n_pieces], 0));
+	return stage_mask(S, F, b->copy_stream);
+}
+
+// piece l travels; the compute stream waits for it
+static int feed_piece(kwg_bloom* b, size_t l, const FeedPiece& L, const BaseSource& S, const HostFeed& F)
+{
+	size_t o = L.off, n = L.len;
+	if (S.packed) { n = (size_t)ceil_div(o + n, 4) - o / 4; o /= 4; }      // (piece boundaries are multiples of 4 bases)
+	KWG_CUDA(cudaMemcpyAsync(const_cast<char*>(S.bases) + o, F.h_bases + o, n, cudaMemcpyHostToDevice, b->copy_stream));
+	KWG_CUDA(cudaEventRecord(b->feed_events[l], b->copy_stream));
+	KWG_CUDA(cudaStreamWaitEvent(b->stream, b->feed_events[l], 0));
+	return KWG_OK;
+}
 
 // min_kmer_count == 1, at most FT_MAX_BUCKETS buckets of 2^20 slots (lc <= 30): count / scan / hash by tile, append into
 // page chains, resolve bucket by bucket against a 1-bit-per-slot tile, mark the invalid occurrences (bloom_first.cuh).
 // The canonical words go straight into the accession's list (entries list_base + ordinal), there is no pass B.
-static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const char* h_feed, uint64_t list_base)
+static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const HostFeed* h_feed, uint64_t list_base)
 {
 	const CountGeom& G = b->geom;
 	const uint32_t slot_bits = G.lc + 1;
@@ -395,35 +456,17 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	const uint32_t n_tiles = (uint32_t)ceil_div(n_pos, HT_POS);
 	int rc;
 
-	// pieces: one, or one per piece of the host feed (at most FT_MAX_CHAINS / sms of them)
-	struct Piece { uint32_t tile0, n_tiles, grid, chain0; size_t feed_off, feed_len; };
-	std::vector<Piece> pieces;
-	if (!h_feed) {
-		pieces.push_back(Piece{0, n_tiles, 0, 0, 0, 0});
-	} else {
-		const size_t max_pieces = std::max<size_t>(1, (size_t)FT_MAX_CHAINS / sms);
-		const size_t chunk = std::max<size_t>(FEED_CHUNK, (size_t)round_up(ceil_div(S.n_bases, max_pieces), 1u << 20));
-		const size_t n_chunks = (size_t)ceil_div(S.n_bases, chunk);
-		uint32_t t_done = 0;
-		for (size_t c = 0; c < n_chunks; ++c) {
-			const size_t off = c * chunk, len = std::min<size_t>(chunk, (size_t)S.n_bases - off);
-			// a tile reads HT_LOAD bases from its first position
-			const uint32_t t_end = (c + 1 == n_chunks) ? n_tiles
-				: (uint32_t)std::min<uint64_t>(n_tiles, (off + len >= (size_t)HT_LOAD) ? (off + len - HT_LOAD) / HT_POS + 1 : 0);
-			pieces.push_back(Piece{t_done, t_end > t_done ? t_end - t_done : 0u, 0, 0, off, len});
-			t_done = std::max(t_done, t_end);
-		}
-	}
-	uint32_t n_chains = 0;
-	uint64_t max_per_cta = FT_SUB;                             // ordinals per append block, upper bound
-	for (Piece& L : pieces) {
-		if (L.n_tiles == 0) continue;
-		const uint64_t ords = (uint64_t)L.n_tiles * HT_POS;
-		L.grid = (uint32_t)std::min<uint64_t>(sms, ceil_div(ords, FT_SUB));
-		L.chain0 = n_chains;
-		n_chains += L.grid;
-		max_per_cta = std::max<uint64_t>(max_per_cta, round_up(ceil_div(ords, L.grid), FT_SUB));
-	}
+	// The count / scan / hash passes run piece by piece behind the host feed (one piece when the bases are resident);
+	// the append is ONE launch over all the ordinals of the sub-batch: every append block opens a chain per bucket, and
+	// the resolver pays for every chain (a table entry, a padded last unit), so fewer and longer chains are cheaper
+	// than an append that starts before the last piece has arrived.
+	std::vector<FeedPiece> pieces;
+	if (!h_feed) pieces.push_back(FeedPiece{0, n_tiles, 0, 0});
+	else pieces = feed_plan(S.src.n_bases, FEED_CHUNK, HT_POS, HT_LOAD, n_tiles);
+	const uint64_t ords = (uint64_t)n_tiles * HT_POS;                          // upper bound of the ordinals
+	const uint32_t append_grid = (uint32_t)std::min<uint64_t>(sms, ceil_div(ords, FT_SUB));
+	const uint32_t n_chains = append_grid;
+	const uint64_t max_per_cta = std::max<uint64_t>(FT_SUB, round_up(ceil_div(ords, append_grid), FT_SUB));   // ordinals per append block, upper bound
 	if (n_chains > (uint32_t)FT_MAX_CHAINS) return fail(KWG_ERR_CUDA, "internal: too many partition chains");
 	const uint32_t max_chains = (uint32_t)round_up(std::max(n_chains, 1u), 32);
 
@@ -438,7 +481,7 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	if (ppc64 * max_chains >= 0xFFFFFFFFull || ppc64 >= (1ull << FT_SEQ_BITS)) return fail(KWG_ERR_CUDA, "internal: page pool too large");
 	const uint32_t ppc = (uint32_t)ppc64;
 	const size_t page_bytes = (size_t)FT_UNIT_BYTES << pu_log2;
-	const size_t meta_words = 2 + 2 * pieces.size();
+	const size_t meta_words = 2;
 	if ((rc = grow((void**)&b->d_ft_pool, &b->ft_pool_cap, (size_t)n_chains * ppc * page_bytes))) return rc;
 	if ((rc = grow((void**)&b->d_ft_log, &b->ft_log_cap, (size_t)n_chains * ppc * sizeof(uint32_t)))) return rc;
 	if ((rc = grow((void**)&b->d_ft_plist, &b->ft_plist_cap, (size_t)n_chains * ppc * sizeof(uint32_t)))) return rc;
@@ -450,7 +493,7 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	KWG_CUDA(cudaMemsetAsync(b->d_ft_meta, 0, meta_words * sizeof(uint32_t), b->stream));
 
 	FtTileParams T{};
-	T.bases = S.bases; T.n_bases = S.n_bases; T.start_mask = S.start_mask; T.k = S.k;
+	T.src = S.src; T.start_mask = S.start_mask; T.k = S.k;
 	T.pos0 = pos0; T.n_pos = n_pos;
 	T.tile_cnt = b->d_ft_tiles;
 	T.count_mask = G.count_mask;
@@ -465,40 +508,25 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	A.max_chains = max_chains; A.pu_log2 = pu_log2; A.ppc = ppc;
 	A.pool = b->d_ft_pool; A.page_log = b->d_ft_log; A.plist = b->d_ft_plist; A.info = b->d_ft_info;
 
-	if (h_feed) {
-		if (!b->copy_stream) KWG_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
-		while (b->feed_events.size() < pieces.size() + 1) {
-			cudaEvent_t e;
-			KWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-			b->feed_events.push_back(e);
-		}
-		// the staging buffer may still be read by work queued earlier on the compute stream
-		KWG_CUDA(cudaEventRecord(b->feed_events[pieces.size()], b->stream));
-		KWG_CUDA(cudaStreamWaitEvent(b->copy_stream, b->feed_events[pieces.size()], 0));
-	}
+	if (h_feed && (rc = feed_begin(b, pieces.size(), S.src, *h_feed))) return rc;
 	for (size_t l = 0; l < pieces.size(); ++l) {
-		const Piece& L = pieces[l];
-		if (h_feed) {
-			KWG_CUDA(cudaMemcpyAsync(const_cast<char*>(S.bases) + L.feed_off, h_feed + L.feed_off, L.feed_len, cudaMemcpyHostToDevice, b->copy_stream));
-			KWG_CUDA(cudaEventRecord(b->feed_events[l], b->copy_stream));
-			KWG_CUDA(cudaStreamWaitEvent(b->stream, b->feed_events[l], 0));
-		}
+		const FeedPiece& L = pieces[l];
+		if (h_feed && (rc = feed_piece(b, l, L, S.src, *h_feed))) return rc;
 		if (L.n_tiles == 0) continue;
 		T.tile0 = L.tile0;
 		b->timers.begin(KWG_T_SCAN_A, b->stream);
 		ft_count_kernel<<<L.n_tiles, HT_THREADS, 0, b->stream>>>(T);
 		KWG_LAUNCHED();
-		ft_scan_kernel<<<1, 1024, 0, b->stream>>>(b->d_ft_tiles, L.tile0, L.n_tiles, b->d_ft_meta, (uint32_t)l);
+		ft_scan_kernel<<<1, 1024, 0, b->stream>>>(b->d_ft_tiles, L.tile0, L.n_tiles, b->d_ft_meta);
 		KWG_LAUNCHED();
 		ft_hash_kernel<<<L.n_tiles, HT_THREADS, 0, b->stream>>>(T);
 		b->timers.end(b->stream);
 		KWG_LAUNCHED();
-		A.piece = (uint32_t)l; A.chain0 = L.chain0;
-		b->timers.begin(KWG_T_REGROUP, b->stream);
-		ft_append_kernel<<<L.grid, FT_THREADS, ft_append_smem_bytes(), b->stream>>>(A);
-		b->timers.end(b->stream);
-		KWG_LAUNCHED();
 	}
+	b->timers.begin(KWG_T_REGROUP, b->stream);
+	ft_append_kernel<<<append_grid, FT_THREADS, ft_append_smem_bytes(), b->stream>>>(A);
+	b->timers.end(b->stream);
+	KWG_LAUNCHED();
 
 	FtResolveParams K3{};
 	K3.pool = b->d_ft_pool; K3.plist = b->d_ft_plist; K3.info = b->d_ft_info;
@@ -523,7 +551,7 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 // partition (K1) -> [regroup (K2)] -> resolve (K3) -> pass B (valid-word list).
 // h_feed != NULL: the bases of this (single) sub-batch are still on the host at h_feed; they are copied in
 // FEED_CHUNK pieces on the copy stream and the partition scan is launched piece by piece behind them.
-static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const char* h_feed)
+static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uint64_t n_pos, const HostFeed* h_feed)
 {
 	const CountGeom& G = b->geom;
 	const uint32_t F1 = 1u << G.f1_log2, F2 = 1u << G.f2_log2;
@@ -567,7 +595,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	if (b->min_count > 1 && (rc = grow((void**)&b->d_elig, &b->elig_cap, loss_words / 4 * sizeof(uint32_t)))) return rc;
 
 	PartParams K1{};
-	K1.bases = S.bases; K1.n_bases = S.n_bases; K1.start_mask = S.start_mask; K1.k = S.k;
+	K1.src = S.src; K1.start_mask = S.start_mask; K1.k = S.k;
 	K1.pos0 = pos0; K1.n_pos = n_pos;
 	K1.count_mask = G.count_mask;
 	K1.f1_log2 = G.f1_log2;
@@ -582,29 +610,14 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		partition_scan_kernel<<<(unsigned)n_tiles, PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
 		KWG_LAUNCHED();
 	} else {
-		if (!b->copy_stream) KWG_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
-		const size_t n_chunks = (size_t)ceil_div(S.n_bases, FEED_CHUNK);
-		while (b->feed_events.size() < n_chunks + 1) {
-			cudaEvent_t e;
-			KWG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-			b->feed_events.push_back(e);
-		}
-		// the staging buffer may still be read by work queued earlier on the compute stream
-		KWG_CUDA(cudaEventRecord(b->feed_events[n_chunks], b->stream));
-		KWG_CUDA(cudaStreamWaitEvent(b->copy_stream, b->feed_events[n_chunks], 0));
-		uint64_t t_done = 0;
-		for (size_t c = 0; c < n_chunks; ++c) {
-			const size_t off = c * FEED_CHUNK, len = std::min<size_t>(FEED_CHUNK, (size_t)S.n_bases - off);
-			KWG_CUDA(cudaMemcpyAsync(const_cast<char*>(S.bases) + off, h_feed + off, len, cudaMemcpyHostToDevice, b->copy_stream));
-			KWG_CUDA(cudaEventRecord(b->feed_events[c], b->copy_stream));
-			KWG_CUDA(cudaStreamWaitEvent(b->stream, b->feed_events[c], 0));
-			// a tile reads PT_LOAD bases from its first position
-			const uint64_t t_end = (c + 1 == n_chunks) ? n_tiles : std::min<uint64_t>(n_tiles, (off + len >= (size_t)PT_LOAD) ? (off + len - PT_LOAD) / PT_POS + 1 : 0);
-			if (t_end > t_done) {
-				K1.tile0 = (uint32_t)t_done;
-				partition_scan_kernel<<<(unsigned)(t_end - t_done), PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
+		const std::vector<FeedPiece> pieces = feed_plan(S.src.n_bases, FEED_CHUNK, PT_POS, PT_LOAD, (uint32_t)n_tiles);
+		if ((rc = feed_begin(b, pieces.size(), S.src, *h_feed))) return rc;
+		for (size_t l = 0; l < pieces.size(); ++l) {
+			if ((rc = feed_piece(b, l, pieces[l], S.src, *h_feed))) return rc;
+			if (pieces[l].n_tiles) {
+				K1.tile0 = pieces[l].tile0;
+				partition_scan_kernel<<<pieces[l].n_tiles, PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
 				KWG_LAUNCHED();
-				t_done = t_end;
 			}
 		}
 	}
@@ -715,15 +728,17 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 	return launch_scan<MODE_PASS_B>(b, P);
 }
 
-// All inputs on the device: d_bases (16-byte aligned), d_offsets[n_reads+1] with offsets relative
-// to off0.  n_bases < 2^32 - 2.
-static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
-	uint64_t off0, uint64_t n_bases, const char* h_feed = nullptr)
+// All inputs on the device (or on their way: `feed`): src.bases 16-byte aligned, d_offsets[n_reads+1] with offsets
+// relative to off0.  n_bases < 2^32 - 16.
+static int add_batch_dev(kwg_bloom* b, const BaseSource& src, const uint64_t* d_offsets, uint64_t n_reads,
+	uint64_t off0, const HostFeed* feed = nullptr)
 {
+	const uint64_t n_bases = src.n_bases;
 	if (n_bases == 0 || n_reads == 0) return KWG_OK;
 	if (n_bases >= 0xFFFFFFF0ull) return fail(KWG_ERR_INVALID_ARG, "a device batch must hold fewer than 2^32-16 bases");
 	if (b->raw) b->n_valid_known = false;      // (counting mode invalidates after it has read the counter, below)
-	if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) != 0) return fail(KWG_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+	if ((reinterpret_cast<uintptr_t>(src.bases) & 15u) != 0) return fail(KWG_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+	if ((reinterpret_cast<uintptr_t>(src.bad_mask) & 1u) != 0) return fail(KWG_ERR_INVALID_ARG, "the not-a-base mask must be 2-byte aligned");
 
 	const size_t start_words = (size_t)(n_bases / 32 + 2);
 	int rc = grow((void**)&b->d_start, &b->start_cap, start_words * sizeof(uint32_t));
@@ -735,8 +750,7 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	KWG_LAUNCHED();
 
 	ScanParams P{};
-	P.bases = d_bases;
-	P.n_bases = n_bases;
+	P.src = src;
 	P.start_mask = b->d_start;
 	P.k = b->k;
 	P.counter = b->d_counter;
@@ -746,16 +760,38 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 	if (b->raw) {
 		P.filter = b->d_filter;
 		P.filter_mask = (b->raw_L >= 32) ? 0xFFFFFFFFu : ((1u << b->raw_L) - 1u);
-		P.n_win = (b->raw_L > WINDOW_LOG2 && !getenv("KWG_NO_WINDOWS")) ? 1u << (b->raw_L - WINDOW_LOG2) : 1u;
-		for (P.win_id = 0; P.win_id < P.n_win; ++P.win_id)
-			if ((rc = launch_scan<MODE_RAW>(b, P))) return rc;
+		P.n_win = (b->raw_L > WINDOW_LOG2) ? 1u << (b->raw_L - WINDOW_LOG2) : 1u;
+		const uint32_t n_tiles = (uint32_t)ceil_div(n_bases, TILE_BASES);
+		// the first pass over the bases runs piece by piece behind the host feed; further window passes find them in HBM
+		std::vector<FeedPiece> pieces;
+		if (feed) {
+			pieces = feed_plan(n_bases, FEED_CHUNK, TILE_BASES, TILE_LOAD, n_tiles);
+			if ((rc = feed_begin(b, pieces.size(), src, *feed))) return rc;
+		} else {
+			pieces.push_back(FeedPiece{0, n_tiles, 0, (size_t)n_bases});
+		}
+		for (P.win_id = 0; P.win_id < P.n_win; ++P.win_id) {
+			for (size_t l = 0; l < pieces.size(); ++l) {
+				if (feed && P.win_id == 0 && (rc = feed_piece(b, l, pieces[l], src, *feed))) return rc;
+				if (!pieces[l].n_tiles) continue;
+				P.pos0 = (uint64_t)pieces[l].tile0 * TILE_BASES;
+				P.n_pos = std::min<uint64_t>((uint64_t)pieces[l].n_tiles * TILE_BASES, n_bases - P.pos0);
+				if ((rc = launch_scan<MODE_RAW>(b, P))) return rc;
+			}
+		}
 		return KWG_OK;
 	}
 
 	// counting mode: sub-batches of just under 2^28 start positions (a record carries a 28-bit position)
+	if (feed && n_bases > FT_MAX_POS) {
+		// (several sub-batches: the bases go over in one piece first)
+		if ((rc = feed_begin(b, 1, src, *feed))) return rc;
+		if ((rc = feed_piece(b, 0, FeedPiece{0, 0, 0, (size_t)n_bases}, src, *feed))) return rc;
+		feed = nullptr;
+	}
 	for (uint64_t pos0 = 0; pos0 < n_bases; pos0 += FT_MAX_POS) {
 		const uint64_t n_pos = std::min<uint64_t>(FT_MAX_POS, n_bases - pos0);
-		rc = count_sub_batch(b, P, pos0, n_pos, (n_bases <= FT_MAX_POS) ? h_feed : nullptr);
+		rc = count_sub_batch(b, P, pos0, n_pos, feed);
 		if (rc) return rc;
 	}
 	return KWG_OK;
@@ -763,12 +799,6 @@ static int add_batch_dev(kwg_bloom* b, const char* d_bases, const uint64_t* d_of
 
 static int bloom_alloc_common(kwg_bloom* b)
 {
-	if (const char* e = getenv("KWG_L2_FETCH")) {    // experiment knob: L2 fetch granularity hint (32/64/128)
-		cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
-		size_t v = 0;
-		cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity);
-		fprintf(stderr, "[kwg] L2 fetch granularity = %zu\n", v);
-	}
 	KWG_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	KWG_CUDA(cudaMalloc(&b->d_counter, 3 * sizeof(unsigned long long)));
 	KWG_CUDA(cudaMallocHost(&b->h_counter, 3 * sizeof(unsigned long long)));
@@ -801,6 +831,7 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	cudaFree(b->d_bases);
 	cudaFree(b->d_offsets);
 	cudaFree(b->d_start);
+	cudaFree(b->d_bad);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	delete b;
 }
@@ -897,7 +928,72 @@ int kwg_bloom_add_reads_dev(kwg_bloom_t* b, const char* d_bases, const uint64_t*
 	if (!d_bases || !d_offsets) return fail(KWG_ERR_INVALID_ARG, "NULL input");
 	int rc = select_device(b->device);
 	if (rc) return rc;
-	return add_batch_dev(b, d_bases, d_offsets, n_reads, 0, n_bases);
+	return add_batch_dev(b, BaseSource{d_bases, nullptr, n_bases, 0u}, d_offsets, n_reads, 0);
+}
+
+int kwg_bloom_add_packed_dev(kwg_bloom_t* b, const uint8_t* d_packed, const uint8_t* d_bad_mask, const uint64_t* d_offsets,
+	uint64_t n_reads, uint64_t n_bases)
+{
+	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	if (n_reads == 0 || n_bases == 0) return KWG_OK;
+	if (!d_packed || !d_offsets) return fail(KWG_ERR_INVALID_ARG, "NULL input");
+	int rc = select_device(b->device);
+	if (rc) return rc;
+	return add_batch_dev(b, BaseSource{reinterpret_cast<const char*>(d_packed), reinterpret_cast<const uint16_t*>(d_bad_mask), n_bases, 1u},
+		d_offsets, n_reads, 0);
+}
+
+// Host batches: whole reads, at most MAX_BATCH_BASES bases each (at least one read).  ASCII (`packed` false: `bases` holds one
+// byte per base) or 2na (`bases` holds four bases per byte from base 0 of the call, `bad` the optional mask).
+static int add_reads_host(kwg_bloom* b, const char* bases, const uint16_t* bad, bool packed, const uint64_t* offsets, uint64_t n_reads)
+{
+	int rc;
+	{
+		uint64_t wrong = 0;                    // branch-free so that the compiler vectorises the scan
+		for (uint64_t r = 0; r < n_reads; ++r) wrong |= (uint64_t)(offsets[r + 1] < offsets[r]);
+		if (wrong) return fail(KWG_ERR_INVALID_ARG, "offsets must be non-decreasing");
+	}
+	uint64_t r0 = 0;
+	while (r0 < n_reads) {
+		uint64_t r1;
+		if (offsets[n_reads] - offsets[r0] <= MAX_BATCH_BASES) {
+			r1 = n_reads;
+		} else {
+			r1 = (uint64_t)(std::upper_bound(offsets + r0 + 1, offsets + n_reads + 1, offsets[r0] + MAX_BATCH_BASES) - offsets) - 1;
+			if (r1 <= r0) r1 = r0 + 1;
+		}
+		// a packed batch starts on a 16-bit word of the mask (hence on a byte of the 2na stream): the bases between that
+		// boundary and the first read of the batch ride along and are blanked through the mask
+		const uint64_t first = offsets[r0];
+		const uint64_t off0 = packed ? (first & ~(uint64_t)15) : first;
+		const uint32_t lead = (uint32_t)(first - off0);
+		const uint64_t nb = offsets[r1] - off0;
+		if (nb >= 0xFFFFFFF0ull) return fail(KWG_ERR_INVALID_ARG, "a single read of 2^32 bases or more is not supported");
+		if (offsets[r1] > first) {
+			const size_t base_bytes = packed ? (size_t)ceil_div(nb, 4) : (size_t)nb;
+			const bool mask = packed && (bad || lead);
+			rc = grow((void**)&b->d_bases, &b->bases_cap, round_up(base_bytes, 16) + 16);
+			if (rc) return rc;
+			rc = grow((void**)&b->d_offsets, &b->offsets_cap, (r1 - r0 + 1) * sizeof(uint64_t));
+			if (rc) return rc;
+			if (mask && (rc = grow((void**)&b->d_bad, &b->bad_cap, round_up(ceil_div(nb, 8), 16) + 16))) return rc;
+			KWG_CUDA(cudaMemcpyAsync(b->d_offsets, offsets + r0, (r1 - r0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
+			const BaseSource src{b->d_bases, mask ? b->d_bad : nullptr, nb, packed ? 1u : 0u};
+			const HostFeed feed{bases + (packed ? off0 / 4 : off0), (packed && bad) ? bad + off0 / 16 : nullptr, lead};
+			// batches of more than one piece are fed piece by piece behind the scan; small ones go over in one copy
+			const bool chunked = nb > FEED_CHUNK;
+			if (!chunked) {
+				KWG_CUDA(cudaMemcpyAsync(b->d_bases, feed.h_bases, base_bytes, cudaMemcpyHostToDevice, b->stream));
+				if ((rc = stage_mask(src, feed, b->stream))) return rc;
+			}
+			rc = add_batch_dev(b, src, b->d_offsets, r1 - r0, off0, chunked ? &feed : nullptr);
+			if (rc) return rc;
+		}
+		r0 = r1;
+	}
+	// host buffers may be reused by the caller as soon as we return
+	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	return KWG_OK;
 }
 
 int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offsets, uint64_t n_reads)
@@ -907,41 +1003,18 @@ int kwg_bloom_add_reads(kwg_bloom_t* b, const char* bases, const uint64_t* offse
 	if (!bases || !offsets) return fail(KWG_ERR_INVALID_ARG, "NULL input");
 	int rc = select_device(b->device);
 	if (rc) return rc;
-	{
-		uint64_t bad = 0;                      // branch-free so that the compiler vectorises the scan
-		for (uint64_t r = 0; r < n_reads; ++r) bad |= (uint64_t)(offsets[r + 1] < offsets[r]);
-		if (bad) return fail(KWG_ERR_INVALID_ARG, "offsets must be non-decreasing");
-	}
+	return add_reads_host(b, bases, nullptr, false, offsets, n_reads);
+}
 
-	uint64_t r0 = 0;
-	while (r0 < n_reads) {
-		// cut a batch of whole reads of at most MAX_BATCH_BASES bases (at least one read)
-		uint64_t r1;
-		if (offsets[n_reads] - offsets[r0] <= MAX_BATCH_BASES) {
-			r1 = n_reads;
-		} else {
-			r1 = (uint64_t)(std::upper_bound(offsets + r0 + 1, offsets + n_reads + 1, offsets[r0] + MAX_BATCH_BASES) - offsets) - 1;
-			if (r1 <= r0) r1 = r0 + 1;
-		}
-		const uint64_t off0 = offsets[r0];
-		const uint64_t nb = offsets[r1] - off0;
-		if (nb >= 0xFFFFFFF0ull) return fail(KWG_ERR_INVALID_ARG, "a single read of 2^32 bases or more is not supported");
-		if (nb > 0) {
-			rc = grow((void**)&b->d_bases, &b->bases_cap, round_up(nb, 16) + 16);
-			if (rc) return rc;
-			rc = grow((void**)&b->d_offsets, &b->offsets_cap, (r1 - r0 + 1) * sizeof(uint64_t));
-			if (rc) return rc;
-			KWG_CUDA(cudaMemcpyAsync(b->d_offsets, offsets + r0, (r1 - r0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
-			const bool feed = !b->raw && nb <= FT_MAX_POS && nb > FEED_CHUNK;
-			if (!feed) KWG_CUDA(cudaMemcpyAsync(b->d_bases, bases + off0, nb, cudaMemcpyHostToDevice, b->stream));
-			rc = add_batch_dev(b, b->d_bases, b->d_offsets, r1 - r0, off0, nb, feed ? bases + off0 : nullptr);
-			if (rc) return rc;
-		}
-		r0 = r1;
-	}
-	// host buffers may be reused by the caller as soon as we return
-	KWG_CUDA(cudaStreamSynchronize(b->stream));
-	return KWG_OK;
+int kwg_bloom_add_packed(kwg_bloom_t* b, const uint8_t* packed, const uint8_t* bad_mask, const uint64_t* offsets, uint64_t n_reads)
+{
+	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	if (n_reads == 0) return KWG_OK;
+	if (!packed || !offsets) return fail(KWG_ERR_INVALID_ARG, "NULL input");
+	if ((reinterpret_cast<uintptr_t>(bad_mask) & 1u) != 0) return fail(KWG_ERR_INVALID_ARG, "bad_mask must be 2-byte aligned");
+	int rc = select_device(b->device);
+	if (rc) return rc;
+	return add_reads_host(b, reinterpret_cast<const char*>(packed), reinterpret_cast<const uint16_t*>(bad_mask), true, offsets, n_reads);
 }
 
 int kwg_bloom_num_valid(kwg_bloom_t* b, uint64_t* n)
@@ -977,7 +1050,7 @@ int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 		uint32_t* f = reinterpret_cast<uint32_t*>(d_out_bits);
 		b->timers.begin(KWG_T_INSERT, b->stream);
 #define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_list, b->k, f, mask, w, n_win, b->use_ft ? b->d_inv : nullptr); break;
-		const uint32_t n_win = (log2_len > WINDOW_LOG2 && !getenv("KWG_NO_WINDOWS")) ? 1u << (log2_len - WINDOW_LOG2) : 1u;
+		const uint32_t n_win = (log2_len > WINDOW_LOG2) ? 1u << (log2_len - WINDOW_LOG2) : 1u;
 		for (uint32_t w = 0; w < n_win; ++w) {
 			switch (num_hash) {
 				KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5)

@@ -74,8 +74,7 @@ static inline CountGeom count_geometry(uint32_t lc)
 }
 
 struct PartParams {
-	const char* bases;           // device, 16-byte aligned (whole batch)
-	uint64_t n_bases;
+	BaseSource src;              // device, 16-byte aligned (whole batch)
 	const uint32_t* start_mask;
 	uint32_t k;
 	uint64_t pos0;               // absolute base index of the first start position of this sub-batch (multiple of 16)
@@ -146,23 +145,14 @@ partition_scan_kernel(const PartParams P)
 
 	for (uint32_t v = tid; v < (uint32_t)PT_VEC; v += PT_THREADS) {
 		const uint64_t g = t0 + (uint64_t)v * 16;
-		uint32_t codes = 0, bad16 = 0xFFFFu;
-		if (g + 16 <= P.n_bases) {
-			encode16(ld_nc_v4(P.bases + g), codes, bad16);
-		} else if (g < P.n_bases) {
-			uint32_t w[4] = {0, 0, 0, 0};
-			for (uint32_t j = 0; j < 16; ++j) {
-				const uint32_t b = (g + j < P.n_bases) ? (uint8_t)P.bases[g + j] : (uint32_t)'N';
-				w[j >> 2] |= b << (8 * (j & 3));
-			}
-			encode16(make_uint4(w[0], w[1], w[2], w[3]), codes, bad16);
-		}
+		uint32_t codes, bad16;
+		load_group16(P.src, g, codes, bad16);
 		s_codes[v] = codes;
 		reinterpret_cast<uint16_t*>(s_bad)[v] = (uint16_t)bad16;
 	}
 	for (uint32_t v = tid; v < (uint32_t)(PT_LOAD / 32 + 1); v += PT_THREADS) {
 		const uint64_t w = (t0 >> 5) + v;
-		s_start[v] = (w * 32 < P.n_bases) ? P.start_mask[w] : 0u;
+		s_start[v] = (w * 32 < P.src.n_bases) ? P.start_mask[w] : 0u;
 	}
 	for (uint32_t v = tid; v <= F1; v += PT_THREADS) s_hist[v] = 0;
 	if (tid == 0) {

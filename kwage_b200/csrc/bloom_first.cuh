@@ -71,8 +71,7 @@ constexpr int HT_VEC = HT_LOAD / 16;
 constexpr int HT_IT = HT_POS / HT_THREADS;
 
 struct FtTileParams {
-	const char* bases;           // device, 16-byte aligned (whole batch)
-	uint64_t n_bases;
+	BaseSource src;              // device, 16-byte aligned (whole batch)
 	const uint32_t* start_mask;
 	uint32_t k;
 	uint64_t pos0;               // absolute base index of the sub-batch's first start position (multiple of 16)
@@ -94,23 +93,14 @@ __device__ __forceinline__ void ft_stage_tile(const FtTileParams& P, uint64_t t0
 	const uint32_t tid = threadIdx.x;
 	for (uint32_t v = tid; v < (uint32_t)HT_VEC; v += HT_THREADS) {
 		const uint64_t g = t0 + (uint64_t)v * 16;
-		uint32_t codes = 0, bad16 = 0xFFFFu;
-		if (g + 16 <= P.n_bases) {
-			encode16(ld_nc_v4(P.bases + g), codes, bad16);
-		} else if (g < P.n_bases) {
-			uint32_t w[4] = {0, 0, 0, 0};
-			for (uint32_t j = 0; j < 16; ++j) {
-				const uint32_t c = (g + j < P.n_bases) ? (uint8_t)P.bases[g + j] : (uint32_t)'N';
-				w[j >> 2] |= c << (8 * (j & 3));
-			}
-			encode16(make_uint4(w[0], w[1], w[2], w[3]), codes, bad16);
-		}
+		uint32_t codes, bad16;
+		load_group16(P.src, g, codes, bad16);
 		if (CODES) s_codes[v] = codes;
 		reinterpret_cast<uint16_t*>(s_bad)[v] = (uint16_t)bad16;
 	}
 	for (uint32_t v = tid; v < (uint32_t)(HT_LOAD / 32 + 1); v += HT_THREADS) {
 		const uint64_t w = (t0 >> 5) + v;
-		s_start[v] = (w * 32 < P.n_bases) ? P.start_mask[w] : 0u;
+		s_start[v] = (w * 32 < P.src.n_bases) ? P.start_mask[w] : 0u;
 	}
 	if (tid == 0) {
 		if (CODES) { s_codes[HT_VEC] = 0; s_codes[HT_VEC + 1] = 0; }
@@ -144,14 +134,13 @@ ft_count_kernel(const FtTileParams P)
 	}
 }
 
-// meta[0] = ordinals of the sub-batch so far; piece l of the sub-batch: meta[2 + 2l] = its valid windows, meta[3 + 2l] = its first ordinal
+// meta[0] = ordinals of the sub-batch so far (the scan is launched once per piece of the host feed, in stream order)
 __global__ void __launch_bounds__(1024)
-ft_scan_kernel(uint32_t* __restrict__ tile_cnt, uint32_t tile0, uint32_t n_tiles, uint32_t* __restrict__ meta, uint32_t piece)
+ft_scan_kernel(uint32_t* __restrict__ tile_cnt, uint32_t tile0, uint32_t n_tiles, uint32_t* __restrict__ meta)
 {
 	__shared__ uint32_t s_warp[32];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t ord0 = meta[0];
-	uint32_t carry = ord0;
+	uint32_t carry = meta[0];
 	for (uint32_t i0 = 0; i0 < n_tiles; i0 += 1024) {
 		const uint32_t i = i0 + tid;
 		const uint32_t c = (i < n_tiles) ? tile_cnt[tile0 + i] : 0u;
@@ -161,7 +150,7 @@ ft_scan_kernel(uint32_t* __restrict__ tile_cnt, uint32_t tile0, uint32_t n_tiles
 		carry += total;
 	}
 	__syncthreads();
-	if (tid == 0) { meta[2 + 2 * piece] = carry - ord0; meta[3 + 2 * piece] = ord0; meta[0] = carry; }
+	if (tid == 0) meta[0] = carry;
 }
 
 __global__ void __launch_bounds__(HT_THREADS)
@@ -225,11 +214,9 @@ ft_hash_kernel(const FtTileParams P)
 // ------------------------------------------------------------------------------------------ append
 struct FtAppendParams {
 	const uint4* hm;             // [ordinal]
-	const uint32_t* meta;        // ft_scan_kernel
-	uint32_t piece;
+	const uint32_t* meta;        // ft_scan_kernel: [0] = ordinals of the sub-batch
 	uint32_t lc;
 	uint32_t n_buckets;          // power of two <= FT_MAX_BUCKETS
-	uint32_t chain0;             // chain id of block 0 (launches of one sub-batch number their chains in stream order)
 	uint32_t max_chains;         // pitch of an info row
 	uint32_t pu_log2;            // units per page, log2
 	uint32_t ppc;                // pages per chain pool
@@ -300,7 +287,7 @@ ft_append_kernel(const FtAppendParams P)
 	uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_items + FT_MAX_BUCKETS);          // [0] next page of the pool, [1..2] item counts by round parity
 
 	const uint32_t tid = threadIdx.x;
-	const uint32_t chain = P.chain0 + blockIdx.x;
+	const uint32_t chain = blockIdx.x;
 	const uint32_t pu = 1u << P.pu_log2;
 	const uint32_t nb = P.n_buckets;
 
@@ -310,8 +297,8 @@ ft_append_kernel(const FtAppendParams P)
 	if (tid < 3) s_misc[tid] = 0;
 	__syncthreads();
 
-	// my stretch of the piece's ordinals; rounds are aligned to multiples of 1024 ordinals (the resolver's ordering unit)
-	const uint32_t n_ok = P.meta[2 + 2 * P.piece], ord0 = P.meta[3 + 2 * P.piece];
+	// my stretch of the sub-batch's ordinals; rounds are aligned to multiples of 1024 ordinals (the resolver's ordering unit)
+	const uint32_t n_ok = P.meta[0], ord0 = 0;
 	const uint32_t per = (((n_ok + gridDim.x - 1) / gridDim.x) + FT_SUB - 1) & ~(uint32_t)(FT_SUB - 1);
 	const uint32_t o_begin = ord0 + min(n_ok, blockIdx.x * per);
 	const uint32_t o_end = ord0 + min(n_ok, (blockIdx.x + 1) * per);

@@ -247,7 +247,7 @@ int crc32_launch(int device, const uint8_t* d_base, uint64_t n_seg, uint64_t seg
 	const uint64_t n_bytes = n_rows * row_bytes;
 	const bool flat = n_rows == 1 || row_pitch == row_bytes;
 	const bool fast = flat && n_bytes % 32 == 0 && seg_stride % 32 == 0 && (reinterpret_cast<uintptr_t>(d_base) & 31u) == 0 &&
-	                  n_seg * n_bytes >= (uint64_t)(128 << 10) && !getenv("KWG_CRC_SLOW");
+	                  n_seg * n_bytes >= (uint64_t)(128 << 10);
 	int level;
 	if (fast) {
 		static std::once_flag once[64];

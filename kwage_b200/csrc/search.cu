@@ -334,6 +334,9 @@ struct kwg_db {
 	unsigned long long* d_hit_total = nullptr;          // running length of d_hits
 	unsigned long long* h_hit_total = nullptr;          // pinned
 	uint64_t count_budget = 1ull << 30;                 // bytes of per-(query, filter) counts held at a time (kwg_search batches its queries)
+	uint8_t* d_stage[2] = {nullptr, nullptr};           // kwg_db_upload_columns: pieces of a file on their way into the slab
+	size_t stage_cap[2] = {0, 0};
+	int stage_next = 0;
 	KernelTimers timers;
 };
 
@@ -449,6 +452,7 @@ void kwg_db_unload(kwg_db_t* db)
 	cudaSetDevice(db->device);
 	if (db->stream) cudaStreamSynchronize(db->stream);
 	if (db->owns_slab) cudaFree(db->slab);
+	cudaFree(db->d_stage[0]); cudaFree(db->d_stage[1]);
 	cudaFree(db->d_bases); cudaFree(db->d_offsets); cudaFree(db->d_table); cudaFree(db->d_kmers); cudaFree(db->d_rows);
 	cudaFree(db->d_nk); cudaFree(db->d_counts); cudaFree(db->d_hit_count); cudaFree(db->d_hit_base); cudaFree(db->d_hits);
 	cudaFree(db->d_hit_total);
@@ -489,7 +493,7 @@ int kwg_db_alloc(kwg_db_t** out, int device, uint32_t kmer_len, uint32_t num_has
 	return KWG_OK;
 }
 
-int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
+int kwg_db_upload_rows_async(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
 {
 	if (!db || !rows) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
 	if (!db->owns_slab || db->n_filters_total == 0) return fail(KWG_ERR_STATE, "handle was not created by kwg_db_alloc/kwg_db_load");
@@ -499,9 +503,21 @@ int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const 
 	if (rc) return rc;
 	const uint64_t src_pitch = ceil_div(db->n_filters_total, 8);
 	const uint64_t width = ceil_div(db->n_filters, 8);
-	KWG_CUDA(cudaMemcpy2DAsync(db->slab + row_begin * db->row_pitch, db->row_pitch, rows + db->col_begin / 8, src_pitch, width, n_rows,
-		cudaMemcpyHostToDevice, db->stream));
-	KWG_CUDA(cudaStreamSynchronize(db->stream));   // the caller may reuse `rows`
+	if (src_pitch == width && width == db->row_pitch) {
+		// the file's rows are the slab's rows: one flat copy at the full PCIe rate
+		KWG_CUDA(cudaMemcpyAsync(db->slab + row_begin * db->row_pitch, rows, (size_t)(n_rows * width), cudaMemcpyHostToDevice, db->stream));
+	} else {
+		KWG_CUDA(cudaMemcpy2DAsync(db->slab + row_begin * db->row_pitch, db->row_pitch, rows + db->col_begin / 8, src_pitch, width, n_rows,
+			cudaMemcpyHostToDevice, db->stream));
+	}
+	return KWG_OK;
+}
+
+int kwg_db_upload_rows(kwg_db_t* db, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
+{
+	int rc = kwg_db_upload_rows_async(db, row_begin, n_rows, rows);
+	if (rc) return rc;
+	if (n_rows) KWG_CUDA(cudaStreamSynchronize(db->stream));   // the caller may reuse `rows`
 	return KWG_OK;
 }
 
@@ -529,7 +545,7 @@ place_columns_kernel(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32
 	if (bits) atomicOr(slab + row * slab_pitch_words + w, bits);
 }
 
-int kwg_db_upload_columns(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
+int kwg_db_upload_columns_async(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
 {
 	if (!db || !rows) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
 	if (!db->owns_slab || db->n_filters_total == 0) return fail(KWG_ERR_STATE, "handle was not created by kwg_db_alloc");
@@ -539,23 +555,35 @@ int kwg_db_upload_columns(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uin
 	int rc = select_device(db->device);
 	if (rc) return rc;
 	const uint64_t src_pitch = ceil_div(n_cols, 8);
+	// the piece crosses PCIe as ONE flat copy (a pitched host-to-device copy of 256-byte rows runs far below the link
+	// rate), then it is laid into its columns at HBM speed: a pitched device copy for whole bytes, else bits OR-ed into
+	// place (the slab starts out all zero).  Two staging buffers alternate so that a piece can travel while the one
+	// before it is still being placed.
+	const size_t bytes = (size_t)(n_rows * src_pitch);
+	const int sb = db->stage_next;
+	db->stage_next ^= 1;
+	rc = grow_db((void**)&db->d_stage[sb], &db->stage_cap[sb], bytes);
+	if (rc) return rc;
+	KWG_CUDA(cudaMemcpyAsync(db->d_stage[sb], rows, bytes, cudaMemcpyHostToDevice, db->stream));
 	if (col_begin % 8 == 0 && n_cols % 8 == 0) {
-		// whole bytes: a pitched copy straight into the rows
-		KWG_CUDA(cudaMemcpy2DAsync(db->slab + row_begin * db->row_pitch + col_begin / 8, db->row_pitch, rows, src_pitch, src_pitch, n_rows,
-			cudaMemcpyHostToDevice, db->stream));
+		KWG_CUDA(cudaMemcpy2DAsync(db->slab + row_begin * db->row_pitch + col_begin / 8, db->row_pitch, db->d_stage[sb], src_pitch, src_pitch, n_rows,
+			cudaMemcpyDeviceToDevice, db->stream));
 	} else {
-		// any bit offset: stage the piece, then OR its bits into place (the slab starts out all zero)
-		rc = grow_db((void**)&db->d_bases, &db->bases_cap, (size_t)(n_rows * src_pitch));
-		if (rc) return rc;
-		KWG_CUDA(cudaMemcpyAsync(db->d_bases, rows, (size_t)(n_rows * src_pitch), cudaMemcpyHostToDevice, db->stream));
 		const uint32_t w0 = col_begin / 32, n_words = (col_begin + n_cols - 1) / 32 - w0 + 1;
 		const uint64_t total = n_rows * n_words;
 		if (ceil_div(total, 256) > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "piece too large: upload fewer rows per call");
-		place_columns_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, db->stream>>>(reinterpret_cast<const uint8_t*>(db->d_bases), src_pitch, n_cols,
+		place_columns_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, db->stream>>>(db->d_stage[sb], src_pitch, n_cols,
 			col_begin, n_rows, reinterpret_cast<uint32_t*>(db->slab + row_begin * db->row_pitch), db->row_pitch / 4, w0, n_words);
 		KWG_LAUNCHED();
 	}
-	KWG_CUDA(cudaStreamSynchronize(db->stream));   // the caller may reuse `rows`
+	return KWG_OK;
+}
+
+int kwg_db_upload_columns(kwg_db_t* db, uint32_t col_begin, uint32_t n_cols, uint64_t row_begin, uint64_t n_rows, const uint8_t* rows)
+{
+	int rc = kwg_db_upload_columns_async(db, col_begin, n_cols, row_begin, n_rows, rows);
+	if (rc) return rc;
+	if (n_rows) KWG_CUDA(cudaStreamSynchronize(db->stream));   // the caller may reuse `rows`
 	return KWG_OK;
 }
 

@@ -39,6 +39,11 @@ void kwh_accession_to_str(uint64_t acc, char* out, size_t cap)
 	out[cap - 1] = 0;
 }
 
+int kwh_pack_2na(uint8_t* packed, uint8_t* mask, uint64_t cursor, const char* bases, uint64_t n)
+{
+	return pack_2na(packed, mask, cursor, bases, (size_t)n) ? 1 : 0;
+}
+
 // make_bloom_filter() on a reads file; results through plain out-parameters
 int kwh_make_bloom_file(const char* accession, const char* reads_path, uint64_t num_bp, const char* bloom_dir, uint32_t kmer_len,
 	uint32_t min_kmer_count, float p, uint32_t min_log2, uint32_t max_log2, int device,
@@ -96,6 +101,27 @@ int kwh_build_db(const char* filename, uint32_t kmer_len, uint32_t log2_len, uin
 	}
 	set_build_db_device(device);
 	return build_db(filename, param, files) ? 1 : 0;
+}
+
+// merge_database_files(); returns the remaining-capacity filter count (>= 0) or -1 on error
+long kwh_merge_db(const char* file_1, const char* file_2, uint64_t max_num_filters, int device, char* error, size_t error_cap)
+{
+	try {
+		const size_t max_f = max_num_filters ? (size_t)max_num_filters : 0;
+		size_t m = max_f;
+		if (!m) {
+			std::ifstream f(file_1, std::ios::binary);
+			DBFileHeader h;
+			binary_read(f, h);
+			m = max_filters_per_database_file(h.log_2_filter_len);
+		}
+		return (long)merge_database_files(file_1, file_2, m, device).first;
+	}
+	catch (const char* e) {
+		if (error && error_cap) { std::strncpy(error, e, error_cap - 1); error[error_cap - 1] = 0; }
+		return -1;
+	}
+	catch (...) { return -1; }
 }
 
 } // extern "C"

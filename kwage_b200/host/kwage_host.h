@@ -23,6 +23,7 @@
 #include <iostream>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/kwage_cuda.h"
@@ -174,6 +175,9 @@ ReadSource* open_read_collection(const std::string& accession_or_path);
 uint64_t number_of_bases(const std::string& accession);
 void set_number_of_bases_hook(uint64_t (*hook)(const std::string&));
 
+// 2-bit packing of a fragment into a batch for kwg_bloom_add_packed (NCBI 2na + not-a-base mask); see stages.cpp
+bool pack_2na(uint8_t* packed, uint8_t* mask, uint64_t cursor, const char* bases, size_t n);
+
 // ---- the three stages
 unsigned char make_bloom_filter(const SraAccession& acc, const FilterInfo& info, BloomParam& param, BloomProgress& progress,
 	const std::string& bloom_dir, const MaestroOptions& opt, bool force_unaligned = false);
@@ -182,6 +186,10 @@ unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAcc
 
 bool build_db(const std::string& filename, const BloomParam& param, const std::deque<std::string>& bloom_files);
 void set_build_db_device(int device);
+
+// merge_db (reference merge_db.cpp:278-820): append file_2's filters to file_1's columns, overflow becomes the new file_2
+std::pair<size_t, std::string> merge_database_files(const std::string& file_1, const std::string& file_2, const size_t& max_num_filters, int device = 0);
+size_t max_filters_per_database_file(uint32_t log_2_filter_len);   // merge_db.cpp:88-100
 
 struct MatchResult {                     // reference output.h:9-33
 	unsigned int num_kmers_found, num_query_kmer;
@@ -215,7 +223,7 @@ private:
 	SubjectDatabase(const SubjectDatabase&);
 	SubjectDatabase& operator=(const SubjectDatabase&);
 	void open_files(const std::vector<std::string>& filenames, int device);
-	struct Part { std::ifstream* fin; DBFileHeader hdr; uint32_t col_begin; };
+	struct Part { std::ifstream* fin; DBFileHeader hdr; uint32_t col_begin; uint64_t slices_start; };
 	std::vector<Part> parts;     // one per file, in column order
 	DBFileHeader hdr;
 	kwg_db_t* db;

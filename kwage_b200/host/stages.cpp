@@ -4,11 +4,17 @@
 #include "kwage_host.h"
 
 #include <algorithm>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iomanip>
+#include <mutex>
 #include <sstream>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 #include <zlib.h>
 
 namespace kwage {
@@ -123,9 +129,197 @@ uint64_t number_of_bases(const std::string& accession)
 
 void set_build_db_device(int device) { g_build_db_device = device; }
 
+// page-locked when the CUDA library can provide it, plain memory otherwise (the calls accept any host pointer)
+class PinnedBuffer {
+public:
+	explicit PinnedBuffer(size_t n) : p(NULL), pinned(true)
+	{
+		p = static_cast<uint8_t*>(kwg_host_alloc(n ? n : 1));
+		if (!p) { pinned = false; p = static_cast<uint8_t*>(malloc(n ? n : 1)); }
+		if (!p) throw __FILE__ ":PinnedBuffer: Unable to allocate a staging buffer";
+	}
+	~PinnedBuffer() { if (pinned) kwg_host_free(p); else free(p); }
+	uint8_t* data() { return p; }
+private:
+	PinnedBuffer(const PinnedBuffer&);
+	PinnedBuffer& operator=(const PinnedBuffer&);
+	uint8_t* p;
+	bool pinned;
+};
+
+// ================================================================ read ingestion
+// 2-bit packing on the parser thread: the bases of a fragment are appended to the batch at base position `cursor` in
+// the format of kwg_bloom_add_packed (NCBI 2na: four bases per byte, the first in bits 7..6; A=0 C=1 G=2 T=3, lower case
+// folded, word.h:19,80-101) and every other byte sets its bit in the not-a-base mask (LSB first), which breaks the
+// k-mers there exactly like word.h:98-100.  `mask` must be zero where nothing has been written yet; returns true if the
+// fragment held such a byte.
+namespace {
+struct PackTable {
+	uint8_t code[256];
+	PackTable()
+	{
+		std::memset(code, 0x80, sizeof(code));
+		code[(unsigned char)'A'] = code[(unsigned char)'a'] = 0; code[(unsigned char)'C'] = code[(unsigned char)'c'] = 1;
+		code[(unsigned char)'G'] = code[(unsigned char)'g'] = 2; code[(unsigned char)'T'] = code[(unsigned char)'t'] = 3;
+	}
+};
+const PackTable g_pack;
+}
+
+bool pack_2na(uint8_t* packed, uint8_t* mask, uint64_t cursor, const char* bases, size_t n)
+{
+	const unsigned char* s = reinterpret_cast<const unsigned char*>(bases);
+	unsigned any = 0;
+	size_t i = 0;
+	uint64_t pos = cursor;
+	// up to the next byte boundary of the 2na stream (the byte already holds the previous fragment's last bases)
+	for (; i < n && (pos & 3u); ++i, ++pos) {
+		const unsigned c = g_pack.code[s[i]];
+		if (c & 0x80u) { mask[pos >> 3] |= (uint8_t)(1u << (pos & 7u)); any = 1; }
+		packed[pos >> 2] |= (uint8_t)((c & 3u) << (6 - 2 * (pos & 3u)));
+	}
+	for (; i + 4 <= n; i += 4, pos += 4) {
+		const unsigned c0 = g_pack.code[s[i]], c1 = g_pack.code[s[i + 1]], c2 = g_pack.code[s[i + 2]], c3 = g_pack.code[s[i + 3]];
+		packed[pos >> 2] = (uint8_t)(((c0 & 3u) << 6) | ((c1 & 3u) << 4) | ((c2 & 3u) << 2) | (c3 & 3u));
+		if ((c0 | c1 | c2 | c3) & 0x80u) {
+			const unsigned m = (c0 >> 7) | ((c1 >> 7) << 1) | ((c2 >> 7) << 2) | ((c3 >> 7) << 3);
+			mask[pos >> 3] |= (uint8_t)(m << (pos & 7u));          // (pos % 4 == 0: the four flags stay inside the byte)
+			any = 1;
+		}
+	}
+	if (i < n) {
+		packed[pos >> 2] = 0;
+		for (; i < n; ++i, ++pos) {
+			const unsigned c = g_pack.code[s[i]];
+			if (c & 0x80u) { mask[pos >> 3] |= (uint8_t)(1u << (pos & 7u)); any = 1; }
+			packed[pos >> 2] |= (uint8_t)((c & 3u) << (6 - 2 * (pos & 3u)));
+		}
+	}
+	return any != 0;
+}
+
+// The reference's fragment loop (make_bloom.cpp:194-300) reads one fragment, counts its k-mers, reads the next.  Here a
+// parser thread reads and packs batch n + 1 while the device works on batch n: a ring of page-locked batches, the
+// parser fills, the caller's thread feeds them to kwg_bloom_add_packed in stream order.
+namespace {
+
+struct ReadBatch {
+	PinnedBuffer packed, mask;
+	std::vector<uint64_t> offsets;
+	uint64_t n_bases, n_fragments;           // (a fragment longer than a batch arrives as several reads)
+	bool any_bad, last;
+	std::string error;                       // what the parser threw, rethrown on the feeding thread
+	explicit ReadBatch(size_t cap_bases) : packed(cap_bases / 4 + 64), mask(cap_bases / 8 + 64), n_bases(0), n_fragments(0), any_bad(false), last(false) {}
+};
+
+class BatchPipeline {
+public:
+	BatchPipeline(ReadSource& src, size_t batch_bases, size_t n_batches, size_t kmer_len) : overlap(kmer_len ? kmer_len - 1 : 0), reads(src), cap(batch_bases), stop(false)
+	{
+		for (size_t i = 0; i < n_batches; ++i) { pool.push_back(new ReadBatch(cap + (1u << 16))); free_q.push_back(pool.back()); }
+		worker = std::thread(&BatchPipeline::run, this);
+	}
+	~BatchPipeline()
+	{
+		{ std::lock_guard<std::mutex> l(mu); stop = true; }
+		cv.notify_all();
+		if (worker.joinable()) worker.join();
+		for (size_t i = 0; i < pool.size(); ++i) delete pool[i];
+	}
+	ReadBatch* next()                        // blocks until the parser has a batch; the last one has last == true
+	{
+		std::unique_lock<std::mutex> l(mu);
+		cv.wait(l, [this] { return !full_q.empty(); });
+		ReadBatch* b = full_q.front();
+		full_q.pop_front();
+		return b;
+	}
+	void release(ReadBatch* b)
+	{
+		{ std::lock_guard<std::mutex> l(mu); free_q.push_back(b); }
+		cv.notify_all();
+	}
+private:
+	void run()
+	{
+		std::string fragment;
+		bool pending = false;                    // `fragment` (from pending_off on) still has to go out
+		size_t pending_off = 0;
+		bool more = true;
+		while (more || pending) {
+			ReadBatch* b = NULL;
+			{
+				std::unique_lock<std::mutex> l(mu);
+				cv.wait(l, [this] { return stop || !free_q.empty(); });
+				if (stop) return;
+				b = free_q.front();
+				free_q.pop_front();
+			}
+			b->offsets.assign(1, 0);
+			b->n_bases = 0; b->n_fragments = 0; b->any_bad = false; b->last = false; b->error.clear();
+			std::memset(b->mask.data(), 0, cap / 8 + 64);
+			try {
+				while (b->n_bases < cap) {
+					if (!pending) {
+						more = reads.next_fragment(fragment);
+						if (!more) break;
+						pending = true;
+						pending_off = 0;
+					}
+					const size_t remaining = fragment.size() - pending_off, room = cap - b->n_bases;
+					size_t take = remaining;
+					if (remaining > room) {
+						if (b->n_bases) break;           // goes out with the next batch
+						// a fragment longer than a whole batch: pieces that overlap by k - 1 bases hold every one of its
+						// k-mers exactly once and in order (a window lies in the first piece that contains it whole)
+						take = cap;
+					}
+					append(b, fragment.data() + pending_off, take);
+					if (take == remaining) { pending = false; ++b->n_fragments; }
+					else pending_off += take - (overlap < take ? overlap : 0);
+				}
+			}
+			catch (const char* e) { b->error = e; more = false; pending = false; }
+			catch (const std::exception& e) { b->error = e.what(); more = false; pending = false; }
+			catch (...) { b->error = "unknown error while reading"; more = false; pending = false; }
+			b->last = !more && !pending;
+			{ std::lock_guard<std::mutex> l(mu); full_q.push_back(b); }
+			cv.notify_all();
+		}
+	}
+	void append(ReadBatch* b, const char* bases, size_t n)
+	{
+		if ((b->n_bases & 3u) == 0) b->packed.data()[b->n_bases >> 2] = 0;
+		if (n) b->any_bad |= pack_2na(b->packed.data(), b->mask.data(), b->n_bases, bases, n);
+		b->n_bases += n;
+		b->offsets.push_back(b->n_bases);
+	}
+	size_t overlap;                              // kmer_len - 1
+	ReadSource& reads;
+	size_t cap;
+	std::vector<ReadBatch*> pool;
+	std::deque<ReadBatch*> free_q, full_q;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::thread worker;
+	bool stop;
+};
+
+} // namespace
+
+// bases per batch: 64 Mi (16 MiB packed); KWAGE_BATCH_BASES overrides it (tests drive the batch boundaries with it)
+static size_t batch_bases()
+{
+	if (const char* e = std::getenv("KWAGE_BATCH_BASES")) {
+		const size_t v = (size_t)std::strtoull(e, NULL, 10);
+		if (v >= 64) return v;
+	}
+	return size_t(64) << 20;
+}
+
 // ================================================================ construction
-// Mirrors make_bloom_filter() (reference make_bloom.cpp:76-504).  Fragments are batched so that one
-// libkwage_cuda call carries ~64 MiB; stream order is preserved (it matters for the counting filter).
+// Mirrors make_bloom_filter() (reference make_bloom.cpp:76-504).  Fragments are batched so that one libkwage_cuda call
+// carries ~64 Mi bases (16 MiB packed); stream order is preserved (it matters for the counting filter).
 unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAccession& acc, const FilterInfo& info, BloomParam& param,
 	BloomProgress& progress, const std::string& bloom_dir, const MaestroOptions& opt)
 {
@@ -142,33 +336,37 @@ unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAcc
 			(uint32_t)progress.log_2_counting_filter_len, opt.max_log_2_filter_len), __FILE__ ":make_bloom_filter: kwg_bloom_create failed");
 		progress.valid_read_collection = true;
 
-		const size_t batch_bytes = size_t(64) << 20;
-		std::string flat, fragment;
-		std::vector<uint64_t> offsets(1, 0);
-		flat.reserve(batch_bytes + (1 << 20));
-		bool more = true;
-		while (more) {
-			more = reads.next_fragment(fragment);
-			if (more) {
-				progress.num_bp += fragment.size();
-				flat += fragment;
-				offsets.push_back(flat.size());
-				++progress.curr_read;
-				++progress.num_read;
-			}
-			if ((!more && offsets.size() > 1) || flat.size() >= batch_bytes) {
-				cuda_check(kwg_bloom_add_reads(builder, flat.data(), offsets.data(), offsets.size() - 1),
-					__FILE__ ":make_bloom_filter: kwg_bloom_add_reads failed");
-				uint64_t n = 0;
-				cuda_check(kwg_bloom_num_valid(builder, &n), __FILE__ ":make_bloom_filter: kwg_bloom_num_valid failed");
-				progress.num_kmer = n;
-				flat.clear();
-				offsets.assign(1, 0);
-				// the reference tests this after every fragment (make_bloom.cpp:208,246,288); per batch
-				// the outcome (STATUS_BLOOM_INVALID) is the same, only num_kmer at the abort differs
-				if (max_num_kmer < progress.num_kmer) {
+		{
+			BatchPipeline pipe(reads, batch_bases(), 3, opt.kmer_len);
+			bool last = false;
+			while (!last) {
+				ReadBatch* rb = pipe.next();
+				if (!rb->error.empty()) {
+					progress.error = rb->error;
+					pipe.release(rb);
 					kwg_bloom_destroy(builder);
-					return STATUS_BLOOM_INVALID;
+					return STATUS_BLOOM_FAIL;
+				}
+				last = rb->last;
+				const size_t n_reads = rb->offsets.size() - 1;
+				progress.num_bp += rb->n_bases;
+				progress.curr_read += rb->n_fragments;
+				progress.num_read += rb->n_fragments;
+				if (n_reads) {
+					const int rc = kwg_bloom_add_packed(builder, rb->packed.data(), rb->any_bad ? rb->mask.data() : NULL, rb->offsets.data(), n_reads);
+					pipe.release(rb);                 // (the call has copied the batch: the parser may refill it)
+					cuda_check(rc, __FILE__ ":make_bloom_filter: kwg_bloom_add_packed failed");
+					uint64_t n = 0;
+					cuda_check(kwg_bloom_num_valid(builder, &n), __FILE__ ":make_bloom_filter: kwg_bloom_num_valid failed");
+					progress.num_kmer = n;
+					// the reference tests this after every fragment (make_bloom.cpp:208,246,288); per batch
+					// the outcome (STATUS_BLOOM_INVALID) is the same, only num_kmer at the abort differs
+					if (max_num_kmer < progress.num_kmer) {
+						kwg_bloom_destroy(builder);
+						return STATUS_BLOOM_INVALID;
+					}
+				} else {
+					pipe.release(rb);
 				}
 			}
 		}
@@ -235,24 +433,6 @@ unsigned char make_bloom_filter(const SraAccession& acc, const FilterInfo& info,
 		return STATUS_BLOOM_FAIL;
 	}
 }
-
-// page-locked when the CUDA library can provide it, plain memory otherwise (the calls accept any host pointer)
-class PinnedBuffer {
-public:
-	explicit PinnedBuffer(size_t n) : p(NULL), pinned(true)
-	{
-		p = static_cast<uint8_t*>(kwg_host_alloc(n ? n : 1));
-		if (!p) { pinned = false; p = static_cast<uint8_t*>(malloc(n ? n : 1)); }
-		if (!p) throw __FILE__ ":build_db: Unable to allocate a staging buffer";
-	}
-	~PinnedBuffer() { if (pinned) kwg_host_free(p); else free(p); }
-	uint8_t* data() { return p; }
-private:
-	PinnedBuffer(const PinnedBuffer&);
-	PinnedBuffer& operator=(const PinnedBuffer&);
-	uint8_t* p;
-	bool pinned;
-};
 
 // ================================================================ transposition
 // Mirrors build_db() (reference build_db.cpp:24-456): same validation, same chunking of the slice
@@ -361,6 +541,163 @@ static void read_db_header(std::ifstream& fin, DBFileHeader& h)
 	if (h.magic != KWAGE_MAGIC_NUMBER) throw __FILE__ ":main: Not a KWAGE database file";
 }
 
+// ================================================================ merging database files
+// Mirrors merge_database_files() (reference merge_db.cpp:278-820): file 2's filters are appended to file 1's columns; if
+// file 1 fills up (max_num_filters) the rest of file 2's columns become the new file 2.  Same checks, same temp files
+// and renames, same header / crc32 / FilterInfo layout; the per-slice bit moving (merge_db.cpp:533-566) is kwg_merge_slices.
+// Returns {filters in the file that can still take more, its name} like the reference ({0, ""} if none).
+std::pair<size_t, std::string> merge_database_files(const std::string& file_1, const std::string& file_2, const size_t& max_num_filters, int device)
+{
+	const std::string tmp_suffix = ".tmp";
+	std::pair<size_t, std::string> ret(size_t(0), "");
+	std::ifstream fin_1(file_1.c_str(), std::ios::binary);
+	if (!fin_1) throw __FILE__ ":merge_database_files: Unable to open database file 1";
+	std::ifstream fin_2(file_2.c_str(), std::ios::binary);
+	if (!fin_2) throw __FILE__ ":merge_database_files: Unable to open database file 2";
+	DBFileHeader src_1, src_2;
+	binary_read(fin_1, src_1);
+	if (!fin_1) throw __FILE__ ":merge_database_files: Error reading header 1";
+	binary_read(fin_2, src_2);
+	if (!fin_2) throw __FILE__ ":merge_database_files: Error reading header 2";
+	if (src_1.log_2_filter_len != src_2.log_2_filter_len || src_1.num_hash != src_2.num_hash || src_1.kmer_len != src_2.kmer_len ||
+	    src_1.hash_func != src_2.hash_func)
+		throw __FILE__ ":merge_database_files: Incompatible database files";
+	if (src_1.compression != 0 || src_2.compression != 0)
+		throw __FILE__ ":merge_database_files: Compressed database files are not currently supported";
+	if (src_1.num_filter >= max_num_filters) throw __FILE__ ":merge_database_files: Database file 1 has more than expected filters";
+	if (src_2.num_filter >= max_num_filters) throw __FILE__ ":merge_database_files: Database file 2 has more than expected filters";
+	if (src_1.num_filter == 0 || src_2.num_filter == 0) throw __FILE__ ":merge_database_files: A database file without filters";
+
+	const bool has_remainder = (size_t(src_1.num_filter) + src_2.num_filter) > max_num_filters;
+	const std::string dst_file_1 = file_1 + tmp_suffix;
+	const std::string dst_file_2 = has_remainder ? file_2 + tmp_suffix : "";
+	if (file_exists(dst_file_1)) throw __FILE__ ":merge_database_files: Temp database file 1 already exists";
+	if (has_remainder && file_exists(dst_file_2)) throw __FILE__ ":merge_database_files: Temp database file 2 already exists";
+	std::ofstream fout_1(dst_file_1.c_str(), std::ios::binary), fout_2;
+	if (!fout_1) throw __FILE__ ":merge_database_files: Unable to open new_file_1";
+	if (has_remainder) {
+		fout_2.open(dst_file_2.c_str(), std::ios::binary);
+		if (!fout_2) throw __FILE__ ":merge_database_files: Unable to open new_file_2";
+	}
+
+	DBFileHeader dst_1 = src_1, dst_2 = src_2;
+	dst_1.crc32 = dst_2.crc32 = 0;
+	dst_1.info_start = dst_2.info_start = 0;
+	if (has_remainder) {
+		dst_1.num_filter = (uint32_t)max_num_filters;
+		dst_2.num_filter = (uint32_t)((size_t(src_1.num_filter) + src_2.num_filter) - max_num_filters);
+		ret = std::make_pair(size_t(dst_2.num_filter), file_2);
+	}
+	else {
+		dst_1.num_filter = src_1.num_filter + src_2.num_filter;
+		dst_2.num_filter = 0;
+		if (dst_1.num_filter < max_num_filters) ret = std::make_pair(size_t(dst_1.num_filter), file_1);
+	}
+	binary_write(fout_1, dst_1);
+	if (!fout_1) throw __FILE__ ":merge_database_files: Error writing database file 1 header placeholder";
+	if (has_remainder) {
+		binary_write(fout_2, dst_2);
+		if (!fout_2) throw __FILE__ ":merge_database_files: Error writing database file 1 header placeholder";
+	}
+
+	const size_t num_bitslice = src_1.filter_len();
+	const size_t bps_src_1 = src_1.num_filter / 8 + ((src_1.num_filter % 8) ? 1 : 0), bps_src_2 = src_2.num_filter / 8 + ((src_2.num_filter % 8) ? 1 : 0);
+	const size_t bps_dst_1 = dst_1.num_filter / 8 + ((dst_1.num_filter % 8) ? 1 : 0), bps_dst_2 = dst_2.num_filter / 8 + ((dst_2.num_filter % 8) ? 1 : 0);
+	// chunks of slices sized for ~32 MiB per buffer (the reference moves 1024 slices at a time)
+	const size_t per_chunk = std::max<size_t>(1024, (size_t(32) << 20) / std::max(bps_dst_1, size_t(1)));
+	{
+		PinnedBuffer b_src_1(per_chunk * bps_src_1), b_src_2(per_chunk * bps_src_2), b_dst_1(per_chunk * bps_dst_1), b_dst_2(per_chunk * bps_dst_2 + 1);
+		uint32_t crc_src_1 = 0, crc_src_2 = 0;
+		for (size_t i = 0; i < num_bitslice; i += per_chunk) {
+			const size_t n = std::min(per_chunk, num_bitslice - i);
+			fin_1.read(reinterpret_cast<char*>(b_src_1.data()), (std::streamsize)(n * bps_src_1));
+			if (!fin_1) throw __FILE__ ":merge_database_files: Error reading bitslices from source file 1";
+			fin_2.read(reinterpret_cast<char*>(b_src_2.data()), (std::streamsize)(n * bps_src_2));
+			if (!fin_2) throw __FILE__ ":merge_database_files: Error reading bitslices from source file 2";
+			crc_src_1 = crc32_bytes(crc_src_1, b_src_1.data(), n * bps_src_1);
+			crc_src_2 = crc32_bytes(crc_src_2, b_src_2.data(), n * bps_src_2);
+			cuda_check(kwg_merge_slices(device, b_src_1.data(), src_1.num_filter, b_src_2.data(), src_2.num_filter, n, dst_1.num_filter,
+				b_dst_1.data(), has_remainder ? b_dst_2.data() : NULL), __FILE__ ":merge_database_files: kwg_merge_slices failed");
+			fout_1.write(reinterpret_cast<const char*>(b_dst_1.data()), (std::streamsize)(n * bps_dst_1));
+			if (!fout_1) throw __FILE__ ":merge_database_files: Error writing bitslices to destination file 1";
+			dst_1.crc32 = crc32_bytes(dst_1.crc32, b_dst_1.data(), n * bps_dst_1);
+			if (has_remainder) {
+				fout_2.write(reinterpret_cast<const char*>(b_dst_2.data()), (std::streamsize)(n * bps_dst_2));
+				if (!fout_2) throw __FILE__ ":merge_database_files: Error writing bitslices to destination file 2";
+				dst_2.crc32 = crc32_bytes(dst_2.crc32, b_dst_2.data(), n * bps_dst_2);
+			}
+		}
+		if (crc_src_1 != src_1.crc32) throw __FILE__ ":merge_database_files: Invalid CRC32 value for source database file 1";
+		if (crc_src_2 != src_2.crc32) throw __FILE__ ":merge_database_files: Invalid CRC32 value for source database file 2";
+	}
+
+	// metadata: location tables (placeholders first), then the FilterInfo records in column order
+	dst_1.info_start = (uint64_t)fout_1.tellp();
+	if (has_remainder) dst_2.info_start = (uint64_t)fout_2.tellp();
+	std::vector<uint64_t> loc_1(dst_1.num_filter, 0), loc_2(dst_2.num_filter, 0);
+	fout_1.write(reinterpret_cast<const char*>(loc_1.data()), (std::streamsize)(loc_1.size() * sizeof(uint64_t)));
+	if (!fout_1) throw __FILE__ ":merge_database_files: Error writing dummy metadata location buffer to destination databaes file 1";
+	if (has_remainder) {
+		fout_2.write(reinterpret_cast<const char*>(loc_2.data()), (std::streamsize)(loc_2.size() * sizeof(uint64_t)));
+		if (!fout_2) throw __FILE__ ":merge_database_files: Error writing dummy metadata location buffer to destination databaes file 2";
+	}
+	fin_1.seekg((std::streamoff)((uint64_t)fin_1.tellg() + sizeof(uint64_t) * src_1.num_filter));
+	fin_2.seekg((std::streamoff)((uint64_t)fin_2.tellg() + sizeof(uint64_t) * src_2.num_filter));
+	const size_t take = dst_1.num_filter - src_1.num_filter;
+	for (size_t i = 0; i < src_1.num_filter; ++i) {
+		FilterInfo info;
+		binary_read(fin_1, info);
+		loc_1[i] = (uint64_t)fout_1.tellp();
+		binary_write(fout_1, info);
+		if (!fout_1) throw __FILE__ ":merge_database_files: Error writing Bloom filter info to destination file 1";
+	}
+	for (size_t i = 0; i < take; ++i) {
+		FilterInfo info;
+		binary_read(fin_2, info);
+		loc_1[src_1.num_filter + i] = (uint64_t)fout_1.tellp();
+		binary_write(fout_1, info);
+		if (!fout_1) throw __FILE__ ":merge_database_files: Error writing Bloom filter info to destination file 1 (b)";
+	}
+	for (size_t i = 0; i < dst_2.num_filter && has_remainder; ++i) {
+		FilterInfo info;
+		binary_read(fin_2, info);
+		loc_2[i] = (uint64_t)fout_2.tellp();
+		binary_write(fout_2, info);
+		if (!fout_2) throw __FILE__ ":merge_database_files: Error writing Bloom filter info to destination file 2";
+	}
+	fout_1.seekp(0);
+	binary_write(fout_1, dst_1);
+	if (!fout_1) throw __FILE__ ":merge_database_files: Error writing database file 1 header (final)";
+	fout_1.seekp((std::streamoff)dst_1.info_start);
+	fout_1.write(reinterpret_cast<const char*>(loc_1.data()), (std::streamsize)(loc_1.size() * sizeof(uint64_t)));
+	if (!fout_1) throw __FILE__ ":merge_database_files: Error writing metadata location buffer to destination file 1";
+	fout_1.close();
+	if (has_remainder) {
+		fout_2.seekp(0);
+		binary_write(fout_2, dst_2);
+		if (!fout_2) throw __FILE__ ":merge_database_files: Error writing database file 2 header (final)";
+		fout_2.seekp((std::streamoff)dst_2.info_start);
+		fout_2.write(reinterpret_cast<const char*>(loc_2.data()), (std::streamsize)(loc_2.size() * sizeof(uint64_t)));
+		if (!fout_2) throw __FILE__ ":merge_database_files: Error writing metadata location buffer to destination file 2";
+		fout_2.close();
+	}
+	fin_1.close();
+	fin_2.close();
+	if (std::rename(dst_file_1.c_str(), file_1.c_str()) != 0) throw __FILE__ ":merge_database_files: Error renaming database file 1";
+	if (has_remainder) {
+		if (std::rename(dst_file_2.c_str(), file_2.c_str()) != 0) throw __FILE__ ":merge_database_files: Error renaming database file 2";
+	}
+	else if (::unlink(file_2.c_str()) != 0) throw __FILE__ ":merge_database_files: Error removing database file 2";
+	return ret;
+}
+
+// filters per database file for a filter length (merge_db.cpp:88-100, options.h:137-138): 2048, fewer when that would pass 64 GiB
+size_t max_filters_per_database_file(uint32_t log_2_filter_len)
+{
+	const uint64_t num_bloom = (64ull * 8ull * (1ull << 30)) >> log_2_filter_len;
+	return (size_t)std::min<uint64_t>(2048, num_bloom);
+}
+
 SubjectDatabase::SubjectDatabase(const std::string& filename, int device) : db(NULL)
 {
 	open_files(std::vector<std::string>(1, filename), device);
@@ -393,6 +730,32 @@ uint64_t SubjectDatabase::slab_bytes(const std::string& filename)
 	return (uint64_t(1) << h.log_2_filter_len) * (h.num_filter / 8 + 1);
 }
 
+// n bytes of a file from `offset` into dst, by up to four threads (pread on one descriptor)
+static void read_slices(const std::string& path, uint64_t offset, uint8_t* dst, size_t n)
+{
+	const int fd = ::open(path.c_str(), O_RDONLY);
+	if (fd < 0) throw __FILE__ ":search: Error reading slice from file (open)";
+	const size_t n_thr = n >= (size_t(8) << 20) ? 4 : 1;
+	const size_t per = (n + n_thr - 1) / n_thr;
+	std::vector<std::thread> thr;
+	std::vector<int> ok(n_thr, 1);
+	for (size_t t = 0; t < n_thr; ++t) {
+		const size_t a = t * per, z = std::min(n, a + per);
+		if (a >= z) continue;
+		thr.push_back(std::thread([fd, offset, dst, a, z, t, &ok]() {
+			size_t done = a;
+			while (done < z) {
+				const ssize_t got = ::pread(fd, dst + done, z - done, (off_t)(offset + done));
+				if (got <= 0) { ok[t] = 0; return; }
+				done += (size_t)got;
+			}
+		}));
+	}
+	for (size_t t = 0; t < thr.size(); ++t) thr[t].join();
+	::close(fd);
+	for (size_t t = 0; t < n_thr; ++t) if (!ok[t]) throw __FILE__ ":search: Error reading slice from file (1)";
+}
+
 void SubjectDatabase::open_files(const std::vector<std::string>& filenames, int device)
 {
 	try {
@@ -403,6 +766,7 @@ void SubjectDatabase::open_files(const std::vector<std::string>& filenames, int 
 			parts.push_back(p);
 			Part& q = parts.back();
 			read_db_header(*q.fin, q.hdr);
+			q.slices_start = (uint64_t)q.fin->tellg();
 			q.col_begin = (uint32_t)total;
 			total += q.hdr.num_filter;
 			const DBFileHeader& h0 = parts[0].hdr;
@@ -415,22 +779,34 @@ void SubjectDatabase::open_files(const std::vector<std::string>& filenames, int 
 		hdr.num_filter = (uint32_t)total;
 		cuda_check(kwg_db_alloc(&db, device, hdr.kmer_len, hdr.num_hash, hdr.log_2_filter_len, hdr.num_filter, 0, hdr.num_filter),
 			__FILE__ ":search: kwg_db_alloc failed");
-		// stream every file's slice region into its columns in bounded pieces (a region can exceed host memory)
+		// Stream every file's slice region into its columns: two page-locked buffers alternate, piece n + 1 is read from
+		// the file (by several threads: one thread copies out of the page cache at a fraction of the PCIe rate) while
+		// piece n travels to the device.  A region may exceed host memory.
 		const uint64_t n_rows = 1ULL << hdr.log_2_filter_len;
+		const size_t piece_bytes = size_t(64) << 20;
+		PinnedBuffer buf0(piece_bytes), buf1(piece_bytes);
+		uint8_t* bufs[2] = {buf0.data(), buf1.data()};
+		struct Piece { size_t part; uint64_t row, rows; };
+		std::vector<Piece> pieces;
 		for (size_t f = 0; f < parts.size(); ++f) {
-			Part& q = parts[f];
-			const size_t slice_size = q.hdr.num_filter / 8 + ((q.hdr.num_filter % 8) ? 1 : 0);
-			const uint64_t piece_rows = std::max<uint64_t>(1, (uint64_t(256) << 20) / std::max<size_t>(slice_size, 1));
-			std::vector<uint8_t> buf((size_t)(std::min(piece_rows, n_rows) * slice_size));
-			for (uint64_t r = 0; r < n_rows; r += piece_rows) {
-				const uint64_t rows = std::min(piece_rows, n_rows - r);
-				q.fin->read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(rows * slice_size));
-				if (!*q.fin) throw __FILE__ ":search: Error reading slice from file (1)";
-				const int rc = (parts.size() == 1) ? kwg_db_upload_rows(db, r, rows, buf.data())
-				                                   : kwg_db_upload_columns(db, q.col_begin, q.hdr.num_filter, r, rows, buf.data());
-				cuda_check(rc, __FILE__ ":search: kwg_db_upload failed");
-			}
+			const size_t slice_size = parts[f].hdr.num_filter / 8 + ((parts[f].hdr.num_filter % 8) ? 1 : 0);
+			const uint64_t piece_rows = std::max<uint64_t>(1, piece_bytes / std::max<size_t>(slice_size, 1));
+			if (slice_size > piece_bytes) throw __FILE__ ":search: A slice is larger than the load buffer";
+			for (uint64_t r = 0; r < n_rows; r += piece_rows) pieces.push_back(Piece{f, r, std::min(piece_rows, n_rows - r)});
 		}
+		for (size_t i = 0; i < pieces.size(); ++i) {
+			const Piece& pc = pieces[i];
+			Part& q = parts[pc.part];
+			const size_t slice_size = q.hdr.num_filter / 8 + ((q.hdr.num_filter % 8) ? 1 : 0);
+			uint8_t* buf = bufs[i & 1];
+			read_slices(filenames[pc.part], q.slices_start + pc.row * slice_size, buf, (size_t)(pc.rows * slice_size));
+			// (piece i - 1 travelled while piece i was read; its buffer is the next one to be filled)
+			if (i) cuda_check(kwg_db_sync(db), __FILE__ ":search: kwg_db_sync failed");
+			const int rc = (parts.size() == 1) ? kwg_db_upload_rows_async(db, pc.row, pc.rows, buf)
+			                                   : kwg_db_upload_columns_async(db, q.col_begin, q.hdr.num_filter, pc.row, pc.rows, buf);
+			cuda_check(rc, __FILE__ ":search: kwg_db_upload failed");
+		}
+		cuda_check(kwg_db_sync(db), __FILE__ ":search: kwg_db_sync failed");
 	}
 	catch (...) {
 		if (db) { kwg_db_unload(db); db = NULL; }

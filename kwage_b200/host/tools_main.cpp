@@ -4,9 +4,12 @@
 //   kwage_tools build_db -o <out.db> <a.bloom> <b.bloom> ...          (parameters come from the first file)
 // Options of make_bloom mirror maestro's (options.cpp:404-820): -k, --min-kmer-count, -p,
 // --len.min, --len.max, --bloom <dir>; plus --device and --num-bases (metadata override).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <map>
+#include <set>
 
 #include "kwage_host.h"
 
@@ -102,10 +105,63 @@ static int cmd_build_db(int argc, char** argv)
 	return ok ? EXIT_SUCCESS : EXIT_FAILURE;
 }
 
+// merge_db <a.db> <b.db> ...: the reference's merge_db main (merge_db.cpp:26-277).  Files that are not full are grouped by
+// Bloom parameters; within a group the two with the fewest filters are merged (the smaller into the larger) until at
+// most one partially filled file is left.
+static int cmd_merge_db(int argc, char** argv)
+{
+	int device = 0;
+	std::deque<std::string> inputs;
+	for (int i = 2; i < argc; ++i) {
+		const std::string a = argv[i];
+		if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
+		else inputs.push_back(a);
+	}
+	if (inputs.size() < 2) { std::cerr << "Please specify 2 or more database files to merge" << std::endl; return EXIT_SUCCESS; }
+	try {
+		struct Key {
+			uint32_t k, L, h; int func;
+			bool operator<(const Key& r) const { return std::make_pair(std::make_pair(k, L), std::make_pair(h, func)) < std::make_pair(std::make_pair(r.k, r.L), std::make_pair(r.h, r.func)); }
+		};
+		std::map<Key, std::deque<std::pair<size_t, std::string> > > groups;
+		std::set<std::string> seen;
+		for (size_t i = 0; i < inputs.size(); ++i) {
+			std::ifstream fin(inputs[i].c_str(), std::ios::binary);
+			if (!fin) { std::cerr << "Unable to open " << inputs[i] << " for reading" << std::endl; return EXIT_FAILURE; }
+			DBFileHeader h;
+			binary_read(fin, h);
+			if (!fin) { std::cerr << "Unable to read database header" << std::endl; return EXIT_FAILURE; }
+			if (max_filters_per_database_file(h.log_2_filter_len) <= h.num_filter) continue;      // full: not a merge candidate
+			if (!seen.insert(inputs[i]).second) { std::cerr << inputs[i] << " appears more than once in the input file list" << std::endl; return EXIT_FAILURE; }
+			const Key key = {h.kmer_len, h.log_2_filter_len, h.num_hash, h.hash_func};
+			groups[key].push_back(std::make_pair(size_t(h.num_filter), inputs[i]));
+		}
+		std::cerr << "Found " << groups.size() << " distinct Bloom parameter groups" << std::endl;
+		for (std::map<Key, std::deque<std::pair<size_t, std::string> > >::iterator g = groups.begin(); g != groups.end(); ++g) {
+			std::deque<std::pair<size_t, std::string> >& files = g->second;
+			std::sort(files.begin(), files.end());
+			const size_t max_f = max_filters_per_database_file(g->first.L);
+			while (files.size() > 1) {
+				const std::string file_small = files.front().second;
+				files.pop_front();
+				const std::string file_large = files.front().second;
+				files.pop_front();
+				std::cerr << "\tmerging:\n\t\t" << file_small << "\n\t\t" << file_large << std::endl;
+				const std::pair<size_t, std::string> rest = merge_database_files(file_large, file_small, max_f, device);
+				if (rest.first > 0) { files.push_back(rest); std::sort(files.begin(), files.end()); }
+			}
+		}
+	}
+	catch (const char* error) { std::cerr << "Caught the error " << error << std::endl; return EXIT_FAILURE; }
+	catch (...) { std::cerr << "Caught an unhandled error" << std::endl; return EXIT_FAILURE; }
+	return EXIT_SUCCESS;
+}
+
 int main(int argc, char** argv)
 {
+	if (argc >= 2 && std::strcmp(argv[1], "merge_db") == 0) return cmd_merge_db(argc, argv);
 	if (argc >= 2 && std::strcmp(argv[1], "make_bloom") == 0) return cmd_make_bloom(argc, argv);
 	if (argc >= 2 && std::strcmp(argv[1], "build_db") == 0) return cmd_build_db(argc, argv);
-	std::cerr << "kwage_tools make_bloom|build_db ..." << std::endl;
+	std::cerr << "kwage_tools make_bloom|build_db|merge_db ..." << std::endl;
 	return EXIT_FAILURE;
 }

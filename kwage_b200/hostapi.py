@@ -33,6 +33,9 @@ def lib():
                                           C.POINTER(u32), C.POINTER(u32), cp, C.c_size_t]
         L.kwh_write_bloom_file.argtypes = [cp, cp, u32, u32, u32, C.c_void_p]
         L.kwh_build_db.argtypes = [cp, u32, u32, u32, cp, i32]
+        L.kwh_merge_db.argtypes = [cp, cp, u64, i32, cp, C.c_size_t]
+        L.kwh_merge_db.restype = C.c_long
+        L.kwh_pack_2na.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p, u64]
         _lib = L
     return _lib
 
@@ -78,3 +81,31 @@ def write_bloom_file(path, accession, k, log2_len, num_hash, bits):
 
 def build_db(filename, k, log2_len, num_hash, bloom_files, *, device=0):
     return bool(lib().kwh_build_db(filename.encode(), k, log2_len, num_hash, "\n".join(bloom_files).encode(), device))
+
+
+def pack_2na(fragments):
+    """The host layer's packer (stages.cpp::pack_2na) over a list of fragments appended one after the other:
+    -> (2na bytes, not-a-base mask, any_bad)."""
+    import numpy as np
+    frs = [np.frombuffer(f if isinstance(f, (bytes, bytearray)) else bytes(f), dtype=np.uint8) for f in fragments]
+    total = sum(len(f) for f in frs)
+    packed = np.zeros(total // 4 + 8, dtype=np.uint8)
+    mask = np.zeros(total // 8 + 8, dtype=np.uint8)
+    cur, any_bad = 0, False
+    for f in frs:
+        if len(f) and cur % 4 == 0:
+            packed[cur // 4] = 0
+        f = np.ascontiguousarray(f)
+        any_bad |= bool(lib().kwh_pack_2na(packed.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), cur,
+                                           f.ctypes.data_as(C.c_void_p), len(f)))
+        cur += len(f)
+    return packed[: (total + 3) // 4], mask[: (total + 7) // 8], any_bad
+
+
+def merge_db(file_1, file_2, max_num_filters=0, *, device=0):
+    """merge_database_files() (reference merge_db.cpp:278): -> filters in the file that can still take more; raises on error"""
+    err = C.create_string_buffer(512)
+    r = lib().kwh_merge_db(file_1.encode(), file_2.encode(), max_num_filters, device, err, 512)
+    if r < 0:
+        raise RuntimeError(err.value.decode() or "merge_database_files failed")
+    return r

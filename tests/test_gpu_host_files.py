@@ -46,6 +46,43 @@ def test_make_bloom_filter_writes_the_reference_file(name, tmp_path):
         assert not os.path.exists(str(tmp_path / (g["accession"] + ".bloom")))
 
 
+@pytest.mark.parametrize("name,batch", [("ragged_k21", 4096), ("ragged_k21", 100), ("min_count_2", 33000), ("uniform_k31", 64)])
+def test_make_bloom_filter_pipeline_batch_boundaries(name, batch, tmp_path, monkeypatch):
+    """the parser thread packs batch n + 1 while the device works on batch n; with tiny batches (KWAGE_BATCH_BASES) every
+    boundary case is hit: batches that end mid-byte of the 2na stream, fragments longer than a batch that go over in
+    pieces overlapping by k - 1 bases, empty fragments at the cuts -- the file must still be the reference's"""
+    monkeypatch.setenv("KWAGE_BATCH_BASES", str(batch))
+    g = load_golden("make_bloom")[name]
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    reads = str(tmp_path / (g["accession"] + ".reads"))
+    S.write_reads_file(reads, bases, offsets)
+    r = H.make_bloom_file(g["accession"], reads, case["num_bp"], str(tmp_path), k=case["k"], min_kmer_count=case["min_count"],
+                          p=case["p"], min_log2=case["lmin"], max_log2=case["lmax"])
+    assert r["status"] == g["status"] == 14, r
+    assert (r["num_kmer"], r["log2_len"], r["num_hash"]) == (g["num_kmer"], g["log2_len"], g["num_hash"])
+    assert sha_file(str(tmp_path / (g["accession"] + ".bloom"))) == g["file_sha256"]
+
+
+def test_make_bloom_filter_fastq_gz_input(tmp_path):
+    """FASTQ.gz -> .bloom through the parser thread (the reference's SequenceIterator role, parse_sequence.cpp:72-262):
+    same file as from the plain reads"""
+    import gzip
+    name = "uniform_k31"
+    g = load_golden("make_bloom")[name]
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    fq = str(tmp_path / (g["accession"] + ".fastq.gz"))
+    with gzip.open(fq, "wb", compresslevel=1) as f:
+        for r in range(len(offsets) - 1):
+            seq = bytes(bases[int(offsets[r]): int(offsets[r + 1])])
+            f.write(b"@r%d\n" % r + seq + b"\n+\n" + b"I" * len(seq) + b"\n")
+    r = H.make_bloom_file(g["accession"], fq, case["num_bp"], str(tmp_path), k=case["k"], min_kmer_count=case["min_count"],
+                          p=case["p"], min_log2=case["lmin"], max_log2=case["lmax"])
+    assert r["status"] == 14, r
+    assert sha_file(str(tmp_path / (g["accession"] + ".bloom"))) == g["file_sha256"]
+
+
 def test_make_bloom_filter_default_min_count_5_no_cpu_path(tmp_path):
     # the reference's default --min-kmer-count is 5 (options.h); the device path must be the one that ran
     from kwage_b200 import capi

@@ -43,3 +43,26 @@ def test_accession_packing():
         a = H.str_to_accession(s)
         assert a != 0 and H.accession_to_str(a) == s.upper()
     assert H.str_to_accession("SR12") == 0 and H.str_to_accession("SRRX") == 0      # reference throws
+
+
+def test_host_packer_matches_the_numpy_packer():
+    """stages.cpp::pack_2na (what the parser thread of make_bloom_filter runs) against capi.pack_2na on fragments of
+    every length and alignment, with N, IUPAC codes and lower case inside"""
+    from kwage_b200 import capi
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNnRY-*", dtype=np.uint8)
+    for trial in range(30):
+        lens = rng.integers(0, 41, size=rng.integers(1, 30))
+        if trial % 3 == 0:
+            frs = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)] for n in lens]       # no bad bases at all
+        else:
+            frs = [alphabet[rng.integers(0, len(alphabet), size=n)] for n in lens]
+        flat = np.concatenate(frs) if len(frs) else np.zeros(0, np.uint8)
+        packed, mask, any_bad = H.pack_2na([bytes(f) for f in frs])
+        exp_p, exp_m = capi.pack_2na(flat)
+        n = len(flat)
+        assert np.array_equal(packed, exp_p[: (n + 3) // 4])
+        if exp_m is None:
+            assert not any_bad and not mask.any()
+        else:
+            assert any_bad and np.array_equal(mask, exp_m[: (n + 7) // 8])
