@@ -542,8 +542,9 @@ def stage_construct_raw(D, args, windows):
     b.set_timing(False)
     t_scan = float(ms[capi.T_SCAN_A]) / steps / 1e3
 
-    # e2e: two host threads per GPU, each with its own handle: one accession's D2H rides beside the other's H2D
-    n_workers = 2
+    # e2e: three host threads per GPU, each with its own handle: one accession's D2H rides beside another's H2D and a
+    # third one's scan (two workers fall into lockstep: both scan, then both copy out)
+    n_workers = 3
     rb = [b] + [capi.BloomBuilder(K, device=dev, raw_num_hash=h, raw_log2_len=L) for _ in range(n_workers - 1)]
     h_offsets = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
     h_offsets.copy_(d_offsets)
@@ -727,6 +728,143 @@ def stage_search(D, args, windows):
             "gpu_launches": int(launches)}
 
 
+# ---------------------------------------------------------------------------------------------- host ingestion
+def stage_ingest(D, args, windows):
+    """FASTQ.gz -> .bloom wall clock through the C++ host layer (kwage_b200/host: gz parser thread + 2-bit packing +
+    kwg_bloom_add_packed + finalize + file write), the path a maestro worker runs per accession (make_bloom.cpp:76-504).
+    Host-bound by design of the format: zlib inflates a few hundred MB/s per thread."""
+    import gzip
+    import numpy as np
+    torch = D.torch
+    from kwage_b200 import capi, hostapi as H
+    from kwage_b200.host import build as hbuild
+    hbuild.build()
+    n_reads = args.ingest_reads
+    n_bases = n_reads * READ_LEN
+    kmers = n_reads * (READ_LEN - K + 1)
+    d_b = torch.empty(n_bases + 16, dtype=torch.uint8, device="cuda")
+    capi.synth_reads_dev(555 + D.rank, 0, n_reads, READ_LEN, d_b.data_ptr(), 0, device=D.device)
+    seq = d_b[:n_bases].cpu().numpy().reshape(n_reads, READ_LEN)
+    del d_b
+    # fixed-width FASTQ records: "@r0000000\n" + bases + "\n+\n" + qualities + "\n"
+    rec = np.empty((n_reads, 10 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
+    ids = np.char.zfill(np.arange(n_reads).astype(str), 7)
+    rec[:, 0] = ord("@")
+    rec[:, 1] = ord("r")
+    rec[:, 2:9] = np.frombuffer("".join(ids).encode(), dtype=np.uint8).reshape(n_reads, 7)
+    rec[:, 9] = ord("\n")
+    rec[:, 10:10 + READ_LEN] = seq
+    rec[:, 10 + READ_LEN: 13 + READ_LEN] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rec[:, 13 + READ_LEN: 13 + 2 * READ_LEN] = ord("I")
+    rec[:, -1] = ord("\n")
+    tmp = tempfile.mkdtemp(prefix="kwage_ingest_")
+    out = {}
+    try:
+        fq = os.path.join(tmp, "SRR0000001.fastq.gz")
+        with open(fq, "wb") as f:
+            f.write(gzip.compress(rec.tobytes(), compresslevel=1))
+        reads = os.path.join(tmp, "SRR0000002.reads")
+        np.concatenate([seq, np.full((n_reads, 1), 10, dtype=np.uint8)], axis=1).tofile(reads)
+        for name, acc, path in (("fastq_gz", "SRR0000001", fq), ("plain_reads", "SRR0000002", reads)):
+            H.make_bloom_file(acc, path, n_bases, tmp, k=K, min_kmer_count=1, p=P_FALSE, min_log2=LMIN, max_log2=LMAX, device=D.device)   # warm-up (page cache, allocations)
+            t0 = time.time()
+            r = H.make_bloom_file(acc, path, n_bases, tmp, k=K, min_kmer_count=1, p=P_FALSE, min_log2=LMIN, max_log2=LMAX, device=D.device)
+            sec = time.time() - t0
+            windows.append((t0, time.time()))
+            if r["status"] != H.STATUS_BLOOM_SUCCESS:
+                raise SystemExit("bench ingest: make_bloom_filter failed: %r" % (r,))
+            out[name] = {"seconds": sec, "kmer_inserts_per_s": kmers / sec, "input_bytes": os.path.getsize(path), "input_MBps": os.path.getsize(path) / sec / 1e6,
+                         "num_kmer": r["num_kmer"], "log2_filter_len": r["log2_len"], "num_hash": r["num_hash"]}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    sec = out["fastq_gz"]["seconds"]
+    return {"metric": "FASTQ.gz -> .bloom wall clock", "value": D.world * kmers / sec, "unit": "kmer_inserts/s", "ms_per_step": sec * 1e3,
+            "config": {"reads": n_reads, "read_len": READ_LEN, "host_threads": "1 parser/packer + 1 feeder per accession"},
+            "e2e": {"value": D.world * kmers / sec, "unit": "kmer_inserts/s", "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1),
+                    "d2h_bytes_per_step": (1 << out["fastq_gz"]["log2_filter_len"]) // 8 + 8},
+            "points": out,
+            "note": "wall clock of make_bloom_filter() incl. gunzip, parsing, 2-bit packing, H2D, kernels, D2H, crc32 and the .bloom file write; "
+                    "bound by zlib inflate on the parser thread, not by the device"}
+
+
+def stage_db_load(D, args, windows):
+    """.db file -> HBM slab through SubjectDatabase (two page-locked buffers, four reader threads per piece, flat copies):
+    GB/s of the load, beside the rate of one flat pinned H2D copy of the same bytes."""
+    import numpy as np
+    import struct
+    torch = D.torch
+    from kwage_b200 import capi, hostapi as H
+    from kwage_b200.host import build as hbuild
+    hbuild.build()
+    F, L = 2048, args.load_log2
+    row = F // 8
+    n_bytes = (1 << L) * row
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * n_bytes + (1 << 30) else None
+    tmp = tempfile.mkdtemp(prefix="kwage_dbload_", dir=base)
+    try:
+        d = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+        capi.synth_filter_bits_dev(4711 + D.rank, 0, 1, n_bytes, n_bytes, d.data_ptr(), device=D.device)
+        h_pin = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+        h_pin.copy_(d)
+        torch.cuda.synchronize()
+        path = os.path.join(tmp, "bench.db")
+        # DBFileHeader (kwage.h:30-72, 44 bytes), the slices, an (unused here) metadata location table
+        hdr = struct.pack("<IIIIIIIiIQ", 0x20191025, 2, 0, K, 3, L, F, 0, 0, 44 + n_bytes)
+        with open(path, "wb") as f:
+            f.write(hdr)
+            f.write(memoryview(h_pin.numpy()))
+            f.write(bytes(8 * F))
+        # yardstick: one flat pinned copy of the same bytes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d.copy_(h_pin, non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        d.copy_(h_pin, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        pinned_gbs = n_bytes / (e0.elapsed_time(e1) / 1e3) / 1e9
+        del d, h_pin
+        torch.cuda.empty_cache()
+        # yardstick 2: the file read alone (one thread, readinto a page-locked buffer), no device involved
+        h_buf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        mv = memoryview(h_buf.numpy())
+        t_r = time.time()
+        with open(path, "rb", buffering=0) as f:
+            while f.readinto(mv):
+                pass
+        read_gbs = (n_bytes + 44 + 8 * F) / (time.time() - t_r) / 1e9
+        del h_buf, mv
+        H.db_load_seconds([path], device=D.device)           # warm-up (page cache)
+        D.barrier()
+        t0 = time.time()
+        sec, _ = H.db_load_seconds([path], device=D.device)
+        windows.append((t0, time.time()))
+        sec = D.max_over_ranks(sec)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    gbs = n_bytes / sec / 1e9
+    return {"metric": ".db -> HBM load bytes/s", "value": D.world * n_bytes / sec, "unit": "bytes/s", "ms_per_step": sec * 1e3,
+            "config": {"filters": F, "log2_filter_len": L, "slice_bytes": n_bytes, "file_on": "tmpfs" if base else "tmp"},
+            "e2e": {"value": D.world * n_bytes / sec, "unit": "bytes/s", "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": 0},
+            "GBps": gbs, "pinned_h2d_copy_GBps": pinned_gbs, "frac_of_pinned_copy": gbs / pinned_gbs, "file_read_alone_GBps": read_gbs,
+            "note": "wall clock of SubjectDatabase(file): pread by four threads into two alternating page-locked buffers, each piece uploaded with "
+                    "kwg_db_upload_rows_async while the next is read"}
+
+
+def stage_sweep(D, args, windows):
+    """BASELINE.json configs[4], bounded grid (bench_sweep.GRIDS['bounded']): k 21..32, 1-7 hashes, filters of 2^20..2^32 bits."""
+    import bench_sweep
+    t0 = time.time()
+    doc = bench_sweep.run(reads=args.sweep_reads, reps=2, grid="bounded", device=D.device, log=open(os.devnull, "w"))
+    windows.append((t0, time.time()))
+    best = max(doc["raw_construction"], key=lambda r: r["kmer_inserts_per_s"])
+    return {"metric": "configs[4] sweep: raw-mode k-mer inserts/s (best point)", "value": best["kmer_inserts_per_s"], "unit": "kmer_inserts/s",
+            "ms_per_step": best["ms"], "seconds": time.time() - t0,
+            "e2e": {"value": best["kmer_inserts_per_s"], "unit": "kmer_inserts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "device-resident sweep: the host-buffer numbers are in the construct / construct_raw / search stages"},
+            **doc}
+
+
 # ---------------------------------------------------------------------------------------------- CPU reference
 def reference_construct(n_proc, reads_per_proc, steps, warmup):
     """The UNMODIFIED reference make_bloom_filter (oracle/_ref/ref_driver), one accession per process,
@@ -800,7 +938,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--stages", default="construct,construct_c5,construct_raw,crc32,transpose,search")
+    ap.add_argument("--stages", default="construct,construct_c5,construct_raw,ingest,crc32,transpose,db_load,search,sweep")
+    ap.add_argument("--ingest-reads", type=int, default=200000, help="reads of the FASTQ.gz -> .bloom wall-clock stage")
+    ap.add_argument("--load-log2", type=int, default=23, help="db_load stage: 2048 filters x 2^this slices (23: 2 GiB)")
+    ap.add_argument("--sweep-reads", type=int, default=1000000)
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (handles) per GPU in the construct e2e arm")
     ap.add_argument("--in-flight", type=int, default=1, help="accessions in flight per GPU (handles, streams) in the device-resident construct arm")
     ap.add_argument("--reads", type=int, default=1000000, help="reads per accession (step)")
@@ -871,12 +1012,18 @@ def main():
         out["construct_c5"]["config"] = {"min_kmer_count": 5, "coverage": 30.0, "reads_per_accession": args.reads}
     if "construct_raw" in stages:
         out["construct_raw"] = stage_construct_raw(D, args, windows)
+    if "ingest" in stages:
+        out["ingest"] = stage_ingest(D, args, windows)
     if "crc32" in stages:
         out["crc32"] = stage_crc32(D, args, windows)
     if "transpose" in stages:
         out["transpose"] = stage_transpose(D, args, windows)
+    if "db_load" in stages:
+        out["db_load"] = stage_db_load(D, args, windows)
     if "search" in stages:
         out["search"] = stage_search(D, args, windows)
+    if "sweep" in stages and world == 1:
+        out["sweep"] = stage_sweep(D, args, windows)          # (one GPU: the sweep is about kernel regimes, not scaling)
     if D.rank == 0:
         sampler.stop()
     cpu = None

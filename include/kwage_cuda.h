@@ -12,9 +12,10 @@
  *     (make_bloom.cpp:454-501, build_db.cpp:435-453, kwage.cpp:180-187).
  *   - the library owns all device memory; the caller owns every host buffer.  Host input buffers
  *     may be reused as soon as the call returns.
- *   - one handle = one CUDA stream, no global mutable state: handles may be used from different
- *     host threads concurrently (kwage.cpp:76-87 enters search() from an OpenMP region); a single
- *     handle must not be used by two threads at once.
+ *   - one handle = one CUDA stream: handles may be used from different host threads concurrently
+ *     (kwage.cpp:76-87 enters search() from an OpenMP region); a single handle must not be used by
+ *     two threads at once.  The handle-less calls (kwg_transpose*, kwg_merge_slices) may be called
+ *     from any thread; calls for one device take turns, calls for different devices run side by side.
  *   - there is NO CPU fallback: with no usable CUDA device every call fails with KWG_ERR_CUDA.
  *   - bit order everywhere is the reference's BitVector order (bloom.h:131-163): bit i of a
  *     vector lives in byte i/8 at bit position i%8.
@@ -152,6 +153,9 @@ int kwg_transpose_crc(int device, const uint8_t* const* filter_chunks, uint32_t 
  * ------------------------------------------------------------------------------------------ */
 int kwg_merge_slices(int device, const uint8_t* src1, uint32_t n1, const uint8_t* src2, uint32_t n2, uint64_t n_slices,
 	uint32_t n_dst1, uint8_t* dst1, uint8_t* dst2);
+
+/* kwg_transpose[_crc] keep their streams and staging buffers (up to ~0.5 GB per device) between calls; this releases them. */
+void kwg_release_caches(void);
 
 /* Page-locked host memory for the staging buffers of the calls above (filter chunks, slices, read batches): the
  * library's copies then run at PCIe rate and overlap with its kernels.  Optional: any host pointer works. */

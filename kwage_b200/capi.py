@@ -27,7 +27,7 @@ EXPORTS = [
     "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_finalize_crc", "kwg_bloom_reset",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
     "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev", "kwg_host_alloc", "kwg_host_free",
-    "kwg_merge_slices", "kwg_db_upload_rows_async", "kwg_db_upload_columns_async",
+    "kwg_merge_slices", "kwg_release_caches", "kwg_db_upload_rows_async", "kwg_db_upload_columns_async",
     "kwg_db_load", "kwg_db_alloc", "kwg_db_upload_rows", "kwg_db_upload_columns", "kwg_db_attach_dev", "kwg_db_unload", "kwg_search", "kwg_search_ptrs",
     "kwg_search_counts", "kwg_search_counts_dev", "kwg_db_sync", "kwg_db_stream", "kwg_free_hits",
     "kwg_db_set_count_budget", "kwg_search_hits_dev",
@@ -96,6 +96,7 @@ def lib():
     L.kwg_db_upload_columns.argtypes = [vp, u32, u32, u64, u64, vp]
     L.kwg_db_upload_rows_async.argtypes = [vp, u64, u64, vp]
     L.kwg_db_upload_columns_async.argtypes = [vp, u32, u32, u64, u64, vp]
+    L.kwg_release_caches.restype = None
     L.kwg_merge_slices.argtypes = [i32, vp, u32, vp, u32, u64, u32, vp, vp]
     L.kwg_db_attach_dev.argtypes = [pvp, i32, vp, u64, u32, u32, u32, u32]
     L.kwg_db_unload.argtypes = [vp]

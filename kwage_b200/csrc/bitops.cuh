@@ -168,18 +168,33 @@ KWG_DEV void encode16(uint4 v, uint32_t& codes, uint32_t& bad16)
 
 // In-register transpose of a 32x32 bit matrix, LSB-first on both axes:
 // out[b] bit i == in[i] bit b.
+// Five butterfly stages.  The two coarse ones (half-words, bytes) are byte permutes, one instruction per output word;
+// the fine ones exchange bit groups with two logic operations per output word (a shift and a three-input select).
 KWG_DEV void transpose32(uint32_t (&a)[32])
 {
 #pragma unroll
-	for (int j = 16; j >= 1; j >>= 1) {
-		const uint32_t m = (j == 16) ? 0x0000FFFFu : (j == 8) ? 0x00FF00FFu : (j == 4) ? 0x0F0F0F0Fu :
-		                   (j == 2) ? 0x33333333u : 0x55555555u;
+	for (int k = 0; k < 16; ++k) {
+		const uint32_t lo = a[k], hi = a[k + 16];
+		a[k] = __byte_perm(lo, hi, 0x5410);           // low halves of both
+		a[k + 16] = __byte_perm(lo, hi, 0x7632);      // high halves of both
+	}
+#pragma unroll
+	for (int k = 0; k < 32; ++k) {
+		if ((k & 8) == 0) {
+			const uint32_t lo = a[k], hi = a[k + 8];
+			a[k] = __byte_perm(lo, hi, 0x6240);       // bytes 0 and 2 of both
+			a[k + 8] = __byte_perm(lo, hi, 0x7351);   // bytes 1 and 3 of both
+		}
+	}
+#pragma unroll
+	for (int j = 4; j >= 1; j >>= 1) {
+		const uint32_t m = (j == 4) ? 0x0F0F0F0Fu : (j == 2) ? 0x33333333u : 0x55555555u;
 #pragma unroll
 		for (int k = 0; k < 32; ++k) {
 			if ((k & j) == 0) {
-				const uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
-				a[k | j] ^= t;
-				a[k] ^= t << j;
+				const uint32_t lo = a[k], hi = a[k | j];
+				a[k] = (lo & m) | ((hi << j) & ~m);
+				a[k | j] = ((lo >> j) & m) | (hi & ~m);
 			}
 		}
 	}

@@ -8,8 +8,8 @@
 // sectors of four rows.  Pure HBM streaming: 1 bit read + 1 bit written per bit moved.
 #include "common.cuh"
 
-#include <cstdlib>
 #include <mutex>
+#include <new>
 
 #include <algorithm>
 #include <vector>
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(TR_THREADS)
 transpose_kernel(const uint8_t* __restrict__ filters, uint64_t filter_pitch, uint32_t n_filters, uint64_t n_words,
 	uint8_t* __restrict__ dest, uint64_t dest_pitch, uint32_t ny)
 {
-	__shared__ uint32_t tile[32 * 32 * TR_WARPS];       // [b][lw][group ^ swizzle], 32 KiB
+	__shared__ __align__(16) uint32_t tile[32 * 32 * TR_WARPS];       // [b][lw][group ^ swizzle], 32 KiB
 
 	// 1-D grid, column-group index fastest: blocks that run together write the same rows side by
 	// side (whole 128-byte lines reach DRAM) while each still reads whole lines of its filters.
@@ -57,22 +57,25 @@ transpose_kernel(const uint8_t* __restrict__ filters, uint64_t filter_pitch, uin
 	for (int b = 0; b < 32; ++b) tile[(b * 32 + lw) * TR_WARPS + (g ^ sw)] = a[b];
 	__syncthreads();
 
-	// 8 consecutive lanes write the 32 bytes (8 groups) of one row; a warp covers 4 rows.  Fully unrolled: with
-	// R = it*8 + (tid>>5), everything that depends on `it` is a compile-time constant (lwh = it>>2,
-	// b = (it&3)*8 + tid>>5), so an iteration is one LDS, one address add and one predicated store.
-	const uint32_t wd = threadIdx.x & 7;                 // group within the block
-	const uint32_t q = (threadIdx.x >> 3) & 3;           // low two bits of lw
-	const uint32_t r0 = threadIdx.x >> 5;                // 0..7
-	const uint64_t cbyte = (uint64_t)by * TR_WARPS * 4 + wd * 4;
+	// Copy-out with 16-byte accesses: a thread moves half a row of the block (4 groups = 128 filters), two neighbouring
+	// lanes write the 32 bytes of one row, a warp covers 16 rows.  Thread = (half, q = lw & 3, b); iteration `it` is
+	// lw >> 2, so the swizzle of the row (g ^ it) is known at compile time: the 16-byte piece holding the wanted half
+	// is piece (half ^ (it >> 2)), and its four words are in the order j ^ (it & 3).  A quarter warp reads four
+	// consecutive rows of the tile: conflict free.  8 LDS.128 + 8 STG.128 per thread instead of 32 + 32 narrow ones.
+	const uint32_t hl = threadIdx.x & 1;                 // which 16 bytes of the row's 32
+	const uint32_t q = (threadIdx.x >> 1) & 3;           // low two bits of lw
+	const uint32_t bq = threadIdx.x >> 3;                // b: 0..31
+	const uint64_t cbyte = (uint64_t)by * TR_WARPS * 4 + hl * 16;
 	if (cbyte < dest_pitch) {
-		uint8_t* out0 = dest + ((bx * TR_WORDS + q) * 32 + r0) * dest_pitch + cbyte;
-		const uint32_t* t0 = tile + (r0 * 32 + q) * TR_WARPS;
+		uint8_t* out0 = dest + ((bx * TR_WORDS + q) * 32 + bq) * dest_pitch + cbyte;
+		const uint32_t* t0 = tile + (bq * 32 + q) * TR_WARPS;
 #pragma unroll
-		for (int it = 0; it < 32; ++it) {
-			const int lwh = it >> 2, bb = (it & 3) * 8;      // rlw = lwh*4 + q, b = bb + r0
-			const uint32_t v = t0[(bb * 32 + lwh * 4) * TR_WARPS + (wd ^ lwh)];
-			if (bx * TR_WORDS + lwh * 4 + q < n_words)
-				st_na_u32(out0 + ((uint64_t)(lwh * 4) * 32 + bb) * dest_pitch, v);
+		for (int it = 0; it < 8; ++it) {
+			const uint4 v = *reinterpret_cast<const uint4*>(t0 + (it * 4) * TR_WARPS + ((hl ^ (uint32_t)(it >> 2)) << 2));
+			const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+			const uint4 o = make_uint4(w[0 ^ (it & 3)], w[1 ^ (it & 3)], w[2 ^ (it & 3)], w[3 ^ (it & 3)]);
+			if (bx * TR_WORDS + it * 4 + q < n_words)
+				st_na_v4(out0 + ((uint64_t)(it * 4) * 32) * dest_pitch, o);
 		}
 	}
 }
@@ -114,6 +117,7 @@ int kwg_transpose_dev(int device, const uint8_t* d_filters, uint64_t filter_pitc
 }
 
 struct TransposeCache {
+	std::mutex mu;                     // one caller at a time per DEVICE (callers on other devices run beside it)
 	cudaStream_t stream[2] = {nullptr, nullptr};
 	cudaEvent_t crc_done[2] = {nullptr, nullptr};
 	uint8_t* d_in[2] = {nullptr, nullptr};
@@ -122,6 +126,17 @@ struct TransposeCache {
 	uint32_t* d_crc = nullptr;
 	size_t in_cap[2] = {0, 0}, out_cap[2] = {0, 0}, ws_cap[2] = {0, 0}, crc_cap = 0;
 };
+
+static std::mutex g_tr_mu;                           // guards the table below, never held while work runs
+static std::vector<TransposeCache*> g_tr_caches;
+
+static TransposeCache* transpose_cache(int device)
+{
+	std::lock_guard<std::mutex> lock(g_tr_mu);
+	if ((int)g_tr_caches.size() <= device) g_tr_caches.resize(device + 1, nullptr);
+	if (!g_tr_caches[device]) g_tr_caches[device] = new (std::nothrow) TransposeCache();
+	return g_tr_caches[device];
+}
 
 static int transpose_host(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest,
 	uint32_t* filter_crc, uint32_t* dest_crc)
@@ -142,12 +157,11 @@ static int transpose_host(int device, const uint8_t* const* filter_chunks, uint3
 	// The slice axis is worked through in pieces of ~128 MiB on TWO lanes (stream + staging buffers each): while one
 	// piece is transposed and copied back, the next one is already coming in -- the two copy directions and the
 	// kernel overlap.  The running crc32 values chain from piece to piece through an event.
-	uint64_t budget = 128ull << 20;
-	if (const char* e = getenv("KWG_TR_BUDGET_MIB")) budget = (uint64_t)atoll(e) << 20;      // experiment knob
+	const uint64_t budget = 128ull << 20;
 	uint64_t piece_bits = std::max<uint64_t>(1024, (budget / std::max<uint64_t>(n_filters / 8, 16)) & ~1023ull);
 	piece_bits = std::min(piece_bits, round_up(chunk_bits, 32));
 	const uint64_t piece_pitch = round_up(piece_bits / 8, 16);
-	const int n_lanes = (chunk_bits > piece_bits && !getenv("KWG_TR_ONE_LANE")) ? 2 : 1;
+	const int n_lanes = (chunk_bits > piece_bits) ? 2 : 1;
 	for (uint32_t j = 0; j < n_filters; ++j)
 		if (!filter_chunks[j]) return fail(KWG_ERR_INVALID_ARG, "NULL filter chunk");
 	size_t src_stride = 0;                           // != 0: filter_chunks[j] == filter_chunks[0] + j * src_stride
@@ -158,14 +172,14 @@ static int transpose_host(int device, const uint8_t* const* filter_chunks, uint3
 	}
 	const bool want_crc = filter_crc || dest_crc;
 
-	// Streams and staging buffers live in a per-device cache that only grows: build_db calls this once per chunk, and
-	// allocating / releasing gigabytes per call costs anything from 10 to 400 ms.  The lock is held for the whole call
-	// (it synchronises before returning), which is what keeps concurrent callers on one device apart.
-	static std::mutex mu;
-	static std::vector<TransposeCache> caches;
-	std::lock_guard<std::mutex> lock(mu);
-	if ((int)caches.size() <= device) caches.resize(device + 1);
-	TransposeCache& C = caches[device];
+	// Streams and staging buffers live in a per-device cache that only grows (kwg_release_caches frees it): build_db
+	// calls this once per chunk, and allocating / releasing gigabytes per call costs anything from 10 to 400 ms.  The
+	// device's lock is held for the whole call (it synchronises before returning), which keeps concurrent callers on ONE
+	// device apart; callers on different devices do not meet.
+	TransposeCache* cache = transpose_cache(device);
+	if (!cache) return fail(KWG_ERR_NO_MEMORY, "transpose: out of host memory");
+	std::lock_guard<std::mutex> lock(cache->mu);
+	TransposeCache& C = *cache;
 	cudaStream_t* stream = C.stream;
 	cudaEvent_t* crc_done = C.crc_done;
 	uint8_t** d_in = C.d_in;
@@ -235,6 +249,29 @@ static int transpose_host(int device, const uint8_t* const* filter_chunks, uint3
 #undef KWG_GROW
 #undef KWG_TRY
 	return KWG_OK;
+}
+
+void kwg_release_caches(void)
+{
+	std::vector<TransposeCache*> all;
+	{
+		std::lock_guard<std::mutex> lock(g_tr_mu);
+		all = g_tr_caches;
+	}
+	for (size_t d = 0; d < all.size(); ++d) {
+		TransposeCache* C = all[d];
+		if (!C) continue;
+		std::lock_guard<std::mutex> lock(C->mu);
+		if (cudaSetDevice((int)d) != cudaSuccess) continue;
+		for (int l = 0; l < 2; ++l) {
+			if (C->stream[l]) cudaStreamSynchronize(C->stream[l]);
+			cudaFree(C->d_in[l]); cudaFree(C->d_out[l]); cudaFree(C->d_ws[l]);
+			C->d_in[l] = C->d_out[l] = nullptr; C->d_ws[l] = nullptr;
+			C->in_cap[l] = C->out_cap[l] = C->ws_cap[l] = 0;
+		}
+		cudaFree(C->d_crc);
+		C->d_crc = nullptr; C->crc_cap = 0;
+	}
 }
 
 int kwg_transpose(int device, const uint8_t* const* filter_chunks, uint32_t n_filters, uint64_t chunk_bits, uint8_t* dest)

@@ -1,5 +1,6 @@
 // extern "C" view of the host layer so that tests and bench.py (Python, ctypes) can drive the same
 // C++ entry points a C++ caller uses.  Thin: no logic of its own.
+#include <chrono>
 #include <cstring>
 
 #include "kwage_host.h"
@@ -101,6 +102,31 @@ int kwh_build_db(const char* filename, uint32_t kmer_len, uint32_t log2_len, uin
 	}
 	set_build_db_device(device);
 	return build_db(filename, param, files) ? 1 : 0;
+}
+
+// SubjectDatabase(path): wall-clock seconds of loading the file's slice region into HBM (bench: db_load); < 0 on error
+double kwh_db_load_seconds(const char* paths, int device, uint64_t* slab_bytes)
+{
+	try {
+		std::vector<std::string> files;
+		const char* p = paths;
+		while (*p) {
+			const char* e = std::strchr(p, '\n');
+			const std::string s = e ? std::string(p, e) : std::string(p);
+			if (!s.empty()) files.push_back(s);
+			if (!e) break;
+			p = e + 1;
+		}
+		uint64_t total = 0;
+		for (size_t i = 0; i < files.size(); ++i) total += SubjectDatabase::slab_bytes(files[i]);
+		const auto t0 = std::chrono::steady_clock::now();
+		SubjectDatabase db(files, device);
+		const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		if (slab_bytes) *slab_bytes = total;
+		return sec;
+	}
+	catch (const char* e) { std::cerr << e << std::endl; return -1.0; }
+	catch (...) { return -1.0; }
 }
 
 // merge_database_files(); returns the remaining-capacity filter count (>= 0) or -1 on error

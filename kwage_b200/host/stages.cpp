@@ -214,9 +214,11 @@ struct ReadBatch {
 
 class BatchPipeline {
 public:
-	BatchPipeline(ReadSource& src, size_t batch_bases, size_t n_batches, size_t kmer_len) : overlap(kmer_len ? kmer_len - 1 : 0), reads(src), cap(batch_bases), stop(false)
+	BatchPipeline(ReadSource& src, size_t batch_bases, size_t n_batches, size_t kmer_len) : overlap(kmer_len ? kmer_len - 1 : 0), reads(src), cap(batch_bases),
+		max_batches(n_batches), stop(false)
 	{
-		for (size_t i = 0; i < n_batches; ++i) { pool.push_back(new ReadBatch(cap + (1u << 16))); free_q.push_back(pool.back()); }
+		// (page-locking memory costs ~0.5 ms per MiB: batches are created when the parser first needs them, so a small
+		// accession pins one batch and not the whole ring)
 		worker = std::thread(&BatchPipeline::run, this);
 	}
 	~BatchPipeline()
@@ -229,7 +231,8 @@ public:
 	ReadBatch* next()                        // blocks until the parser has a batch; the last one has last == true
 	{
 		std::unique_lock<std::mutex> l(mu);
-		cv.wait(l, [this] { return !full_q.empty(); });
+		cv.wait(l, [this] { return failed || !full_q.empty(); });
+		if (full_q.empty()) throw __FILE__ ":make_bloom_filter: Unable to allocate a read batch";
 		ReadBatch* b = full_q.front();
 		full_q.pop_front();
 		return b;
@@ -250,6 +253,14 @@ private:
 			ReadBatch* b = NULL;
 			{
 				std::unique_lock<std::mutex> l(mu);
+				if (free_q.empty() && pool.size() < max_batches) {
+					l.unlock();
+					ReadBatch* fresh = NULL;
+					try { fresh = new ReadBatch(cap + (1u << 16)); } catch (...) { fresh = NULL; }
+					l.lock();
+					if (fresh) { pool.push_back(fresh); free_q.push_back(fresh); }
+					else if (pool.empty()) { stop = true; failed = true; l.unlock(); cv.notify_all(); return; }
+				}
 				cv.wait(l, [this] { return stop || !free_q.empty(); });
 				if (stop) return;
 				b = free_q.front();
@@ -296,7 +307,8 @@ private:
 	}
 	size_t overlap;                              // kmer_len - 1
 	ReadSource& reads;
-	size_t cap;
+	size_t cap, max_batches;
+	bool failed = false;
 	std::vector<ReadBatch*> pool;
 	std::deque<ReadBatch*> free_q, full_q;
 	std::mutex mu;
@@ -337,7 +349,9 @@ unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAcc
 		progress.valid_read_collection = true;
 
 		{
-			BatchPipeline pipe(reads, batch_bases(), 3, opt.kmer_len);
+			// (an accession known to be small pins a batch of its own size, not 64 Mi bases)
+			const size_t bb = num_bp ? std::min<size_t>(batch_bases(), std::max<size_t>(size_t(4) << 20, (size_t)num_bp + (1u << 16))) : batch_bases();
+			BatchPipeline pipe(reads, bb, 3, opt.kmer_len);
 			bool last = false;
 			while (!last) {
 				ReadBatch* rb = pipe.next();

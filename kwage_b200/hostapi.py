@@ -35,6 +35,8 @@ def lib():
         L.kwh_build_db.argtypes = [cp, u32, u32, u32, cp, i32]
         L.kwh_merge_db.argtypes = [cp, cp, u64, i32, cp, C.c_size_t]
         L.kwh_merge_db.restype = C.c_long
+        L.kwh_db_load_seconds.argtypes = [cp, i32, C.POINTER(u64)]
+        L.kwh_db_load_seconds.restype = C.c_double
         L.kwh_pack_2na.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p, u64]
         _lib = L
     return _lib
@@ -109,3 +111,12 @@ def merge_db(file_1, file_2, max_num_filters=0, *, device=0):
     if r < 0:
         raise RuntimeError(err.value.decode() or "merge_database_files failed")
     return r
+
+
+def db_load_seconds(paths, *, device=0):
+    """SubjectDatabase over one or several .db files: (wall-clock seconds of the load, bytes of slices)"""
+    n = C.c_uint64(0)
+    sec = lib().kwh_db_load_seconds("\n".join(paths).encode(), device, C.byref(n))
+    if sec < 0:
+        raise RuntimeError("SubjectDatabase load failed")
+    return sec, n.value

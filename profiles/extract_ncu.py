@@ -3,6 +3,7 @@
 
   python profiles/extract_ncu.py launches gpurun_out/launches.csv  profiles/rNN_launches.md
   python profiles/extract_ncu.py full     gpurun_out/prof_x.ncu-rep [...] profiles/rNN_ncu_full.md
+  python profiles/extract_ncu.py traffic  gpurun_out/prof_x.ncu-rep [...] profiles/ncu_traffic.json
 
 `launches` reads the CSV of an `ncu --metrics gpu__time_duration.sum --clock-control none --csv` pass and
 prints per-kernel launch counts, mean/min/max duration and share of the total GPU time.  `full` reads
@@ -98,8 +99,40 @@ def full(reps, out):
     print("wrote", out)
 
 
+def traffic(reps, out):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel -> the file bench.py reads roofline.traffic from,
+    stamped with the commit the captures belong to (HEAD at extraction time; capture and extract from the same tree)."""
+    import json
+    import os
+    sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    kernels = {}
+    try:
+        with open(out) as f:
+            kernels = json.load(f).get("kernels", {})       # other kernels' entries from earlier captures stay
+    except Exception:
+        pass
+    for rep in reps:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            name = short(d["Kernel Name"]).split("<")[0]
+            tot = float(d["dram__bytes_read.sum"]) * sc[units[hdr.index("dram__bytes_read.sum")]] + \
+                float(d["dram__bytes_write.sum"]) * sc[units[hdr.index("dram__bytes_write.sum")]]
+            kernels[name] = tot
+    head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=os.path.dirname(os.path.abspath(__file__))).stdout.strip()
+    with open(out, "w") as f:
+        json.dump({"commit": head, "reports": [os.path.basename(r) for r in reps], "unit": "bytes per launch (dram read + write)",
+                   "kernels": kernels}, f, indent=1)
+        f.write("\n")
+    print("wrote", out, kernels)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2:-1], sys.argv[-1])
     else:
         full(sys.argv[2:-1], sys.argv[-1])

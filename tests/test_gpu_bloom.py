@@ -94,6 +94,19 @@ def test_counting_mode_matches_reference_golden(name):
     assert util.sha256(bits) == g["bits_sha256"]
 
 
+@pytest.mark.parametrize("name,split", [("uniform_k31", None), ("ragged_k21", 7), ("small_count_filter", 3), ("k15_dups", None), ("cfg1_mt64", None)])
+def test_counting_mode_two_level_radix_path_stays_exact(name, split, monkeypatch):
+    """min_kmer_count 1 takes the one-level first-touch path (bloom_first.cuh) up to log2_count_len 30 and the two-level
+    radix partition (bloom_count.cuh) above; KWG_COUNT_TWO_LEVEL (read when the handle is created) forces the latter so
+    that it stays covered at the sizes the goldens have"""
+    monkeypatch.setenv("KWG_COUNT_TWO_LEVEL", "1")
+    g = load_golden("make_bloom")[name]
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    _, n_valid, param, bits = run_counting(case, bases, offsets, split=split)
+    assert n_valid == g["num_kmer"] and util.sha256(bits) == g["bits_sha256"]
+
+
 @pytest.mark.parametrize("name,split", [("ragged_k21", 7), ("small_count_filter", 3), ("k15_dups", 40), ("min_count_2", 5),
                                         ("min_count_5", 3)])
 def test_counting_mode_is_stream_order_exact_across_calls(name, split):
