@@ -218,6 +218,12 @@ public:
 	// Returns true if any query matched.  results[query_id] gets one MatchResult per matching filter.
 	bool search(std::unordered_map<size_t, std::deque<MatchResult> >& results, const std::vector<std::string>& queries,
 		const std::vector<size_t>& query_ids, const SearchOptions& opt);
+	// Multi-device form: every device holds one slab; all of them search the same queries and the hit lists are gathered
+	// on `root` with one NCCL exchange inside the library (kwg_search_gather), the stand-in for the reference's critical
+	// section over thread-local maps (kwage.cpp:154-177).  Collective: one host thread per device calls it.  filter0 =
+	// first global filter index of this slab.  On the root, hits (global filter indices) and n_kmers are filled.
+	void search_gather(kwg_comm_t* comm, int root, uint32_t filter0, const std::vector<std::string>& queries, float threshold,
+		std::vector<kwg_hit_t>& hits, std::vector<uint32_t>& n_kmers);
 	FilterInfo filter_info(uint32_t filter);   // kwage.cpp:505-515
 private:
 	SubjectDatabase(const SubjectDatabase&);

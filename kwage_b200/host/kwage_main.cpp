@@ -176,13 +176,79 @@ int main(int argc, char* argv[])
 			groups.push_back(group);
 			f = g;
 		}
+		if (devices.empty()) devices.push_back(opt.device);
+		// Several devices: rounds of one slab per device.  Every device searches all the queries against its slab and the
+		// per-slab hit lists meet on the first device through ONE NCCL exchange inside the library (kwg_search_gather) --
+		// what the reference's critical section does with its thread-local maps (kwage.cpp:154-177).  Slabs left over
+		// (fewer than devices) and single-device runs take the plain path below.
+		size_t first_plain_group = 0;
+		bool distinct = true;
+		for (size_t a = 0; a < devices.size(); ++a)
+			for (size_t b = a + 1; b < devices.size(); ++b) distinct = distinct && devices[a] != devices[b];
+		if (devices.size() > 1 && distinct && groups.size() >= devices.size()) {
+			const size_t n = devices.size();
+			std::vector<kwg_comm_t*> comms(n, (kwg_comm_t*)NULL);
+			if (kwg_comm_create_all(comms.data(), (int)n, devices.data()) == KWG_OK) {
+				std::vector<std::string> all_seqs(cmd_seqs);
+				all_seqs.insert(all_seqs.end(), file_seqs.begin(), file_seqs.end());
+				const size_t full_rounds = groups.size() / n;
+				std::string round_error;
+				for (size_t r = 0; r < full_rounds && round_error.empty(); ++r) {
+					std::vector<SubjectDatabase*> subj(n, (SubjectDatabase*)NULL);
+					std::vector<std::string> err(n);
+					std::vector<std::thread> th;
+					for (size_t w = 0; w < n; ++w)
+						th.push_back(std::thread([&, w]() {
+							try { subj[w] = new SubjectDatabase(groups[r * n + w], devices[w]); }
+							catch (const char* e) { err[w] = e; } catch (...) { err[w] = "unhandled error"; }
+						}));
+					for (size_t w = 0; w < n; ++w) th[w].join();
+					th.clear();
+					bool ok = true;
+					for (size_t w = 0; w < n; ++w) ok = ok && err[w].empty();
+					std::vector<uint32_t> filter0(n + 1, 0);
+					for (size_t w = 0; w < n && ok; ++w) filter0[w + 1] = filter0[w] + subj[w]->header().num_filter;
+					std::vector<kwg_hit_t> hits;
+					std::vector<uint32_t> nk;
+					if (ok) {
+						for (size_t w = 0; w < n; ++w)
+							th.push_back(std::thread([&, w]() {
+								try {
+									std::vector<kwg_hit_t> h;
+									std::vector<uint32_t> k;
+									subj[w]->search_gather(comms[w], 0, filter0[w], all_seqs, opt.threshold, h, k);
+									if (w == 0) { hits.swap(h); nk.swap(k); }
+								}
+								catch (const char* e) { err[w] = e; } catch (...) { err[w] = "unhandled error"; }
+							}));
+						for (size_t w = 0; w < n; ++w) th[w].join();
+						for (size_t w = 0; w < n; ++w) ok = ok && err[w].empty();
+					}
+					if (ok) {
+						for (size_t i = 0; i < hits.size(); ++i) {
+							size_t w = 0;
+							while (w + 1 < n && hits[i].filter >= filter0[w + 1]) ++w;
+							const FilterInfo info = subj[w]->filter_info(hits[i].filter - filter0[w]);
+							const size_t q = hits[i].query;
+							if (q < cmd_seqs.size()) cmd_results[q].push_back(MatchResult(hits[i].num_match, nk[q], info));
+							else file_results[q - cmd_seqs.size()].push_back(MatchResult(hits[i].num_match, nk[q], info));
+						}
+					}
+					for (size_t w = 0; w < n; ++w) { if (!err[w].empty() && round_error.empty()) round_error = err[w]; delete subj[w]; }
+				}
+				for (size_t w = 0; w < n; ++w) kwg_comm_destroy(comms[w]);
+				if (!round_error.empty()) { std::cerr << "Caught the error " << round_error << std::endl; return EXIT_FAILURE; }
+				first_plain_group = full_rounds * n;
+			}
+			else std::cerr << "kwage: NCCL is not available (" << kwg_last_error() << "); merging the hit lists on the host" << std::endl;
+		}
 		// one host thread per device takes slabs off a shared counter (the reference: one OpenMP thread per file,
 		// kwage.cpp:76-87); every thread collects its matches privately and they are merged afterwards
-		if (devices.empty()) devices.push_back(opt.device);
-		const size_t n_workers = std::min(devices.size(), groups.size());
+		const size_t n_plain = groups.size() - first_plain_group;
+		const size_t n_workers = std::min(devices.size(), n_plain);
 		std::vector<std::unordered_map<size_t, std::deque<MatchResult> > > w_cmd(n_workers), w_file(n_workers);
 		std::vector<std::string> w_error(n_workers);
-		std::atomic<size_t> next(0);
+		std::atomic<size_t> next(first_plain_group);
 		std::vector<std::thread> workers;
 		for (size_t w = 0; w < n_workers; ++w) {
 			workers.push_back(std::thread([&, w]() {

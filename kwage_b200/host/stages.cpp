@@ -852,6 +852,23 @@ FilterInfo SubjectDatabase::filter_info(uint32_t filter)
 	return info;
 }
 
+void SubjectDatabase::search_gather(kwg_comm_t* comm, int root, uint32_t filter0, const std::vector<std::string>& queries, float threshold,
+	std::vector<kwg_hit_t>& hits_out, std::vector<uint32_t>& n_kmers)
+{
+	if (queries.size() > 0xFFFFFFFFull) throw __FILE__ ":search: more than 2^32 queries in one call (split the query set)";
+	std::string flat;
+	std::vector<uint64_t> offsets(1, 0);
+	for (size_t i = 0; i < queries.size(); ++i) { flat += queries[i]; offsets.push_back(flat.size()); }
+	if (flat.empty()) flat.push_back('N');
+	n_kmers.assign(queries.size(), 0);
+	kwg_hit_t* hits = NULL;
+	uint64_t n_hits = 0;
+	cuda_check(kwg_search_gather(db, comm, root, flat.data(), offsets.data(), (uint32_t)queries.size(), threshold, filter0,
+		n_kmers.data(), &hits, &n_hits), __FILE__ ":search: kwg_search_gather failed");
+	hits_out.assign(hits, hits + n_hits);
+	kwg_free_hits(hits);
+}
+
 bool SubjectDatabase::search(std::unordered_map<size_t, std::deque<MatchResult> >& results, const std::vector<std::string>& queries,
 	const std::vector<size_t>& query_ids, const SearchOptions& opt)
 {
