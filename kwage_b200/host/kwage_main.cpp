@@ -11,6 +11,7 @@
 #include <sstream>
 #include <sys/stat.h>
 #include <thread>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "kwage_host.h"
@@ -188,7 +189,16 @@ int main(int argc, char* argv[])
 		if (devices.size() > 1 && distinct && groups.size() >= devices.size()) {
 			const size_t n = devices.size();
 			std::vector<kwg_comm_t*> comms(n, (kwg_comm_t*)NULL);
-			if (kwg_comm_create_all(comms.data(), (int)n, devices.data()) == KWG_OK) {
+			// NCCL prints its version banner (NCCL_DEBUG=VERSION) on stdout while the communicators are created, and
+			// stdout carries the results: it points at stderr for the duration of that call
+			std::cout.flush();
+			fflush(stdout);
+			const int saved_stdout = dup(1);
+			if (saved_stdout >= 0) dup2(2, 1);
+			const int comm_rc = kwg_comm_create_all(comms.data(), (int)n, devices.data());
+			fflush(stdout);
+			if (saved_stdout >= 0) { dup2(saved_stdout, 1); close(saved_stdout); }
+			if (comm_rc == KWG_OK) {
 				std::vector<std::string> all_seqs(cmd_seqs);
 				all_seqs.insert(all_seqs.end(), file_seqs.begin(), file_seqs.end());
 				const size_t full_rounds = groups.size() / n;
