@@ -9,8 +9,8 @@ above, which is the regime change the sweep is there to show.  Counting mode: lo
 min_kmer_count 1.  Search: 1/3/5 hashes against slabs of 1024..32768 filter columns.
 
 Every point is timed with CUDA events on the handle's stream after a warm-up pass, inputs resident in HBM and larger
-than L2 (reads) or randomly gathered (slab).  k > 32 and more than 8 hashes are beyond the reference (word.h:10,
-hash.cpp:243) and are not built.  Prints one JSON document; rows also go to --out.
+than L2 (reads) or randomly gathered (slab).  k in 33..63 (raw mode, 128-bit words) is beyond the reference (word.h:10): parity
+unpinned there; more than 8 hashes (hash.cpp:243) is not built.  Prints one JSON document; rows also go to --out.
 """
 import argparse
 import json
@@ -22,10 +22,10 @@ READ_LEN = 150
 
 GRIDS = {
     # full: every (h, L) at k = 31, six corner points at the other k
-    "full": dict(ks=[21, 25, 31, 32], hs=[1, 2, 3, 4, 5, 7, 8], Ls=[20, 24, 26, 28, 29, 30, 31, 32], lcs=[18, 20, 22, 23, 24, 26, 28, 30, 32],
+    "full": dict(ks=[21, 25, 31, 32, 47, 63], hs=[1, 2, 3, 4, 5, 7, 8], Ls=[20, 24, 26, 28, 29, 30, 31, 32], lcs=[18, 20, 22, 23, 24, 26, 28, 30, 32],
                  Fs=[1024, 8192, 32768], search_hs=[1, 3, 5]),
     # bounded: what `bench.py --stages sweep` runs (a few seconds): 1-7 hashes, filters on both sides of the L2 -> HBM crossover
-    "bounded": dict(ks=[21, 25, 31, 32], hs=[1, 2, 3, 5, 7], Ls=[20, 26, 29, 30, 32], lcs=[24, 28, 30], Fs=[2048, 8192], search_hs=[1, 3, 5]),
+    "bounded": dict(ks=[21, 25, 31, 32, 47, 63], hs=[1, 2, 3, 5, 7], Ls=[20, 26, 29, 30, 32], lcs=[24, 28, 30], Fs=[2048, 8192], search_hs=[1, 3, 5]),
     "quick": dict(ks=[31], hs=[3], Ls=[26, 32], lcs=[23, 30], Fs=[8192], search_hs=[3]),
 }
 
@@ -76,7 +76,7 @@ def run(reads=2000000, reps=3, grid="full", device=0, log=sys.stderr):
                 assert b.num_valid() == kmers
                 b.close()
                 rows["raw_construction"].append({
-                    "k": k, "num_hash": h, "log2_len": L, "filter_MiB": (1 << L) / 8 / 2**20,
+                    "k": k, "parity": "pinned (reference range)" if k <= 32 else "unpinned (beyond word.h:10)", "num_hash": h, "log2_len": L, "filter_MiB": (1 << L) / 8 / 2**20,
                     "regime": "L2-resident" if (1 << L) // 8 <= 64 << 20 else "HBM-resident",
                     "kmer_inserts_per_s": kmers / sec, "bit_sets_per_s": kmers * h / sec, "ms": sec * 1e3,
                     # algorithmic HBM bytes: the bases once; HBM-resident filters add one 32-byte sector read-modify-write per bit
@@ -136,7 +136,8 @@ def run(reads=2000000, reps=3, grid="full", device=0, log=sys.stderr):
             cross = {"last_L2_resident_log2_len": l0, "bit_sets_per_s": v0, "first_HBM_resident_log2_len": l1, "bit_sets_per_s_hbm": v1,
                      "ratio": v0 / v1 if v1 else None}
     return {"what": "configs[4] parameter sweep (%s grid), 1 x B200, inputs resident in HBM, CUDA-event timed; k > 32 and more than 8 hashes "
-                    "are beyond the reference (word.h:10, hash.cpp:243) and are not built" % grid,
+                    "are beyond the reference (word.h:10, hash.cpp:243): k in 33..63 runs in raw mode on 128-bit words with unpinned parity, more than "
+                    "8 hashes is not built" % grid,
             "reads_per_point": n_reads, "read_len": READ_LEN, "time": time.strftime("%Y-%m-%d %H:%M:%S"), "l2_to_hbm_crossover": cross, **rows}
 
 

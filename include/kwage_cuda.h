@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 #define KWG_MAX_KMER_LEN 32   /* reference word.h:10 */
+#define KWG_MAX_KMER_LEN_RAW 63   /* raw mode only: an extension beyond the reference (BASELINE.json configs[4]); parity unpinned above 32 */
 #define KWG_MAX_NUM_HASH 8    /* reference hash.cpp:7 (construction uses <= 5: bloom.h:21) */
 #define KWG_COUNT_NUM_HASH 5  /* hashes evaluated per k-mer in counting mode: bloom.h:21 */
 
@@ -73,7 +74,8 @@ uint64_t kwg_launch_count(void);
  *
  * Raw mode (kwg_bloom_create_raw) sets bit (murmur3(kmer, seed=h) & (2^log2_len - 1)) for
  * h < num_hash for every valid canonical k-mer: the ground-truth construction of the reference's
- * own rig (bloom_test.cpp:268-275).
+ * own rig (bloom_test.cpp:268-275).  Raw mode also takes kmer_len 33..63 (128-bit words, the same rules); the reference
+ * has no such k-mers (word.h:10), so there is nothing to be bit-exact with: checked against oracle/kwo_raw_insert_wide.
  * ------------------------------------------------------------------------------------------ */
 typedef struct kwg_bloom kwg_bloom_t;
 
@@ -229,7 +231,8 @@ int kwg_search_ptrs(kwg_db_t* db, const char* const* queries, const uint64_t* qu
 int kwg_search_counts(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries,
 	uint32_t* n_query_kmers, uint32_t* counts);
 /* Device-resident variant: d_counts is n_queries * count_pitch uint32 (count_pitch >= n_filters,
- * multiple of 4).  d_n_query_kmers: n_queries uint32.  Asynchronous on the db's stream. */
+ * multiple of 4).  d_n_query_kmers: n_queries uint32.  d_bases: 4-byte aligned, read in whole 32-bit words (up to the
+ * word that holds base n_bases - 1).  Asynchronous on the db's stream. */
 int kwg_search_counts_dev(kwg_db_t* db, const char* d_bases, const uint64_t* d_offsets, uint32_t n_queries,
 	uint64_t n_bases, uint32_t* d_n_query_kmers, uint32_t* d_counts, uint64_t count_pitch);
 int kwg_db_sync(kwg_db_t* db);

@@ -277,4 +277,105 @@ KWG_DEV uint64_t window_sense(const uint32_t* codes, uint32_t p, uint32_t k)
 	return (((uint64_t)hi << 32) | lo) >> (64 - 2 * k);
 }
 
+
+// ---------------------------------------------------------------- k in 33..63 (raw mode only)
+// PARITY UNPINNED: the reference stops at k = 32 (word.h:10).  The same rules on a 128-bit word (hi:lo, the 5' base most
+// significant, 2k bits right-aligned); checked against oracle/kwo_raw_insert_wide, which equals the narrow restatement
+// for k <= 32 and an independent pure-Python statement above (tests/test_oracle_wide.py).
+struct Word128 { uint64_t hi, lo; };
+
+KWG_DEV Word128 shr128(Word128 v, uint32_t s)            // 0 <= s < 128
+{
+	Word128 r;
+	if (s == 0) return v;
+	if (s >= 64) { r.hi = 0; r.lo = v.hi >> (s - 64); }
+	else { r.hi = v.hi >> s; r.lo = (v.lo >> s) | (v.hi << (64 - s)); }
+	return r;
+}
+
+KWG_DEV uint64_t reverse_groups64(uint64_t w)            // all 32 2-bit groups of a 64-bit word, order reversed
+{
+	const uint64_t r = __brevll(w);
+	return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
+}
+
+// the k bases starting at position p of the tile (codes[]: 16 bases per word, first base in the top bits), k <= 64
+KWG_DEV Word128 window_sense_wide(const uint32_t* codes, uint32_t p, uint32_t k)
+{
+	const uint32_t wi = p >> 4, off = 2 * (p & 15);
+	const uint32_t w0 = codes[wi], w1 = codes[wi + 1], w2 = codes[wi + 2], w3 = codes[wi + 3], w4 = codes[wi + 4];
+	Word128 v;
+	v.hi = ((uint64_t)__funnelshift_l(w1, w0, off) << 32) | __funnelshift_l(w2, w1, off);
+	v.lo = ((uint64_t)__funnelshift_l(w3, w2, off) << 32) | __funnelshift_l(w4, w3, off);
+	return shr128(v, 128 - 2 * k);
+}
+
+struct CanonWide {
+	Word128 word;    // min(sense, antisense)
+	Word128 low;     // the same k-mer with base i at bits [2i, 2i+1]
+};
+
+KWG_DEV CanonWide canonical_wide(Word128 sense, uint32_t k)
+{
+	// mask of the low 2k bits
+	Word128 m;
+	m.hi = (2 * k >= 128) ? ~0ull : ((2 * k > 64) ? ((1ull << (2 * k - 64)) - 1ull) : 0ull);
+	m.lo = (2 * k >= 64) ? ~0ull : ((1ull << (2 * k)) - 1ull);
+	// reverse the k groups: reverse all 64 groups of the 128-bit word, then drop the 64 - k empty ones at the bottom
+	Word128 full;
+	full.hi = reverse_groups64(sense.lo);
+	full.lo = reverse_groups64(sense.hi);
+	const Word128 rev = shr128(full, 128 - 2 * k);
+	Word128 anti;
+	anti.hi = ~rev.hi & m.hi; anti.lo = ~rev.lo & m.lo;
+	CanonWide c;
+	const bool sense_first = (sense.hi < anti.hi) || (sense.hi == anti.hi && sense.lo <= anti.lo);
+	if (sense_first) { c.word = sense; c.low = rev; }
+	else { c.word = anti; c.low.hi = ~sense.hi & m.hi; c.low.lo = ~sense.lo & m.lo; }      // reverse_groups(anti) == ~sense
+	return c;
+}
+
+template <int NH>
+KWG_DEV void murmur3_multi_wide(Word128 low, uint32_t k, uint32_t (&h)[NH])
+{
+	const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
+#pragma unroll
+	for (int s = 0; s < NH; ++s) h[s] = (uint32_t)s;
+	const uint32_t nblocks = k >> 2;
+	for (uint32_t i = 0; i < nblocks; ++i) {
+		uint32_t k1 = ascii4((uint32_t)low.lo & 0xFFu);
+		low = shr128(low, 8);
+		k1 *= c1; k1 = rotl32(k1, 15); k1 *= c2;
+#pragma unroll
+		for (int s = 0; s < NH; ++s) {
+			uint32_t x = h[s] ^ k1;
+			x = rotl32(x, 13);
+			h[s] = x * 5u + 0xe6546b64u;
+		}
+	}
+	const uint32_t rem = k & 3u;
+	if (rem) {
+		uint32_t k1 = ascii4((uint32_t)low.lo & 0xFFu) & ((1u << (8 * rem)) - 1u);
+		k1 *= c1; k1 = rotl32(k1, 15); k1 *= c2;
+#pragma unroll
+		for (int s = 0; s < NH; ++s) h[s] ^= k1;
+	}
+#pragma unroll
+	for (int s = 0; s < NH; ++s) {
+		uint32_t x = h[s] ^ k;
+		x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+		h[s] = x;
+	}
+}
+
+// a window [p, p+k), k <= 64, is a k-mer iff it has no bad base and no read starts strictly inside it
+KWG_DEV bool window_ok_wide(const uint32_t* bad, const uint32_t* start, uint32_t p, uint32_t k)
+{
+	const uint64_t win_mask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
+	const uint32_t bw = p >> 5, bo = p & 31;
+	const uint64_t bad_win = (((uint64_t)__funnelshift_r(bad[bw + 1], bad[bw + 2], bo) << 32) | __funnelshift_r(bad[bw], bad[bw + 1], bo)) & win_mask;
+	const uint64_t start_win = ((((uint64_t)__funnelshift_r(start[bw + 1], start[bw + 2], bo) << 32) | __funnelshift_r(start[bw], start[bw + 1], bo)) & win_mask) >> 1;
+	return (bad_win | start_win) == 0;
+}
+
 } // namespace kwg

@@ -168,6 +168,61 @@ kmer_scan_kernel(const ScanParams P)
 	}
 }
 
+// Raw mode for k in 33..63 (BASELINE.json configs[4] sweeps k up to 63; the reference stops at 32, word.h:10, so parity is
+// UNPINNED there: the yardstick is oracle kwo_raw_insert_wide).  Same structure as kmer_scan_kernel<MODE_RAW>, 128-bit
+// words, a 64-base halo.
+constexpr int WT_HALO = 64;
+constexpr int WT_LOAD = TILE_BASES + WT_HALO;
+constexpr int WT_VEC = WT_LOAD / 16;
+
+template <int NH>
+__global__ void __launch_bounds__(SCAN_THREADS)
+kmer_scan_wide_kernel(const ScanParams P)
+{
+	__shared__ uint32_t s_codes[WT_VEC + 4];
+	__shared__ uint32_t s_bad[WT_LOAD / 32 + 3];
+	__shared__ uint32_t s_start[WT_LOAD / 32 + 3];
+
+	const uint32_t tid = threadIdx.x;
+	const uint32_t k = P.k;
+	const uint64_t rel0 = (uint64_t)blockIdx.x * TILE_BASES;
+	const uint64_t t0 = P.pos0 + rel0;
+	for (uint32_t v = tid; v < (uint32_t)WT_VEC; v += SCAN_THREADS) {
+		uint32_t codes, bad16;
+		load_group16(P.src, t0 + (uint64_t)v * 16, codes, bad16);
+		s_codes[v] = codes;
+		reinterpret_cast<uint16_t*>(s_bad)[v] = (uint16_t)bad16;
+	}
+	for (uint32_t v = tid; v < (uint32_t)(WT_LOAD / 32 + 1); v += SCAN_THREADS) {
+		const uint64_t w = (t0 >> 5) + v;
+		s_start[v] = (w * 32 < P.src.n_bases) ? P.start_mask[w] : 0u;
+	}
+	if (tid < 4) s_codes[WT_VEC + tid] = 0;
+	if (tid < 3) s_bad[WT_LOAD / 32 + tid] = 0xFFFFFFFFu;
+	if (tid < 2) s_start[WT_LOAD / 32 + 1 + tid] = 0;
+	__syncthreads();
+
+	unsigned long long raw_local = 0;
+	const uint64_t pol_keep = l2_policy_evict_last();
+#pragma unroll 1
+	for (uint32_t it = 0; it < TILE_BASES / SCAN_THREADS; ++it) {
+		const uint32_t p = it * SCAN_THREADS + tid;
+		if ((rel0 + p < P.n_pos) && window_ok_wide(s_bad, s_start, p, k)) {
+			const CanonWide c = canonical_wide(window_sense_wide(s_codes, p, k), k);
+			uint32_t h[NH];
+			murmur3_multi_wide<NH>(c.low, k, h);
+#pragma unroll
+			for (int s = 0; s < NH; ++s) {
+				const uint32_t bit = h[s] & P.filter_mask;
+				if (P.n_win == 1 || (bit >> WINDOW_LOG2) == P.win_id) red_or_hint(P.filter + (bit >> 5), 1u << (bit & 31), pol_keep);
+			}
+			if (P.win_id == 0) ++raw_local;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) raw_local += __shfl_down_sync(0xFFFFFFFFu, raw_local, o);
+	if ((tid & 31) == 0 && raw_local) atomicAdd(P.counter, raw_local);
+}
+
 // bit p of start_mask <=> some read starts at base p of the batch
 __global__ void mark_read_starts_kernel(const uint64_t* __restrict__ offsets, uint64_t n_reads, uint64_t off0,
 	uint64_t n_bases, uint32_t* __restrict__ start_mask)
@@ -333,7 +388,14 @@ static int launch_scan(kwg_bloom* b, const ScanParams& P)
 	if (tiles > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "batch too large");
 	const dim3 grid((unsigned)tiles), block(SCAN_THREADS);
 	b->timers.begin(MODE == MODE_PASS_B ? KWG_T_SCAN_B : KWG_T_SCAN_A, b->stream);
-	if (MODE == MODE_RAW) {
+	if (MODE == MODE_RAW && b->k > KWG_MAX_KMER_LEN) {
+		switch (b->raw_nh) {
+#define KWG_CASE(N) case N: kmer_scan_wide_kernel<N><<<grid, block, 0, b->stream>>>(P); break;
+			KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
+#undef KWG_CASE
+			default: return fail(KWG_ERR_INVALID_ARG, "num_hash out of range");
+		}
+	} else if (MODE == MODE_RAW) {
 		switch (b->raw_nh) {
 #define KWG_CASE(N) case N: kmer_scan_kernel<MODE_RAW, N><<<grid, block, 0, b->stream>>>(P); break;
 			KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
@@ -765,7 +827,7 @@ static int add_batch_dev(kwg_bloom* b, const BaseSource& src, const uint64_t* d_
 		// the first pass over the bases runs piece by piece behind the host feed; further window passes find them in HBM
 		std::vector<FeedPiece> pieces;
 		if (feed) {
-			pieces = feed_plan(n_bases, FEED_CHUNK, TILE_BASES, TILE_LOAD, n_tiles);
+			pieces = feed_plan(n_bases, FEED_CHUNK, TILE_BASES, b->k > KWG_MAX_KMER_LEN ? WT_LOAD : TILE_LOAD, n_tiles);
 			if ((rc = feed_begin(b, pieces.size(), src, *feed))) return rc;
 		} else {
 			pieces.push_back(FeedPiece{0, n_tiles, 0, (size_t)n_bases});
@@ -884,7 +946,8 @@ int kwg_bloom_create_raw(kwg_bloom_t** out, int device, uint32_t kmer_len, uint3
 {
 	if (!out) return fail(KWG_ERR_INVALID_ARG, "out is NULL");
 	*out = nullptr;
-	if (kmer_len < 1 || kmer_len > KWG_MAX_KMER_LEN) return fail(KWG_ERR_INVALID_ARG, "kmer_len must be in [1,32] (reference word.h:10)");
+	if (kmer_len < 1 || kmer_len > KWG_MAX_KMER_LEN_RAW)
+		return fail(KWG_ERR_INVALID_ARG, "kmer_len must be in [1,63] in raw mode (the reference stops at 32, word.h:10; 33..63 is an extension)");
 	if (num_hash < 1 || num_hash > KWG_MAX_NUM_HASH) return fail(KWG_ERR_INVALID_ARG, "num_hash must be in [1,8] (reference hash.cpp:7,243-245)");
 	if (log2_len < 5 || log2_len > 32) return fail(KWG_ERR_INVALID_ARG, "log2_len must be in [5,32]");
 	int rc = select_device(device);

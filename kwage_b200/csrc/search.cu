@@ -32,9 +32,23 @@ constexpr int QK_THREADS = 128;
 constexpr int QK_TILE = 2048;                       // k-mer start positions per staged tile
 constexpr int QK_LOAD = QK_TILE + 32;               // bytes staged per tile (halo >= k - 1)
 
+// Queries of up to QK_SMEM_SLOTS / 2 bases (the BIGSI use case: genes) keep their hash set in shared memory; longer
+// ones use their region of the table in HBM, which this kernel clears for them (and only for them).
+constexpr int QK_SMEM_SLOTS = 4096;
+
+__global__ void __launch_bounds__(256)
+query_table_init_kernel(const uint64_t* __restrict__ offsets, uint64_t* __restrict__ table)
+{
+	const uint32_t q = blockIdx.x;
+	const uint64_t o0 = offsets[q] - offsets[0], len = offsets[q + 1] - offsets[q];
+	if (2 * len <= (uint64_t)QK_SMEM_SLOTS) return;
+	uint64_t* tab = table + 2 * o0;
+	for (uint64_t i = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < 2 * len; i += (uint64_t)gridDim.y * blockDim.x) tab[i] = SET_EMPTY;
+}
+
 template <int NH>
 __global__ void __launch_bounds__(QK_THREADS)
-query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t k, uint32_t filter_mask,
+query_kmers_kernel(const char* __restrict__ bases, uint64_t n_bases_total, const uint64_t* __restrict__ offsets, uint32_t k, uint32_t filter_mask,
 	uint64_t* __restrict__ table,       // 2 slots per base: query q owns table[2*o0 .. 2*o1)
 	uint64_t* __restrict__ kmers,       // unique words of query q at kmers[o0 ..)
 	uint32_t* __restrict__ rows,        // row indices at rows[(o0 + i) * NH + h]
@@ -43,10 +57,11 @@ query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ 
 	// same front end as the construction kernels: the tile is staged once, 16 bases at a time become 32 bits
 	// of 2-bit codes + 16 "not ACGT" flags (encode16), and every start position extracts its window from
 	// shared memory (no per-position byte loop)
-	__shared__ __align__(16) uint8_t s_bytes[QK_LOAD];
+	__shared__ uint32_t s_w[QK_LOAD / 4 + 8];          // the aligned 32-bit words that cover the tile
 	__shared__ uint32_t s_codes[QK_LOAD / 16 + 2];
 	__shared__ uint32_t s_bad[QK_LOAD / 32 + 2];
 	__shared__ uint32_t s_nostart[QK_LOAD / 32 + 2];
+	__shared__ unsigned long long s_set[QK_SMEM_SLOTS];
 
 	const uint32_t q = blockIdx.x, tid = threadIdx.x;
 	const uint64_t o0 = offsets[q] - offsets[0], o1 = offsets[q + 1] - offsets[0];
@@ -54,18 +69,34 @@ query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ 
 	if (len < k) return;
 	const uint64_t n_pos = len - k + 1;
 	const uint64_t tsize = 2 * len;
-	uint64_t* tab = table + 2 * o0;
-	const char* s = bases + o0;
+	// a short query is one block's work (its set lives in this block's shared memory): the other blocks of its row leave
+	const bool in_smem = tsize <= (uint64_t)QK_SMEM_SLOTS;
+	if (in_smem && blockIdx.y != 0) return;
+	unsigned long long* tab = in_smem ? s_set : reinterpret_cast<unsigned long long*>(table + 2 * o0);
+	const uint32_t* gw = reinterpret_cast<const uint32_t*>(bases);
+	const uint64_t n_words_total = (n_bases_total + 3) >> 2;
 	for (uint32_t v = tid; v < (uint32_t)(QK_LOAD / 32 + 2); v += QK_THREADS) s_nostart[v] = 0u;
+	if (in_smem) for (uint32_t v = tid; v < (uint32_t)tsize; v += QK_THREADS) s_set[v] = SET_EMPTY;
+	const uint64_t tile_first = in_smem ? 0 : (uint64_t)blockIdx.y * QK_TILE, tile_step = in_smem ? QK_TILE : (uint64_t)gridDim.y * QK_TILE;
 
-	for (uint64_t tile0 = (uint64_t)blockIdx.y * QK_TILE; tile0 < n_pos; tile0 += (uint64_t)gridDim.y * QK_TILE) {
+	for (uint64_t tile0 = tile_first; tile0 < n_pos; tile0 += tile_step) {
 		__syncthreads();                                    // previous tile's readers are done
 		const uint64_t avail = len - tile0;
-		for (uint32_t i = tid; i < (uint32_t)QK_LOAD; i += QK_THREADS) s_bytes[i] = (i < avail) ? (uint8_t)s[tile0 + i] : (uint8_t)'N';
+		// A query starts at any byte: the tile is fetched as whole aligned words (coalesced, all in flight together -- a
+		// byte-wise copy is a chain of dependent round trips) and re-aligned with funnel shifts on the way to encode16.
+		const uint64_t g0 = o0 + tile0, w0 = g0 >> 2;
+		const uint32_t sh = 8u * (uint32_t)(g0 & 3u);
+		for (uint32_t i = tid; i < (uint32_t)(QK_LOAD / 4 + 1); i += QK_THREADS) s_w[i] = (w0 + i < n_words_total) ? ld_nc_u32(gw + w0 + i) : 0u;
 		__syncthreads();
 		for (uint32_t v = tid; v < (uint32_t)(QK_LOAD / 16); v += QK_THREADS) {
 			uint32_t codes, bad16;
-			encode16(*reinterpret_cast<const uint4*>(s_bytes + 16 * v), codes, bad16);
+			const uint32_t* w = s_w + 4 * v;
+			encode16(make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh),
+				__funnelshift_r(w[3], w[4], sh)), codes, bad16);
+			// bases at and beyond the end of the query read as separators
+			const uint64_t first = 16ull * v;
+			if (first >= avail) bad16 = 0xFFFFu;
+			else if (first + 16 > avail) bad16 |= (0xFFFFu << (uint32_t)(avail - first)) & 0xFFFFu;
 			s_codes[v] = codes;
 			reinterpret_cast<uint16_t*>(s_bad)[v] = (uint16_t)bad16;
 		}
@@ -77,9 +108,9 @@ query_kmers_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ 
 		for (uint32_t p = tid; p < (uint32_t)QK_TILE && tile0 + p < n_pos; p += QK_THREADS) {
 			if (!window_ok(s_bad, s_nostart, p, k)) continue;
 			const Canon c = canonical(window_sense(s_codes, p, k), k);
-			uint64_t slot = mix64(c.word) % tsize;
+			uint64_t slot = __umul64hi(mix64(c.word), tsize);      // (a 64-bit remainder costs more than the rest of the loop)
 			for (;;) {
-				const unsigned long long old = atomicCAS((unsigned long long*)(tab + slot), (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
+				const unsigned long long old = atomicCAS(tab + slot, (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
 				if (old == SET_EMPTY) {
 					const uint32_t i = atomicAdd(n_kmers + q, 1u);
 					kmers[o0 + i] = c.word;
@@ -372,7 +403,6 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	if ((rc = grow_db((void**)&db->d_table, &db->table_cap, std::max<uint64_t>(n_bases, 1) * 2 * sizeof(uint64_t)))) return rc;
 	if ((rc = grow_db((void**)&db->d_kmers, &db->kmers_cap, std::max<uint64_t>(n_bases, 1) * sizeof(uint64_t)))) return rc;
 	if ((rc = grow_db((void**)&db->d_rows, &db->rows_cap, std::max<uint64_t>(n_bases, 1) * db->num_hash * sizeof(uint32_t)))) return rc;
-	KWG_CUDA(cudaMemsetAsync(db->d_table, 0xFF, n_bases * 2 * sizeof(uint64_t), db->stream));
 	KWG_CUDA(cudaMemsetAsync(d_nk, 0, (size_t)n_queries * sizeof(uint32_t), db->stream));
 
 	const uint32_t filter_mask = (db->log2_len >= 32) ? 0xFFFFFFFFu : ((1u << db->log2_len) - 1u);
@@ -382,8 +412,10 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	const uint32_t parts = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ceil_div(len_bound, QK_TILE), 1), 256);
 	const dim3 qgrid(n_queries, parts);
 	db->timers.begin(KWG_T_AUX, db->stream);
+	query_table_init_kernel<<<qgrid, 256, 0, db->stream>>>(d_offsets, db->d_table);
+	KWG_LAUNCHED();
 	switch (db->num_hash) {
-#define KWG_CASE(N) case N: query_kmers_kernel<N><<<qgrid, QK_THREADS, 0, db->stream>>>(d_bases, d_offsets, db->k, filter_mask, \
+#define KWG_CASE(N) case N: query_kmers_kernel<N><<<qgrid, QK_THREADS, 0, db->stream>>>(d_bases, n_bases, d_offsets, db->k, filter_mask, \
 		db->d_table, db->d_kmers, db->d_rows, d_nk); break;
 		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
 #undef KWG_CASE
@@ -621,6 +653,7 @@ int kwg_search_counts_dev(kwg_db_t* db, const char* d_bases, const uint64_t* d_o
 	if (!db || !d_bases || !d_offsets || !d_n_query_kmers || !d_counts) return fail(KWG_ERR_INVALID_ARG, "NULL argument");
 	if (count_pitch % 4 || count_pitch < db->n_filters) return fail(KWG_ERR_INVALID_ARG, "count_pitch must be a multiple of 4 and >= n_filters");
 	if (reinterpret_cast<uintptr_t>(d_counts) & 15u) return fail(KWG_ERR_INVALID_ARG, "d_counts must be 16-byte aligned");
+	if (reinterpret_cast<uintptr_t>(d_bases) & 3u) return fail(KWG_ERR_INVALID_ARG, "d_bases must be 4-byte aligned");
 	if (n_queries == 0) return KWG_OK;
 	int rc = select_device(db->device);
 	if (rc) return rc;

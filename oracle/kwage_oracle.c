@@ -261,6 +261,54 @@ uint64_t kwo_raw_insert(const char* bases, const uint64_t* offsets, uint64_t n_r
 /* Bloom parameter search: reference bloom.cpp:10-68 and 72-121.  float/double mixing kept.      */
 /* ------------------------------------------------------------------------------------------ */
 /* returns 0 and fills log2_len / num_hash, or -1 where the reference throws */
+/* ---------------------------------------------------------------------------------------------
+ * k in 33..63 -- PARITY UNPINNED.  The reference stops at k = 32 (word.h:10: a k-mer is one 64-bit Word), so there is no
+ * reference output to check this against; BASELINE.json configs[4] asks for k up to 63 all the same.  What follows is the
+ * reference's rule set carried over to a 128-bit word, nothing else changed: 2 bits per base with the 5' base most
+ * significant (word.h:73-104), any byte other than ACGTacgt ends the current run of valid bases (word.h:98-100), canonical
+ * = min(sense, reverse complement) as an unsigned integer (word.h:163-165), murmur3_x86_32 over the k ASCII bytes of the
+ * canonical k-mer in 5'->3' order, seeds 0..n-1 (hash.cpp:176-234), bit (hash & (2^L - 1)) set LSB first.
+ * For k <= 32 it gives exactly what kwo_raw_insert gives (tests/test_oracle_wide.py), which is as far as pinning can go.
+ * ------------------------------------------------------------------------------------------- */
+typedef unsigned __int128 kwo_u128;
+
+static uint32_t murmur3_wide(kwo_u128 w, uint32_t k, uint32_t seed)
+{
+	uint8_t ascii[64];
+	for (uint32_t i = 0; i < k; ++i) ascii[i] = (uint8_t)"ACGT"[(unsigned)(w >> (2 * (k - 1 - i))) & 3u];
+	return kwo_murmur3_bytes(ascii, k, seed);
+}
+
+uint64_t kwo_raw_insert_wide(const char* bases, const uint64_t* offsets, uint64_t n_reads, uint32_t k,
+	uint32_t num_hash, uint32_t log2_len, uint8_t* bits)
+{
+	const uint64_t mask = (log2_len >= 64) ? ~0ULL : ((1ULL << log2_len) - 1ULL);
+	const kwo_u128 kmask = (k >= 64) ? ~(kwo_u128)0 : ((((kwo_u128)1) << (2 * k)) - 1);
+	uint64_t n = 0;
+	for (uint64_t r = 0; r < n_reads; ++r) {
+		kwo_u128 sense = 0, anti = 0;
+		uint32_t valid = 0;
+		for (uint64_t i = offsets[r]; i < offsets[r + 1]; ++i) {
+			unsigned code;
+			switch (bases[i]) {
+				case 'A': case 'a': code = 0; break;
+				case 'C': case 'c': code = 1; break;
+				case 'G': case 'g': code = 2; break;
+				case 'T': case 't': code = 3; break;
+				default: valid = 0; sense = 0; anti = 0; continue;
+			}
+			sense = ((sense << 2) | code) & kmask;
+			anti = (anti >> 2) | ((kwo_u128)(3u - code) << (2 * (k - 1)));
+			if (++valid >= k) {
+				const kwo_u128 w = sense < anti ? sense : anti;
+				for (uint32_t h = 0; h < num_hash; ++h) set_bit(bits, murmur3_wide(w, k, h) & mask);
+				++n;
+			}
+		}
+	}
+	return n;
+}
+
 int kwo_optimal_bloom_param(uint64_t num_kmer, float p_max, uint32_t min_log2, uint32_t max_log2,
 	uint32_t* log2_len, uint32_t* num_hash)
 {

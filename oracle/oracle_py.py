@@ -47,6 +47,8 @@ def lib():
         L.kwo_crc32.argtypes = [p, u64]
         L.kwo_raw_insert.restype = u64
         L.kwo_raw_insert.argtypes = [p, p, u64, u32, u32, u32, p]
+        L.kwo_raw_insert_wide.restype = u64
+        L.kwo_raw_insert_wide.argtypes = [p, p, u64, u32, u32, u32, p]
         L.kwo_optimal_bloom_param.restype = C.c_int
         L.kwo_optimal_bloom_param.argtypes = [u64, C.c_float, u32, u32, C.POINTER(u32), C.POINTER(u32)]
         L.kwo_approximate_max_kmers.restype = u64
@@ -135,6 +137,16 @@ def raw_insert(bases, offsets, k, num_hash, log2_len, bits=None):
     if bits is None:
         bits = np.zeros(max((1 << log2_len) // 8, 1), dtype=np.uint8)
     n = lib().kwo_raw_insert(_ptr(bases), _ptr(offsets), len(offsets) - 1, k, num_hash, log2_len, _ptr(bits))
+    return bits, n
+
+
+def raw_insert_wide(bases, offsets, k, num_hash, log2_len, bits=None):
+    """k up to 63 on a 128-bit word: PARITY UNPINNED (the reference stops at k = 32, word.h:10); equals raw_insert for k <= 32"""
+    bases = _bytes_arr(bases)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    if bits is None:
+        bits = np.zeros(max((1 << log2_len) // 8, 1), dtype=np.uint8)
+    n = lib().kwo_raw_insert_wide(_ptr(bases), _ptr(offsets), len(offsets) - 1, k, num_hash, log2_len, _ptr(bits))
     return bits, n
 
 

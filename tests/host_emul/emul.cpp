@@ -73,6 +73,55 @@ uint64_t emu_scan(const char* bases, uint64_t n_bases, const uint64_t* offsets, 
 	return n;
 }
 
+// Mirrors kmer_scan_wide_kernel (raw mode, k in 1..63 through the 128-bit helpers): sets bit (hash_h & mask), h < nh, of every
+// valid window.  Returns the number of k-mers.
+uint64_t emu_scan_wide_insert(const char* bases, uint64_t n_bases, const uint64_t* offsets, uint64_t n_reads, uint32_t k,
+	uint32_t nh, uint32_t log2_len, uint8_t* bits)
+{
+	const uint32_t TILE_BASES = 4096, TILE_LOAD = 4096 + 64, TILE_VEC = TILE_LOAD / 16;
+	const uint32_t mask = (log2_len >= 32) ? 0xFFFFFFFFu : ((1u << log2_len) - 1u);
+	std::vector<uint32_t> start_mask(n_bases / 32 + 4, 0);
+	for (uint64_t r = 0; r < n_reads; ++r) {
+		const uint64_t p = offsets[r] - offsets[0];
+		if (p < n_bases) start_mask[p >> 5] |= 1u << (p & 31);
+	}
+	uint64_t n = 0;
+	for (uint64_t t0 = 0; t0 < n_bases; t0 += TILE_BASES) {
+		uint32_t s_codes[TILE_VEC + 4], s_bad[TILE_LOAD / 32 + 3], s_start[TILE_LOAD / 32 + 3];
+		uint16_t* bad16p = reinterpret_cast<uint16_t*>(s_bad);
+		for (uint32_t v = 0; v < TILE_VEC; ++v) {
+			const uint64_t g = t0 + (uint64_t)v * 16;
+			uint32_t codes = 0, bad16 = 0xFFFFu;
+			if (g < n_bases) {
+				uint32_t w[4] = {0, 0, 0, 0};
+				for (uint32_t j = 0; j < 16; ++j) {
+					const uint32_t b = (g + j < n_bases) ? (uint8_t)bases[g + j] : (uint32_t)'N';
+					w[j >> 2] |= b << (8 * (j & 3));
+				}
+				encode16(make_uint4(w[0], w[1], w[2], w[3]), codes, bad16);
+			}
+			s_codes[v] = codes;
+			bad16p[v] = (uint16_t)bad16;
+		}
+		for (uint32_t v = 0; v < TILE_LOAD / 32 + 1; ++v) {
+			const uint64_t w = (t0 >> 5) + v;
+			s_start[v] = (w * 32 < n_bases) ? start_mask[w] : 0u;
+		}
+		for (uint32_t v = TILE_VEC; v < TILE_VEC + 4; ++v) s_codes[v] = 0;
+		s_bad[TILE_LOAD / 32] = 0xFFFFFFFFu; s_bad[TILE_LOAD / 32 + 1] = 0xFFFFFFFFu; s_bad[TILE_LOAD / 32 + 2] = 0xFFFFFFFFu;
+		s_start[TILE_LOAD / 32 + 1] = 0; s_start[TILE_LOAD / 32 + 2] = 0;
+		for (uint32_t p = 0; p < TILE_BASES; ++p) {
+			if (!window_ok_wide(s_bad, s_start, p, k)) continue;
+			const CanonWide c = canonical_wide(window_sense_wide(s_codes, p, k), k);
+			uint32_t h[8];
+			murmur3_multi_wide<8>(c.low, k, h);
+			for (uint32_t s = 0; s < nh; ++s) { const uint32_t b = h[s] & mask; bits[b >> 3] |= (uint8_t)(1u << (b & 7)); }
+			++n;
+		}
+	}
+	return n;
+}
+
 // hash of a word given in the reference layout (as insert_words_kernel / query_kmers_kernel do)
 void emu_hash_word(uint64_t word, uint32_t k, uint32_t* out5)
 {

@@ -28,6 +28,33 @@ def test_raw_insert_bit_exact(k, nh, L):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("k,nh,L", [(33, 3, 20), (40, 2, 14), (47, 5, 22), (48, 8, 18), (62, 1, 12), (63, 3, 29), (63, 4, 30)])
+def test_raw_insert_wide_k_matches_the_wide_restatement(k, nh, L):
+    """k in 33..63 (raw mode only; BASELINE.json configs[4]).  PARITY UNPINNED: the reference stops at k = 32 (word.h:10);
+    the yardstick is oracle kwo_raw_insert_wide, which equals the pinned narrow restatement for k <= 32 and an independent
+    pure-Python statement above (tests/test_oracle_wide.py).  ASCII and packed input, reads across several tiles."""
+    flat = S.mutate(O.gen_reads(2000 + k, 0, 600, 260), 2000 + k, n_rate=211, lower_rate=5)
+    bases, offsets = S.ragged(flat, 2000 + k, 600, 0, 260)
+    exp, n = O.raw_insert_wide(bases, offsets, k, nh, L)
+    assert n > 0
+    packed, mask = capi.pack_2na(bases)
+    with capi.BloomBuilder(k, raw_num_hash=nh, raw_log2_len=L) as b:
+        b.add_reads(bases, offsets)
+        assert b.num_valid() == n
+        assert np.array_equal(b.finalize(), exp)
+        b.reset()
+        b.add_packed(packed, mask, offsets)
+        assert b.num_valid() == n
+        assert np.array_equal(b.finalize(), exp)
+
+
+def test_wide_k_is_refused_outside_raw_mode():
+    with pytest.raises(capi.KwageError):
+        capi.BloomBuilder(33, min_kmer_count=1, log2_count_len=20, log2_max_len=24)
+    with pytest.raises(capi.KwageError):
+        capi.BloomBuilder(64, raw_num_hash=3, raw_log2_len=20)
+
+
 def test_raw_insert_accumulates_over_calls_and_reset():
     k, nh, L = 31, 3, 22
     b1, o1 = S.uniform_reads(7, 0, 3000, 150)
@@ -353,7 +380,9 @@ def test_unsupported_and_bad_arguments_raise():
         capi.BloomBuilder(31, min_kmer_count=16, log2_count_len=20, log2_max_len=24)
     assert e.value.code == capi.KWG_ERR_INVALID_ARG
     with pytest.raises(capi.KwageError):
-        capi.BloomBuilder(33, raw_num_hash=3, raw_log2_len=20)
+        capi.BloomBuilder(64, raw_num_hash=3, raw_log2_len=20)               # raw mode goes up to 63 (an extension), no further
+    with pytest.raises(capi.KwageError):
+        capi.BloomBuilder(33, min_kmer_count=1, log2_count_len=20, log2_max_len=24)      # counting mode: the reference's limit
     with capi.BloomBuilder(31, raw_num_hash=3, raw_log2_len=20) as b:
         with pytest.raises(capi.KwageError):
             b.add_reads(np.zeros(10, np.uint8), np.array([5, 2], np.uint64))      # decreasing offsets

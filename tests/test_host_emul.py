@@ -55,6 +55,23 @@ def test_tile_scan_matches_oracle(E, k):
     assert np.array_equal(hs[sel], exp)
 
 
+@pytest.mark.parametrize("k", [1, 5, 16, 31, 32, 33, 34, 40, 47, 48, 49, 62, 63])
+def test_wide_tile_scan_matches_wide_oracle(E, k):
+    """the 128-bit helpers (window_sense_wide, canonical_wide, murmur3_multi_wide, window_ok_wide) as kmer_scan_wide_kernel drives
+    them; parity beyond k = 32 is unpinned (the reference stops there), the yardstick is oracle kwo_raw_insert_wide"""
+    nh, L = 1 + (k % 8), 16
+    n_reads = 150
+    flat = S.mutate(O.gen_reads(300 + k, 0, n_reads, 200), 300 + k, n_rate=97, lower_rate=5)
+    bases, offsets = S.ragged(flat, 300 + k, n_reads, 0, 200)
+    exp, n = O.raw_insert_wide(bases, offsets, k, nh, L)
+    bits = np.zeros((1 << L) // 8, np.uint8)
+    E.emu_scan_wide_insert.restype = C.c_uint64
+    cnt = E.emu_scan_wide_insert(p(bases), C.c_uint64(len(bases)), p(offsets), C.c_uint64(n_reads), C.c_uint32(k), C.c_uint32(nh),
+                                 C.c_uint32(L), p(bits))
+    assert cnt == n and n > 0
+    assert np.array_equal(bits, exp)
+
+
 def test_hash_of_reference_layout_word(E):
     for seq, k in S.HASH_KAT_INPUTS:
         words, _ = O.canonical_kmers(seq, k)
