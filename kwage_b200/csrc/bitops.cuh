@@ -92,55 +92,30 @@ KWG_DEV uint32_t ascii4(uint32_t c)
 	return __byte_perm(0x54474341u, 0u, s);      // table bytes: 'A','C','G','T'
 }
 
-// 8 bases (16 bits, first base lowest) -> the byte-permute selectors of their ASCII bytes: nibble i = code of base i.
-// The low half selects the first four bases, the high half the next four (__byte_perm reads 16 selector bits).
-KWG_DEV uint32_t ascii_selectors8(uint32_t c16)
-{
-	uint32_t s = (c16 | (c16 << 8)) & 0x00FF00FFu;
-	s = (s | (s << 4)) & 0x0F0F0F0Fu;
-	return (s | (s << 2)) & 0x33333333u;
-}
-
-template <int NH>
-KWG_DEV void murmur3_block(uint32_t k1, uint32_t (&h)[NH])
-{
-	k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u;
-#pragma unroll
-	for (int s = 0; s < NH; ++s) {
-		uint32_t x = h[s] ^ k1;
-		x = rotl32(x, 13);
-		h[s] = x * 5u + 0xe6546b64u;
-	}
-}
-
-template <int NH>
-KWG_DEV void murmur3_tail(uint32_t k1, uint32_t rem, uint32_t (&h)[NH])
-{
-	k1 &= (1u << (8 * rem)) - 1u;
-	k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u;
-#pragma unroll
-	for (int s = 0; s < NH; ++s) h[s] ^= k1;
-}
-
 template <int NH>
 KWG_DEV void murmur3_multi(uint64_t low, uint32_t k, uint32_t (&h)[NH])
 {
+	const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
 #pragma unroll
 	for (int s = 0; s < NH; ++s) h[s] = (uint32_t)s;
-	const uint32_t nblocks = k >> 2, rem = k & 3u;
-	// two 4-byte blocks (8 bases) per step: one selector word serves both byte permutes
-	uint32_t b = 0;
-	for (; b + 2 <= nblocks; b += 2) {
-		const uint32_t sel = ascii_selectors8((uint32_t)low & 0xFFFFu);
-		low >>= 16;
-		murmur3_block<NH>(__byte_perm(0x54474341u, 0u, sel), h);
-		murmur3_block<NH>(__byte_perm(0x54474341u, 0u, sel >> 16), h);
+	const uint32_t nblocks = k >> 2;
+	for (uint32_t i = 0; i < nblocks; ++i) {
+		uint32_t k1 = ascii4((uint32_t)low & 0xFFu);
+		low >>= 8;
+		k1 *= c1; k1 = rotl32(k1, 15); k1 *= c2;
+#pragma unroll
+		for (int s = 0; s < NH; ++s) {
+			uint32_t x = h[s] ^ k1;
+			x = rotl32(x, 13);
+			h[s] = x * 5u + 0xe6546b64u;
+		}
 	}
-	if (b < nblocks || rem) {
-		const uint32_t sel = ascii_selectors8((uint32_t)low & 0xFFFFu);
-		uint32_t k1 = __byte_perm(0x54474341u, 0u, sel);
-		if (b < nblocks) { murmur3_block<NH>(k1, h); k1 = __byte_perm(0x54474341u, 0u, sel >> 16); }
-		if (rem) murmur3_tail<NH>(k1, rem, h);
+	const uint32_t rem = k & 3u;
+	if (rem) {
+		uint32_t k1 = ascii4((uint32_t)low & 0xFFu) & ((1u << (8 * rem)) - 1u);
+		k1 *= c1; k1 = rotl32(k1, 15); k1 *= c2;
+#pragma unroll
+		for (int s = 0; s < NH; ++s) h[s] ^= k1;
 	}
 #pragma unroll
 	for (int s = 0; s < NH; ++s) {
@@ -363,21 +338,27 @@ KWG_DEV CanonWide canonical_wide(Word128 sense, uint32_t k)
 template <int NH>
 KWG_DEV void murmur3_multi_wide(Word128 low, uint32_t k, uint32_t (&h)[NH])
 {
+	const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
 #pragma unroll
 	for (int s = 0; s < NH; ++s) h[s] = (uint32_t)s;
-	const uint32_t nblocks = k >> 2, rem = k & 3u;
-	uint32_t b = 0;
-	for (; b + 2 <= nblocks; b += 2) {
-		const uint32_t sel = ascii_selectors8((uint32_t)low.lo & 0xFFFFu);
-		low = shr128(low, 16);
-		murmur3_block<NH>(__byte_perm(0x54474341u, 0u, sel), h);
-		murmur3_block<NH>(__byte_perm(0x54474341u, 0u, sel >> 16), h);
+	const uint32_t nblocks = k >> 2;
+	for (uint32_t i = 0; i < nblocks; ++i) {
+		uint32_t k1 = ascii4((uint32_t)low.lo & 0xFFu);
+		low = shr128(low, 8);
+		k1 *= c1; k1 = rotl32(k1, 15); k1 *= c2;
+#pragma unroll
+		for (int s = 0; s < NH; ++s) {
+			uint32_t x = h[s] ^ k1;
+			x = rotl32(x, 13);
+			h[s] = x * 5u + 0xe6546b64u;
+		}
 	}
-	if (b < nblocks || rem) {
-		const uint32_t sel = ascii_selectors8((uint32_t)low.lo & 0xFFFFu);
-		uint32_t k1 = __byte_perm(0x54474341u, 0u, sel);
-		if (b < nblocks) { murmur3_block<NH>(k1, h); k1 = __byte_perm(0x54474341u, 0u, sel >> 16); }
-		if (rem) murmur3_tail<NH>(k1, rem, h);
+	const uint32_t rem = k & 3u;
+	if (rem) {
+		uint32_t k1 = ascii4((uint32_t)low.lo & 0xFFu) & ((1u << (8 * rem)) - 1u);
+		k1 *= c1; k1 = rotl32(k1, 15); k1 *= c2;
+#pragma unroll
+		for (int s = 0; s < NH; ++s) h[s] ^= k1;
 	}
 #pragma unroll
 	for (int s = 0; s < NH; ++s) {
