@@ -105,23 +105,42 @@ query_kmers_kernel(const char* __restrict__ bases, uint64_t n_bases_total, const
 			s_bad[QK_LOAD / 32] = 0xFFFFFFFFu; s_bad[QK_LOAD / 32 + 1] = 0xFFFFFFFFu;
 		}
 		__syncthreads();
-		for (uint32_t p = tid; p < (uint32_t)QK_TILE && tile0 + p < n_pos; p += QK_THREADS) {
-			if (!window_ok(s_bad, s_nostart, p, k)) continue;
-			const Canon c = canonical(window_sense(s_codes, p, k), k);
-			uint64_t slot = __umul64hi(mix64(c.word), tsize);      // (a 64-bit remainder costs more than the rest of the loop)
-			for (;;) {
-				const unsigned long long old = atomicCAS(tab + slot, (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
-				if (old == SET_EMPTY) {
-					const uint32_t i = atomicAdd(n_kmers + q, 1u);
+		// One start position per thread and iteration; the trip count is the same for every lane, so that the warp can
+		// vote below.  The probing loop only decides WHO inserted a new k-mer: lanes leave it after different numbers of
+		// probes, and anything heavy inside it (the hashes) would run once per probe with a few lanes each.  New k-mers of
+		// a warp take their list places with one counter update, then every inserting lane hashes its k-mer once.
+		const uint64_t left = n_pos - tile0;
+		const uint32_t n_here = (uint32_t)(left < (uint64_t)QK_TILE ? left : (uint64_t)QK_TILE);
+		const uint32_t lane = tid & 31u;
+		for (uint32_t p0 = 0; p0 < n_here; p0 += QK_THREADS) {
+			const uint32_t p = p0 + tid;
+			bool inserted = false;
+			Canon c;
+			c.word = 0; c.low = 0;
+			if (p < n_here && window_ok(s_bad, s_nostart, p, k)) {
+				c = canonical(window_sense(s_codes, p, k), k);
+				uint64_t slot = __umul64hi(mix64(c.word), tsize);      // (a 64-bit remainder costs more than the rest of the loop)
+				for (;;) {
+					const unsigned long long old = atomicCAS(tab + slot, (unsigned long long)SET_EMPTY, (unsigned long long)c.word);
+					if (old == SET_EMPTY) { inserted = true; break; }
+					if (old == c.word) break;
+					slot = (slot + 1 == tsize) ? 0 : slot + 1;
+				}
+			}
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, inserted);
+			if (m) {
+				const uint32_t leader = (uint32_t)__ffs(m) - 1u;
+				uint32_t base = 0;
+				if (lane == leader) base = atomicAdd(n_kmers + q, (uint32_t)__popc(m));
+				base = __shfl_sync(0xFFFFFFFFu, base, leader);
+				if (inserted) {
+					const uint32_t i = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 					kmers[o0 + i] = c.word;
 					uint32_t h[NH];
 					murmur3_multi<NH>(c.low, k, h);
 #pragma unroll
 					for (int t = 0; t < NH; ++t) rows[(o0 + i) * NH + t] = h[t] & filter_mask;
-					break;
 				}
-				if (old == c.word) break;
-				slot = (slot + 1 == tsize) ? 0 : slot + 1;
 			}
 		}
 	}
