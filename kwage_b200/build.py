@@ -37,6 +37,9 @@ def _stale(out, deps):
 
 
 def build(force=False, verbose=False, ptxas_info=False):
+    # KWG_NVCC_EXTRA: extra nvcc flags for A/B builds of experiment macros (profiles/run/*.sh); forces a rebuild
+    extra = os.environ.get("KWG_NVCC_EXTRA", "").split()
+    force = force or bool(extra)
     os.makedirs(LIB_DIR, exist_ok=True)
     obj_dir = os.path.join(PKG, "build")
     os.makedirs(obj_dir, exist_ok=True)
@@ -48,7 +51,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         obj = os.path.join(obj_dir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + HEADERS):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -384,6 +384,8 @@ ft_append_kernel(const FtAppendParams P)
 			__syncthreads();
 			const uint32_t n_items = *items_n;
 			if (tid == 0) s_misc[1 + ((round + 1u) & 1u)] = 0;
+			// (tried: every other thread takes a flush so that all 32 warps share them -- slower, 2.87 vs 2.71 ms: the flushes
+			// are issue work, not latency, and half-empty warps double it)
 			for (uint32_t i = tid; i < n_items; i += FT_THREADS)
 				ft_flush_bucket(P, s_ring, s_head, s_page, s_tailu, s_npg, &s_misc[0], chain, s_items[i], false);
 			++round;
