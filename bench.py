@@ -418,14 +418,18 @@ def stage_construct(D, args, windows):
         "accessions_in_flight": in_flight,
         "single_stream": {"value": n * kmers * args.steps / sec_single, "ms_per_step": single_ms,
                           "note": "one handle, one stream, one accession at a time (the latency of an accession; the per-kernel times below are taken here)"},
-        "e2e": {"value": n * kmers * e2e_steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
-                "d2h_bytes_per_step": (1 << state["L"]) // 8 + 8, "ms_per_step": sec_e2e / e2e_steps * 1e3, "steps": e2e_steps,
+        # headline e2e: the reads cross PCIe 2-bit packed (kwg_bloom_add_packed; SURVEY.md 8d, config 2: "generated on device or
+        # streamed 2-bit-packed"; NCBI 2na is how the SRA stores them, and what the host layer's parser thread produces); the
+        # ASCII call of the drop-in shim (kwg_bloom_add_reads, 4x the H2D bytes) is reported beside it
+        "e2e": {"value": n * kmers * e2e_steps / sec_e2e_packed, "unit": "kmer_inserts/s", "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1),
+                "d2h_bytes_per_step": (1 << state["L"]) // 8 + 8, "ms_per_step": sec_e2e_packed / e2e_steps * 1e3, "steps": e2e_steps,
                 "workers_per_gpu": n_workers,
-                "packed_input": {"value": n * kmers * e2e_steps / sec_e2e_packed, "ms_per_step": sec_e2e_packed / e2e_steps * 1e3,
-                                 "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1),
-                                 "how": "the same through kwg_bloom_add_packed (2-bit NCBI 2na input, no N mask needed for this input)"},
-                "how": "%d host threads per GPU, one accession at a time each through kwg_bloom_add_reads/num_valid/finalize with pinned "
-                       "host buffers; device time from the first start to the last end over their streams" % n_workers},
+                "ascii_input": {"value": n * kmers * e2e_steps / sec_e2e, "ms_per_step": sec_e2e / e2e_steps * 1e3,
+                                "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
+                                "how": "the same through kwg_bloom_add_reads (one byte per base, what NGS hands the reference)"},
+                "how": "%d host threads per GPU, one accession at a time each through kwg_bloom_add_packed/num_valid/finalize_crc with pinned "
+                       "host buffers (2-bit NCBI 2na reads + 64-bit offsets in, filter bits + crc32 out); device time from the first start "
+                       "to the last end over their streams" % n_workers},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
@@ -590,10 +594,11 @@ def stage_construct_raw(D, args, windows):
     alg = n_bases * (1 + 1 / 8) + 2 * (1 << L) / 8
     return {"metric": "Bloom k-mer inserts/s (raw mode)", "value": n * kmers * steps / sec, "unit": "kmer_inserts/s", "ms_per_step": sec / steps * 1e3,
             "config": {"reads_per_accession": n_reads, "kmer_len": K, "num_hash": h, "log2_filter_len": L},
-            "e2e": {"value": n * kmers * e2e_steps / sec_e2e, "unit": "kmer_inserts/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1),
-                    "d2h_bytes_per_step": (1 << L) // 8 + 4, "ms_per_step": sec_e2e / e2e_steps * 1e3, "workers_per_gpu": n_workers,
-                    "packed_input": {"value": n * kmers * e2e_steps / sec_e2e_packed, "ms_per_step": sec_e2e_packed / e2e_steps * 1e3,
-                                     "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1)}},
+            "e2e": {"value": n * kmers * e2e_steps / sec_e2e_packed, "unit": "kmer_inserts/s", "h2d_bytes_per_step": (n_bases + 3) // 4 + 8 * (n_reads + 1),
+                    "d2h_bytes_per_step": (1 << L) // 8 + 4, "ms_per_step": sec_e2e_packed / e2e_steps * 1e3, "workers_per_gpu": n_workers,
+                    "how": "kwg_bloom_add_packed (2-bit reads) + kwg_bloom_finalize_crc, pinned host buffers",
+                    "ascii_input": {"value": n * kmers * e2e_steps / sec_e2e, "ms_per_step": sec_e2e / e2e_steps * 1e3,
+                                    "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1)}},
             "gpu_launches": int(launches),
             "l2_atomics_per_s": kmers * h / t_scan if t_scan > 0 else None,
             "roofline": {"bound": "hbm", "kernel": "kmer_scan_kernel<RAW,3> (bound by L2 atomics and integer issue, not by HBM: see l2_atomics_per_s)",

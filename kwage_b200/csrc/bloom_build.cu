@@ -437,7 +437,14 @@ static int count_kernels_init()
 	return KWG_OK;
 }
 
-constexpr size_t FEED_CHUNK = 16u << 20;          // bases per piece of the host feed
+constexpr size_t FEED_CHUNK = 16u << 20;          // bases per piece of the host feed, at least
+constexpr size_t FEED_MAX_PIECES = 4;             // ... and at most this many pieces: every piece costs a copy, two event calls and
+                                                  // its launches, and the callers that care about throughput keep several
+                                                  // accessions in flight (whose copies and kernels overlap anyway)
+static inline size_t feed_chunk(uint64_t n_bases)
+{
+	return std::max<size_t>(FEED_CHUNK, (size_t)round_up(ceil_div(n_bases, FEED_MAX_PIECES), 1u << 20));
+}
 
 // Bases that are still on the host when the first kernel is launched: they are copied piece by piece on the copy
 // stream and the scan is launched piece by piece behind them, so that the H2D copy hides behind the kernels.
@@ -524,7 +531,7 @@ static int count_first_touch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, u
 	// than an append that starts before the last piece has arrived.
 	std::vector<FeedPiece> pieces;
 	if (!h_feed) pieces.push_back(FeedPiece{0, n_tiles, 0, 0});
-	else pieces = feed_plan(S.src.n_bases, FEED_CHUNK, HT_POS, HT_LOAD, n_tiles);
+	else pieces = feed_plan(S.src.n_bases, feed_chunk(S.src.n_bases), HT_POS, HT_LOAD, n_tiles);
 	const uint64_t ords = (uint64_t)n_tiles * HT_POS;                          // upper bound of the ordinals
 	const uint32_t append_grid = (uint32_t)std::min<uint64_t>(sms, ceil_div(ords, FT_SUB));
 	const uint32_t n_chains = append_grid;
@@ -672,7 +679,7 @@ static int count_sub_batch(kwg_bloom* b, const ScanParams& S, uint64_t pos0, uin
 		partition_scan_kernel<<<(unsigned)n_tiles, PT_THREADS, partition_smem_bytes(), b->stream>>>(K1);
 		KWG_LAUNCHED();
 	} else {
-		const std::vector<FeedPiece> pieces = feed_plan(S.src.n_bases, FEED_CHUNK, PT_POS, PT_LOAD, (uint32_t)n_tiles);
+		const std::vector<FeedPiece> pieces = feed_plan(S.src.n_bases, feed_chunk(S.src.n_bases), PT_POS, PT_LOAD, (uint32_t)n_tiles);
 		if ((rc = feed_begin(b, pieces.size(), S.src, *h_feed))) return rc;
 		for (size_t l = 0; l < pieces.size(); ++l) {
 			if ((rc = feed_piece(b, l, pieces[l], S.src, *h_feed))) return rc;
@@ -827,7 +834,7 @@ static int add_batch_dev(kwg_bloom* b, const BaseSource& src, const uint64_t* d_
 		// the first pass over the bases runs piece by piece behind the host feed; further window passes find them in HBM
 		std::vector<FeedPiece> pieces;
 		if (feed) {
-			pieces = feed_plan(n_bases, FEED_CHUNK, TILE_BASES, b->k > KWG_MAX_KMER_LEN ? WT_LOAD : TILE_LOAD, n_tiles);
+			pieces = feed_plan(n_bases, feed_chunk(n_bases), TILE_BASES, b->k > KWG_MAX_KMER_LEN ? WT_LOAD : TILE_LOAD, n_tiles);
 			if ((rc = feed_begin(b, pieces.size(), src, *feed))) return rc;
 		} else {
 			pieces.push_back(FeedPiece{0, n_tiles, 0, (size_t)n_bases});

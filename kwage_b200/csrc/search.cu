@@ -13,6 +13,8 @@
 //                        489-503) and compact (query, filter, num_match) in (query, filter) order.
 #include "common.cuh"
 
+#include <mutex>
+
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is loaded with dlopen
 
@@ -459,10 +461,22 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	if (blocks > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "too many (query, column chunk) pairs for one launch");
 	const uint32_t nsub = SC_WARPS * (32 / lpr);
 	const size_t smem = (size_t)nsub * SC_PLANES * lpr * 4 * sizeof(uint32_t);
+	// (the limit is raised when a launch needs more than any launch on this device before it, not on every call -- every
+	// runtime call counts when eight processes drive eight devices through one host -- and it is never lowered: another
+	// handle on the device may still need the larger value)
+	static std::mutex attr_mu;
+	static size_t attr_set[64][KWG_MAX_NUM_HASH + 1];
+	bool raise;
+	{
+		std::lock_guard<std::mutex> lock(attr_mu);
+		size_t& cur = attr_set[db->device & 63][db->num_hash];
+		raise = smem > cur;
+		if (raise) cur = smem;
+	}
 	db->timers.begin(KWG_T_SEARCH, db->stream);
 	switch (db->num_hash) {
 #define KWG_CASE(N) case N: \
-		KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		if (raise) KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		search_count_kernel<N><<<(unsigned)blocks, SC_THREADS, smem, db->stream>>>(P); break;
 		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
 #undef KWG_CASE
