@@ -13,6 +13,10 @@
 //                        489-503) and compact (query, filter, num_match) in (query, filter) order.
 #include "common.cuh"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <mutex>
 
 #include <dlfcn.h>
@@ -996,8 +1000,14 @@ int kwg_search_gather(kwg_db_t* db, kwg_comm_t* c, int root, const char* bases, 
 	NcclApi& N = nccl_api();
 	int rc = select_device(db->device);
 	if (rc) return rc;
+	// KWG_GATHER_TRACE=1: host wall clock of the phases of this call on stderr (scaling studies; read once per process)
+	static const bool trace = getenv("KWG_GATHER_TRACE") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
 	uint64_t mine = 0;
 	if (n_queries && (rc = search_hits_device(db, bases, offsets, n_queries, threshold, n_query_kmers, filter0, &mine))) return rc;
+	const double ms_search = since(t0);
+	const auto t1 = std::chrono::steady_clock::now();
 	const int W = c->n_ranks;
 	// list lengths of all ranks
 	c->h_totals[W] = mine;
@@ -1015,6 +1025,8 @@ int kwg_search_gather(kwg_db_t* db, kwg_comm_t* c, int root, const char* bases, 
 		KWG_CUDA(cudaMalloc(&c->d_gathered, want));
 		c->gathered_cap = want;
 	}
+	const double ms_sizes = since(t1);
+	const auto t2 = std::chrono::steady_clock::now();
 	// the lists themselves, HBM to HBM (3 words per hit)
 	KWG_NCCL(N.GroupStart());
 	if (c->rank == root) {
@@ -1026,6 +1038,7 @@ int kwg_search_gather(kwg_db_t* db, kwg_comm_t* c, int root, const char* bases, 
 	KWG_NCCL(N.GroupEnd());
 	if (c->rank != root || total == 0) {
 		KWG_CUDA(cudaStreamSynchronize(db->stream));      // the list may be overwritten by the next call
+		if (trace) fprintf(stderr, "[kwg gather] rank %d: search %.3f ms, sizes %.3f ms, lists %.3f ms\n", c->rank, ms_search, ms_sizes, since(t2));
 		return KWG_OK;
 	}
 	if (mine) KWG_CUDA(cudaMemcpyAsync(c->d_gathered + off[(size_t)root], db->d_hits, mine * sizeof(kwg_hit_t), cudaMemcpyDeviceToDevice, db->stream));
@@ -1034,9 +1047,13 @@ int kwg_search_gather(kwg_db_t* db, kwg_comm_t* c, int root, const char* bases, 
 	KWG_CUDA(cudaStreamSynchronize(db->stream));
 	kwg_hit_t* h = (kwg_hit_t*)std::malloc((size_t)total * sizeof(kwg_hit_t));
 	if (!h) return fail(KWG_ERR_NO_MEMORY, "host allocation of the hit list failed");
+	const double ms_lists = since(t2);
+	const auto t3 = std::chrono::steady_clock::now();
 	kwg_merge_hits(flat.data(), len.data(), (uint32_t)W, n_queries, h);
 	*hits = h;
 	*n_hits = total;
+	if (trace) fprintf(stderr, "[kwg gather] root %d: search %.3f ms, sizes %.3f ms, lists %.3f ms, merge %.3f ms (%llu hits)\n", c->rank, ms_search, ms_sizes,
+		ms_lists, since(t3), (unsigned long long)total);
 	return KWG_OK;
 }
 
