@@ -797,7 +797,11 @@ void SubjectDatabase::open_files(const std::vector<std::string>& filenames, int 
 		// the file (by several threads: one thread copies out of the page cache at a fraction of the PCIe rate) while
 		// piece n travels to the device.  A region may exceed host memory.
 		const uint64_t n_rows = 1ULL << hdr.log_2_filter_len;
-		const size_t piece_bytes = size_t(64) << 20;
+		// (page-locking costs ~0.5 ms per MiB: small files get small buffers)
+		uint64_t largest = 0;
+		for (size_t f = 0; f < parts.size(); ++f)
+			largest = std::max<uint64_t>(largest, n_rows * (parts[f].hdr.num_filter / 8 + ((parts[f].hdr.num_filter % 8) ? 1 : 0)));
+		const size_t piece_bytes = (size_t)std::min<uint64_t>(uint64_t(64) << 20, std::max<uint64_t>(largest, 4096));
 		PinnedBuffer buf0(piece_bytes), buf1(piece_bytes);
 		uint8_t* bufs[2] = {buf0.data(), buf1.data()};
 		struct Piece { size_t part; uint64_t row, rows; };
