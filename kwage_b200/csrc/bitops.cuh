@@ -268,6 +268,28 @@ KWG_DEV bool window_ok(const uint32_t* bad, const uint32_t* start, uint32_t p, u
 	return (bad_win | start_win) == 0;
 }
 
+// The same test for 32 consecutive start positions at once: bit i of the result <=> the window at position 32 v + i is a
+// k-mer (1 <= k <= 32).  OR over a sliding window by doubling: R_1 = x, R_2n = R_n | R_n >> n, and any length is a sum of
+// powers of two -- ~50 instructions per 32 positions instead of ~12 per position.
+KWG_DEV uint64_t sliding_or64(uint64_t x, uint32_t n)        // bit p of the result = OR of bits p .. p + n - 1 of x (n <= 32: the low 32 bits are exact)
+{
+	uint64_t acc = 0, r = x;
+	uint32_t done = 0;
+#pragma unroll
+	for (int i = 0; i < 6; ++i) {
+		if (n & (1u << i)) { acc |= r >> done; done += 1u << i; }
+		r |= r >> (1u << i);
+	}
+	return acc;
+}
+
+KWG_DEV uint32_t window_ok_word(const uint32_t* bad, const uint32_t* start, uint32_t v, uint32_t k)
+{
+	const uint64_t b = ((uint64_t)bad[v + 1] << 32) | bad[v];
+	const uint64_t s = (((uint64_t)start[v + 1] << 32) | start[v]) >> 1;       // a read start strictly inside: offsets 1 .. k - 1
+	return ~(uint32_t)(sliding_or64(b, k) | sliding_or64(s, k - 1));
+}
+
 KWG_DEV uint64_t window_sense(const uint32_t* codes, uint32_t p, uint32_t k)
 {
 	const uint32_t wi = p >> 4, off = 2 * (p & 15);

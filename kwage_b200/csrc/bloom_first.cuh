@@ -109,6 +109,16 @@ __device__ __forceinline__ void ft_stage_tile(const FtTileParams& P, uint64_t t0
 	}
 }
 
+// valid windows of 32 consecutive start positions of the tile, as a bit mask (positions at and beyond n_pos excluded)
+__device__ __forceinline__ uint32_t ft_ok_word(const FtTileParams& P, const uint32_t* s_bad, const uint32_t* s_start, uint64_t rel0, uint32_t v)
+{
+	const uint64_t first = rel0 + 32ull * v;
+	if (first >= P.n_pos) return 0u;
+	uint32_t ok = window_ok_word(s_bad, s_start, v, P.k);
+	if (first + 32 > P.n_pos) ok &= (1u << (uint32_t)(P.n_pos - first)) - 1u;
+	return ok;
+}
+
 __global__ void __launch_bounds__(HT_THREADS)
 ft_count_kernel(const FtTileParams P)
 {
@@ -118,12 +128,8 @@ ft_count_kernel(const FtTileParams P)
 	const uint64_t rel0 = tile * HT_POS;
 	ft_stage_tile<false>(P, P.pos0 + rel0, nullptr, s_bad, s_start);
 	__syncthreads();
-	uint32_t n = 0;
-#pragma unroll
-	for (int it = 0; it < HT_IT; ++it) {
-		const uint32_t p = it * HT_THREADS + tid;
-		n += ((rel0 + p < P.n_pos) && window_ok(s_bad, s_start, p, P.k)) ? 1u : 0u;
-	}
+	// 32 start positions per thread at once (window_ok_word): the first 64 threads cover the tile
+	uint32_t n = (tid < (uint32_t)(HT_POS / 32)) ? (uint32_t)__popc(ft_ok_word(P, s_bad, s_start, rel0, tid)) : 0u;
 	for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xFFFFFFFFu, n, o);
 	if ((tid & 31) == 0) s_n[tid >> 5] = n;
 	__syncthreads();
@@ -158,20 +164,18 @@ ft_hash_kernel(const FtTileParams P)
 {
 	__shared__ uint32_t s_codes[HT_VEC + 2], s_bad[HT_LOAD / 32 + 2], s_start[HT_LOAD / 32 + 2];
 	__shared__ uint32_t s_pref[HT_POS / 32 + 1];          // valid windows before every 32-position group of the tile
+	__shared__ uint32_t s_okw[HT_POS / 32];               // which windows of the group are k-mers
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t k = P.k;
 	const uint64_t tile = (uint64_t)blockIdx.x + P.tile0;
 	const uint64_t rel0 = tile * HT_POS;
 	ft_stage_tile<true>(P, P.pos0 + rel0, s_codes, s_bad, s_start);
 	__syncthreads();
-	uint32_t okm = 0;                                      // bit it: my window of iteration it is a k-mer
-#pragma unroll
-	for (int it = 0; it < HT_IT; ++it) {
-		const uint32_t p = it * HT_THREADS + tid;
-		const bool ok = (rel0 + p < P.n_pos) && window_ok(s_bad, s_start, p, k);
-		okm |= ok ? 1u << it : 0u;
-		const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-		if (lane == 0) s_pref[it * (HT_THREADS / 32) + warp] = __popc(m);
+	// which windows are k-mers: one word of 32 start positions per thread (window_ok_word); group g = positions 32 g ..
+	if (tid < (uint32_t)(HT_POS / 32)) {
+		const uint32_t ok = ft_ok_word(P, s_bad, s_start, rel0, tid);
+		s_okw[tid] = ok;
+		s_pref[tid] = __popc(ok);
 	}
 	__syncthreads();
 	if (warp == 0) {
@@ -190,8 +194,8 @@ ft_hash_kernel(const FtTileParams P)
 	const uint32_t ord_tile = P.tile_cnt[tile];
 #pragma unroll 1
 	for (uint32_t it = 0; it < (uint32_t)HT_IT; ++it) {
-		const bool ok = (okm >> it) & 1u;
-		const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+		const uint32_t m = s_okw[it * (HT_THREADS / 32) + warp];       // (position it * 256 + tid lies in group it * 8 + warp, bit lane)
+		const bool ok = (m >> lane) & 1u;
 		if (ok) {
 			const uint32_t p = it * HT_THREADS + tid;
 			const uint32_t ord = ord_tile + s_pref[it * (HT_THREADS / 32) + warp] + __popc(m & ((1u << lane) - 1u));

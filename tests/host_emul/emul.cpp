@@ -122,6 +122,17 @@ uint64_t emu_scan_wide_insert(const char* bases, uint64_t n_bases, const uint64_
 	return n;
 }
 
+// window_ok_word against window_ok over a bitmap pair: returns the number of positions where they differ
+uint32_t emu_window_ok_word_check(const uint32_t* bad, const uint32_t* start, uint32_t n_words, uint32_t k)
+{
+	uint32_t diff = 0;
+	for (uint32_t v = 0; v + 2 < n_words; ++v) {
+		const uint32_t w = window_ok_word(bad, start, v, k);
+		for (uint32_t i = 0; i < 32; ++i) diff += (uint32_t)(((w >> i) & 1u) != (window_ok(bad, start, 32 * v + i, k) ? 1u : 0u));
+	}
+	return diff;
+}
+
 // hash of a word given in the reference layout (as insert_words_kernel / query_kmers_kernel do)
 void emu_hash_word(uint64_t word, uint32_t k, uint32_t* out5)
 {

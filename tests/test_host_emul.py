@@ -72,6 +72,16 @@ def test_wide_tile_scan_matches_wide_oracle(E, k):
     assert np.array_equal(bits, exp)
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 15, 16, 17, 21, 30, 31, 32])
+def test_window_ok_word_equals_window_ok(E, k):
+    """the 32-positions-at-once window test (sliding OR by doubling) against the per-position one, on sparse and dense bitmaps"""
+    rng = np.random.default_rng(k)
+    for density in (0.0, 0.002, 0.02, 0.2, 1.0):
+        bad = np.packbits(rng.random(64 * 32) < density, bitorder="little").view(np.uint32).copy()
+        start = np.packbits(rng.random(64 * 32) < density * 0.5 + 0.005, bitorder="little").view(np.uint32).copy()
+        assert E.emu_window_ok_word_check(p(bad), p(start), C.c_uint32(len(bad)), C.c_uint32(k)) == 0
+
+
 def test_hash_of_reference_layout_word(E):
     for seq, k in S.HASH_KAT_INPUTS:
         words, _ = O.canonical_kmers(seq, k)
