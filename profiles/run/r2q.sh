@@ -20,6 +20,6 @@ try:
 except Exception as e:
     print(f, "ERR", e)
 PY
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo "ref rc=$?"; cut -c1-400 gpurun_out/${T}_bench_reference.json
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo "ref rc=$?"; cut -c1-400 gpurun_out/${T}_bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stages construct,construct_c5,construct_raw,crc32,transpose,search > gpurun_out/${T}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"query_kmers_kernel|search_count_kernel" -s 6 -c 2 -o gpurun_out/${T}_search python bench.py --stages search --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_qk.log 2>&1; echo ncu qk rc=$?
