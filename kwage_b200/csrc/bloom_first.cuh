@@ -337,7 +337,9 @@ ft_append_kernel(const FtAppendParams P)
 		// bucket on the flush list; the list is flushed one bucket per thread; again if a ring was full
 		while (true) {
 			uint32_t* items_n = &s_misc[1 + (round & 1u)];
-			// (the ring counters first, then the stores: independent shared-memory operations in flight together)
+			// (the ring counters first, then the stores: independent shared-memory operations in flight together; tried: a
+			// warp-uniform straight-line path for the common case "every lane has four records and no ring is full" --
+			// 2.74 vs 2.69 ms, the per-record predication is not what this kernel waits for)
 			uint32_t old[FT_REC], tl[FT_REC];
 #pragma unroll
 			for (int j = 0; j < FT_REC; ++j) {
