@@ -56,3 +56,30 @@ def test_transpose_bad_arguments():
         capi.transpose([np.zeros(2, np.uint8)], 12)            # not a multiple of 8
     with pytest.raises(capi.KwageError):
         capi.transpose([], 64)
+
+
+def test_transpose_from_several_threads_and_after_releasing_the_caches():
+    """kwg_transpose keeps its streams and staging buffers in a per-device cache behind a per-device lock: callers on
+    one device take turns (and get the right answer each), kwg_release_caches() frees the buffers and the next call
+    simply allocates again"""
+    import threading
+    rng = np.random.default_rng(5)
+    cases = []
+    for t in range(4):
+        n, bits = int(rng.integers(1, 300)), 8 * int(rng.integers(1, 600))
+        filters = [rng.integers(0, 256, bits // 8, dtype=np.uint8) for _ in range(n)]
+        cases.append((filters, bits, O.transpose(filters, bits)))
+    out = [None] * len(cases)
+
+    def work(i):
+        for _ in range(3):
+            out[i] = capi.transpose(cases[i][0], cases[i][1])
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i, (_, _, exp) in enumerate(cases):
+        assert np.array_equal(out[i], exp)
+    capi.lib().kwg_release_caches()
+    assert np.array_equal(capi.transpose(cases[0][0], cases[0][1]), cases[0][2])
