@@ -383,7 +383,12 @@ def stage_construct(D, args, windows):
             "resolve": ("ft_resolve_kernel (stream-ordered first touch against a 1-bit-per-slot tile in shared memory)", capi.T_RESOLVE,
                         24.0 + touched_b + 0.5),
             "finish": ("ft_finish_kernel (invalid bitmap + valid count)", capi.T_SCAN_B, 0.5),
-            "insert_words": ("insert_words_kernel (final filter, L2-resident red.or)", capi.T_INSERT, 8.0 + (1 << state["L"]) / 8 / kmers),
+            # seeds (0,1) and (2,3) of the filter are the fold of the counting tables' touched bitmap (2^lc bits read per table);
+            # only a last odd seed is set from the word list (8 B + 1 validity bit per occurrence)
+            "insert_words": ("fold_touched_kernel (seed pairs out of the touched bitmap) + insert_words_kernel (a last odd seed, L2-resident red.or)",
+                             capi.T_INSERT,
+                             ((state["h"] // 2) * (1 << lc) / 8 + (1 << state["L"]) / 8) / kmers + (8.125 if state["h"] & 1 else 0.0)
+                             if state["L"] <= lc and state["h"] >= 2 else 8.125 + (1 << state["L"]) / 8 / kmers),
         }
     else:
         # two-level radix partition (bloom_count.cuh): a touch record is 8 bytes, four per k-mer: the partition scan writes

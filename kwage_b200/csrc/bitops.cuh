@@ -93,11 +93,11 @@ KWG_DEV uint32_t ascii4(uint32_t c)
 }
 
 template <int NH>
-KWG_DEV void murmur3_multi(uint64_t low, uint32_t k, uint32_t (&h)[NH])
+KWG_DEV void murmur3_multi(uint64_t low, uint32_t k, uint32_t (&h)[NH], uint32_t seed0 = 0)
 {
 	const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
 #pragma unroll
-	for (int s = 0; s < NH; ++s) h[s] = (uint32_t)s;
+	for (int s = 0; s < NH; ++s) h[s] = seed0 + (uint32_t)s;      // seeds seed0 .. seed0 + NH - 1
 	const uint32_t nblocks = k >> 2;
 	for (uint32_t i = 0; i < nblocks; ++i) {
 		uint32_t k1 = ascii4((uint32_t)low & 0xFFu);

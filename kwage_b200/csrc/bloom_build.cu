@@ -233,11 +233,11 @@ __global__ void mark_read_starts_kernel(const uint64_t* __restrict__ offsets, ui
 	if (p < n_bases) atomicOr(start_mask + (p >> 5), 1u << (p & 31));
 }
 
-// finalize (counting mode): set bit (hash_h & mask) for every listed word
+// finalize (counting mode): set bit (hash_h & mask), h = seed0 .. seed0 + NH - 1, for every listed word
 template <int NH>
 __global__ void __launch_bounds__(256)
 insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint32_t k, uint32_t* __restrict__ filter,
-	uint32_t filter_mask, uint32_t win_id, uint32_t n_win, const uint32_t* __restrict__ invalid)
+	uint32_t filter_mask, uint32_t win_id, uint32_t n_win, const uint32_t* __restrict__ invalid, uint32_t seed0)
 {
 	// the word list streams through once (evict first) and must not push the filter out of the L2, where the red.or
 	// of a filter of up to 2^29 bits are served (evict last)
@@ -249,13 +249,38 @@ insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint
 		const uint64_t w = ld_nc_u64_hint(&chunks[i >> LIST_CHUNK_LOG2][i & (LIST_CHUNK - 1)], pol_stream);
 		const uint64_t low = reverse_groups(w, k);
 		uint32_t h[NH];
-		murmur3_multi<NH>(low, k, h);
+		murmur3_multi<NH>(low, k, h, seed0);
 #pragma unroll
 		for (int s = 0; s < NH; ++s) {
 			const uint32_t bit = h[s] & filter_mask;
 			if (n_win == 1 || (bit >> WINDOW_LOG2) == win_id) red_or_hint(filter + (bit >> 5), 1u << (bit & 31), pol_keep);
 		}
 	}
+}
+
+// finalize, min_kmer_count == 1: the filter bits of a PAIR of seeds are the fold of a counting table's touched bitmap.
+//
+// Seeds 2t and 2t + 1 index counting table t (make_bloom.cpp:546-551), and the same hash values masked to the filter
+// length index the filter (make_bloom.cpp:573-577).  With min_kmer_count 1 a slot of table t is non-zero iff some
+// occurrence touched it; the FIRST occurrence to touch a slot read a zero counter there, so it was valid and both of
+// its table-t hashes are in the filter; an occurrence that is not valid found all its slots touched and adds nothing
+// to the bitmap.  Hence { h_s & (2^L - 1) : valid occurrences, s in {2t, 2t+1} } = { slot & (2^L - 1) : touched slots
+// of table t } whenever L <= lc and both seeds of the table are in use: 2^lc bits are read instead of two random
+// read-modify-writes per k-mer occurrence.  A last odd seed (num_hash 3 or 5) still goes through insert_words_kernel.
+// filter word w = OR of the words w + j * 2^(L-5) of every table, j < 2^(lc-L).
+__device__ __forceinline__ uint32_t vec_or(uint32_t a, uint32_t b) { return a | b; }
+__device__ __forceinline__ uint4 vec_or(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+fold_touched_kernel(const V* __restrict__ touched, uint32_t n_tables, uint64_t table_vecs, uint64_t filter_vecs, V* __restrict__ filter)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= filter_vecs) return;
+	V acc = touched[i];
+	for (uint32_t t = 0; t < n_tables; ++t)
+		for (uint64_t j = (t == 0) ? filter_vecs : 0; j < table_vecs; j += filter_vecs) acc = vec_or(acc, touched[t * table_vecs + j + i]);
+	filter[i] = acc;
 }
 
 } // namespace kwg
@@ -275,6 +300,7 @@ struct kwg_bloom {
 	uint64_t* d_dense = nullptr;         // min_count > 1: dense per-bucket copies of the records for the levels >= 1
 	uint32_t* d_dense_len = nullptr;     // [n_buckets] extents, [1] number of buckets without a dense copy, [n_buckets] their list
 	bool touched_dirty = false;          // false: nothing added since create/reset (the bitmap need not be read)
+	bool no_fold = false;                // KWG_NO_FOLD=1: finalize sets every bit from the word list (A/B runs, tests of that path)
 	std::vector<uint64_t*> chunks;
 	uint64_t** d_chunk_table = nullptr;
 	size_t table_cap = 0;
@@ -924,6 +950,7 @@ int kwg_bloom_create(kwg_bloom_t** out, int device, uint32_t kmer_len, uint32_t 
 		b->geom = count_geometry(b->lc);
 		// the one-level partition covers up to 2048 buckets of 2^20 slots; KWG_COUNT_TWO_LEVEL=1 keeps the first design (A/B runs)
 		b->use_ft = min_kmer_count == 1 && b->lc + 1 <= (uint32_t)FT_BUCKET_LOG2 + 11 && !getenv("KWG_COUNT_TWO_LEVEL");
+		b->no_fold = getenv("KWG_NO_FOLD") != nullptr;
 		rc = count_kernels_init();
 		if (rc == KWG_OK) {
 			// two tables of 2^lc slots: one bit each (min count 1: the first batch after create/reset writes every word
@@ -1112,24 +1139,40 @@ int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 	rc = read_counter(b, &n_valid);
 	if (rc) return rc;
 	const size_t bytes = (size_t)1 << (log2_len - 3);
-	KWG_CUDA(cudaMemsetAsync(d_out_bits, 0, bytes, b->stream));
 	const uint64_t n_list = b->n_list_host;
-	if (n_list) {
+	uint32_t* f = reinterpret_cast<uint32_t*>(d_out_bits);
+	// seeds [0, n_fold) come out of the touched bitmap (fold_touched_kernel), the rest out of the word list
+	uint32_t n_fold = 0;
+	if (b->use_ft && b->touched_dirty && n_list && log2_len <= b->lc && !b->no_fold) n_fold = num_hash & ~1u;
+	b->timers.begin(KWG_T_INSERT, b->stream);
+	if (n_fold) {
+		const uint64_t table_words = (uint64_t)1 << (b->lc - 5), filter_words = (uint64_t)1 << (log2_len - 5);
+		if (filter_words >= 4 && (reinterpret_cast<uintptr_t>(d_out_bits) & 15u) == 0) {
+			const uint64_t fv = filter_words / 4;
+			fold_touched_kernel<uint4><<<(unsigned)ceil_div(fv, 256), 256, 0, b->stream>>>(reinterpret_cast<const uint4*>(b->d_touched),
+				n_fold / 2, table_words / 4, fv, reinterpret_cast<uint4*>(f));
+		} else {
+			fold_touched_kernel<uint32_t><<<(unsigned)ceil_div(filter_words, 256), 256, 0, b->stream>>>(b->d_touched,
+				n_fold / 2, table_words, filter_words, f);
+		}
+		KWG_LAUNCHED();
+	} else {
+		KWG_CUDA(cudaMemsetAsync(d_out_bits, 0, bytes, b->stream));
+	}
+	if (n_list && n_fold < num_hash) {
 		const uint32_t mask = (log2_len >= 32) ? 0xFFFFFFFFu : ((1u << log2_len) - 1u);
 		const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n_list, 256), (uint64_t)sm_count(b->device) * 16);
-		uint32_t* f = reinterpret_cast<uint32_t*>(d_out_bits);
-		b->timers.begin(KWG_T_INSERT, b->stream);
-#define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_list, b->k, f, mask, w, n_win, b->use_ft ? b->d_inv : nullptr); break;
+#define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_list, b->k, f, mask, w, n_win, b->use_ft ? b->d_inv : nullptr, n_fold); break;
 		const uint32_t n_win = (log2_len > WINDOW_LOG2) ? 1u << (log2_len - WINDOW_LOG2) : 1u;
 		for (uint32_t w = 0; w < n_win; ++w) {
-			switch (num_hash) {
+			switch (num_hash - n_fold) {
 				KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5)
 			}
 			KWG_LAUNCHED();
 		}
 #undef KWG_CASE
-		b->timers.end(b->stream);
 	}
+	b->timers.end(b->stream);
 	return KWG_OK;
 }
 

@@ -159,6 +159,38 @@ def test_counting_mode_finalize_any_parameters_equals_fold():
     ob.close()
 
 
+@pytest.mark.parametrize("no_fold", [False, True])
+@pytest.mark.parametrize("name,split", [("small_count_filter", 3), ("k15_dups", None), ("ragged_k21", 2)])
+def test_finalize_seed_pairs_from_the_touched_bitmap(name, split, no_fold, monkeypatch):
+    """min_kmer_count 1, first-touch path: finalize takes the seed pairs (0,1) and (2,3) out of the counting tables' touched
+    bitmap when L <= log2_count_len (fold_touched_kernel) and only a last odd seed out of the word list.  Every num_hash,
+    L below / at / above the counting-filter length, accessions added in several calls (the bitmap accumulates), and
+    the path that sets every bit from the word list (KWG_NO_FOLD, read when the handle is created)."""
+    if no_fold:
+        monkeypatch.setenv("KWG_NO_FOLD", "1")
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    lc = O.counting_log2_len(case["num_bp"])
+    lmax = max(case["lmax"], lc + 1)
+    ob = O.Builder(case["k"], 1, lc, lmax)
+    ob.add_reads(bases, offsets)
+    n = len(offsets) - 1
+    cuts = [0, n] if not split else [0] + [n * (i + 1) // split for i in range(split)]
+    with capi.BloomBuilder(case["k"], min_kmer_count=1, log2_count_len=lc, log2_max_len=lmax) as b:
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            if z > a:
+                b.add_reads(bases, offsets[a: z + 1])
+        assert b.num_valid() == ob.num_valid()
+        for L in (5, 6, 11, lc - 1, lc, lc + 1):
+            for h in (1, 2, 3, 4, 5):
+                assert np.array_equal(b.finalize(L, h), ob.finalize(L, h)), (L, h)
+        # an accession without k-mers after a reset: an all-zero filter, not a stale bitmap
+        b.reset()
+        b.add_reads(np.frombuffer(b"ACGTNNACGT", dtype=np.uint8), np.array([0, 10], dtype=np.uint64))
+        assert b.num_valid() == 0 and not b.finalize(12, 4).any()
+    ob.close()
+
+
 def test_filters_beyond_one_l2_window_are_filled_window_by_window():
     # filters of more than 2^29 bits are filled one 64 MiB window per pass (raw scan and counting-mode finalize alike)
     case = dict(S.MAKE_BLOOM_CASES["uniform_k31"])
