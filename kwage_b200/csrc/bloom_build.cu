@@ -268,6 +268,30 @@ insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint
 // of table t } whenever L <= lc and both seeds of the table are in use: 2^lc bits are read instead of two random
 // read-modify-writes per k-mer occurrence.  A last odd seed (num_hash 3 or 5) still goes through insert_words_kernel.
 // filter word w = OR of the words w + j * 2^(L-5) of every table, j < 2^(lc-L).
+// finalize, first-touch path, num_hash 3 with seeds (0,1) folded out of the touched bitmap: seed 2's hash of every entry
+// was kept by ft_hash_kernel behind the words of the list chunk (it is one of the four counting hashes), so the last
+// seed costs one 4-byte load and one red.or per valid occurrence.  Four entries per thread.
+__global__ void __launch_bounds__(256)
+insert_hash_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint32_t* __restrict__ filter,
+	uint32_t filter_mask, uint32_t win_id, uint32_t n_win, const uint32_t* __restrict__ invalid)
+{
+	const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+	for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_words; i += stride) {
+		const uint32_t* h2 = reinterpret_cast<const uint32_t*>(chunks[i >> LIST_CHUNK_LOG2] + LIST_CHUNK);
+		const uint4 v = ld_nc_v4_hint(h2 + (i & (LIST_CHUNK - 1)), pol_stream);      // (the chunk is allocated whole: entries beyond n_words are readable)
+		const uint32_t inv = (invalid[i >> 5] >> (i & 31u)) & 0xFu;
+		const uint32_t h[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			if (i + q < n_words && !((inv >> q) & 1u)) {
+				const uint32_t bit = h[q] & filter_mask;
+				if (n_win == 1 || (bit >> WINDOW_LOG2) == win_id) red_or_hint(filter + (bit >> 5), 1u << (bit & 31), pol_keep);
+			}
+		}
+	}
+}
+
 __device__ __forceinline__ uint32_t vec_or(uint32_t a, uint32_t b) { return a | b; }
 __device__ __forceinline__ uint4 vec_or(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
 
@@ -388,7 +412,8 @@ static int ensure_list_capacity(kwg_bloom* b, uint64_t words)
 	if (need_chunks <= b->chunks.size()) return KWG_OK;
 	while (b->chunks.size() < need_chunks) {
 		uint64_t* c = nullptr;
-		KWG_CUDA(cudaMalloc(&c, LIST_CHUNK * sizeof(uint64_t)));
+		// first-touch path: the chunk's words are followed by seed 2's hash of every entry (insert_hash_kernel)
+		KWG_CUDA(cudaMalloc(&c, LIST_CHUNK * (sizeof(uint64_t) + (b->use_ft ? sizeof(uint32_t) : 0))));
 		b->chunks.push_back(c);
 	}
 	if (b->chunks.size() > b->table_cap) {
@@ -1164,8 +1189,12 @@ int kwg_bloom_finalize_dev(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 		const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(n_list, 256), (uint64_t)sm_count(b->device) * 16);
 #define KWG_CASE(N) case N: insert_words_kernel<N><<<grid, 256, 0, b->stream>>>(b->d_chunk_table, n_list, b->k, f, mask, w, n_win, b->use_ft ? b->d_inv : nullptr, n_fold); break;
 		const uint32_t n_win = (log2_len > WINDOW_LOG2) ? 1u << (log2_len - WINDOW_LOG2) : 1u;
+		const bool kept_hash = b->use_ft && n_fold == 2 && num_hash == 3;      // seed 2 of every entry lies behind the words
 		for (uint32_t w = 0; w < n_win; ++w) {
-			switch (num_hash - n_fold) {
+			if (kept_hash) {
+				const unsigned hgrid = (unsigned)std::min<uint64_t>(ceil_div(n_list, 1024), (uint64_t)sm_count(b->device) * 16);
+				insert_hash_kernel<<<hgrid, 256, 0, b->stream>>>(b->d_chunk_table, n_list, f, mask, w, n_win, b->d_inv);
+			} else switch (num_hash - n_fold) {
 				KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5)
 			}
 			KWG_LAUNCHED();

@@ -210,7 +210,10 @@ ft_hash_kernel(const FtTileParams P)
 			if (v.w == v.z) { v.w = FT_TWIN; atomicAdd(&P.loss[ord >> 3], 1u << ((ord & 7u) << 2)); }
 			P.hm[ord] = v;
 			const uint64_t at = P.list_base + ord;
-			P.list_chunks[at >> FT_LIST_LOG2][at & ((1ull << FT_LIST_LOG2) - 1)] = c.word;
+			uint64_t* chunk = P.list_chunks[at >> FT_LIST_LOG2];
+			chunk[at & ((1ull << FT_LIST_LOG2) - 1)] = c.word;
+			// seed 2's hash, whole: with three hashes it is the one filter bit that does not come out of the touched bitmap
+			reinterpret_cast<uint32_t*>(chunk + (1ull << FT_LIST_LOG2))[at & ((1ull << FT_LIST_LOG2) - 1)] = h[2];
 		}
 	}
 }
