@@ -117,6 +117,17 @@ int kwg_bloom_finalize_crc(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash,
 
 /* Forget everything added so far; keeps the allocations for the next accession. */
 int kwg_bloom_reset(kwg_bloom_t* b);
+
+/* Counting mode.  The reference tests `max_num_kmer < num_kmer` after EVERY fragment and stops there
+ * (make_bloom.cpp:208-214, 246-252, 288-294); a caller that adds fragments in batches keeps that behaviour with
+ * these two: kwg_bloom_checkpoint before a batch that may cross the limit (num_kmer so far + k-mer positions of the
+ * batch > max_num_kmer), and, if kwg_bloom_num_valid then exceeds the limit, kwg_bloom_rollback followed by shorter
+ * prefixes of the batch until the first fragment that crosses it is known: num_kmer, num_bp and the fragment counters
+ * of the progress record are then the reference's.  The checkpoint is the counting-filter state (the two tables:
+ * 2^(lc+1) bits for min_kmer_count 1, 2^lc bytes otherwise) plus the counters; one checkpoint per handle, a later
+ * one replaces it, kwg_bloom_rollback may be called any number of times. */
+int kwg_bloom_checkpoint(kwg_bloom_t* b);
+int kwg_bloom_rollback(kwg_bloom_t* b);
 int kwg_bloom_sync(kwg_bloom_t* b);
 void kwg_bloom_destroy(kwg_bloom_t* b);
 

@@ -77,6 +77,8 @@ def lib():
     L.kwg_bloom_finalize.argtypes = [vp, u32, u32, vp]
     L.kwg_bloom_finalize_dev.argtypes = [vp, u32, u32, vp]
     L.kwg_bloom_reset.argtypes = [vp]
+    L.kwg_bloom_checkpoint.argtypes = [vp]
+    L.kwg_bloom_rollback.argtypes = [vp]
     L.kwg_bloom_sync.argtypes = [vp]
     L.kwg_bloom_destroy.argtypes = [vp]
     L.kwg_bloom_destroy.restype = None
@@ -268,6 +270,12 @@ class BloomBuilder:
 
     def reset(self):
         check(lib().kwg_bloom_reset(self.h))
+
+    def checkpoint(self):
+        check(lib().kwg_bloom_checkpoint(self.h))
+
+    def rollback(self):
+        check(lib().kwg_bloom_rollback(self.h))
 
     def set_timing(self, enable=True):
         check(lib().kwg_bloom_set_timing(self.h, int(enable)))

@@ -292,6 +292,8 @@ insert_hash_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint3
 	}
 }
 
+__global__ void mask_word_kernel(uint32_t* w, uint32_t keep) { *w &= keep; }
+
 __device__ __forceinline__ uint32_t vec_or(uint32_t a, uint32_t b) { return a | b; }
 __device__ __forceinline__ uint4 vec_or(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
 
@@ -373,6 +375,9 @@ struct kwg_bloom {
 	size_t start_cap = 0;
 	uint16_t* d_bad = nullptr;    // packed input: not-a-base mask of the batch
 	size_t bad_cap = 0;
+	// kwg_bloom_checkpoint / kwg_bloom_rollback: the counting state before a batch that may take num_kmer beyond the limit
+	uint8_t* d_ckpt = nullptr; size_t ckpt_cap = 0;
+	struct { bool valid = false, touched_dirty = false; unsigned long long counter[3] = {0, 0, 0}; } ck;
 	uint32_t* d_crc_ws = nullptr; size_t crc_ws_cap = 0;   // kwg_bloom_finalize_crc
 	uint32_t* h_crc = nullptr;                             // pinned
 	KernelTimers timers;
@@ -947,6 +952,7 @@ void kwg_bloom_destroy(kwg_bloom_t* b)
 	if (b->h_counter) cudaFreeHost(b->h_counter);
 	cudaFree(b->d_filter);
 	cudaFree(b->d_crc_ws);
+	cudaFree(b->d_ckpt);
 	if (b->h_crc) cudaFreeHost(b->h_crc);
 	cudaFree(b->d_bases);
 	cudaFree(b->d_offsets);
@@ -1040,6 +1046,61 @@ int kwg_bloom_reset(kwg_bloom_t* b)
 		b->touched_dirty = false;            // the next batch rewrites every word of the touched bitmap
 		if (b->d_cnt) KWG_CUDA(cudaMemsetAsync(b->d_cnt, 0, (size_t)1 << b->lc, b->stream));
 	}
+	return KWG_OK;
+}
+
+// bytes of the state that an added batch changes for good: the touched bitmap (min_kmer_count 1) or the 4-bit counters
+static size_t counting_state_bytes(const kwg_bloom* b)
+{
+	return b->min_count == 1 ? (size_t)1 << (b->lc + 1 - 3) : (size_t)1 << b->lc;
+}
+
+int kwg_bloom_checkpoint(kwg_bloom_t* b)
+{
+	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	if (b->raw) return fail(KWG_ERR_UNSUPPORTED, "raw mode has no k-mer limit to stop at (reference rig bloom_test.cpp)");
+	int rc = select_device(b->device);
+	if (rc) return rc;
+	const size_t bytes = counting_state_bytes(b);
+	b->ck.valid = false;
+	if ((rc = grow((void**)&b->d_ckpt, &b->ckpt_cap, bytes))) return rc;
+	// (min_kmer_count 1 before the first batch: the bitmap holds nothing yet and need not be kept)
+	if (b->min_count > 1 || b->touched_dirty)
+		KWG_CUDA(cudaMemcpyAsync(b->d_ckpt, b->min_count == 1 ? (const void*)b->d_touched : (const void*)b->d_cnt, bytes, cudaMemcpyDeviceToDevice, b->stream));
+	KWG_CUDA(cudaMemcpyAsync(b->h_counter, b->d_counter, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+	KWG_CUDA(cudaStreamSynchronize(b->stream));
+	for (int i = 0; i < 3; ++i) b->ck.counter[i] = b->h_counter[i];
+	b->ck.touched_dirty = b->touched_dirty;
+	b->ck.valid = true;
+	return KWG_OK;
+}
+
+int kwg_bloom_rollback(kwg_bloom_t* b)
+{
+	if (!b) return fail(KWG_ERR_INVALID_ARG, "handle is NULL");
+	if (b->raw || !b->ck.valid) return fail(KWG_ERR_INVALID_ARG, "no checkpoint to go back to");
+	int rc = select_device(b->device);
+	if (rc) return rc;
+	const size_t bytes = counting_state_bytes(b);
+	if (b->min_count > 1 || b->ck.touched_dirty)
+		KWG_CUDA(cudaMemcpyAsync(b->min_count == 1 ? (void*)b->d_touched : (void*)b->d_cnt, b->d_ckpt, bytes, cudaMemcpyDeviceToDevice, b->stream));
+	b->touched_dirty = b->ck.touched_dirty;
+	for (int i = 0; i < 3; ++i) b->h_counter[i] = b->ck.counter[i];
+	KWG_CUDA(cudaMemcpyAsync(b->d_counter, b->h_counter, 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice, b->stream));
+	b->n_valid_host = b->ck.counter[0];
+	b->n_list_host = b->use_ft ? b->ck.counter[2] : b->ck.counter[0];
+	b->n_valid_known = true;
+	if (b->d_inv) {
+		// first-touch path: the occurrences listed since the checkpoint are forgotten, and so are their invalid marks
+		const uint64_t w0 = b->n_list_host >> 5;
+		const uint32_t keep = (1u << (b->n_list_host & 31u)) - 1u;
+		if ((w0 + 1) * 4 <= b->inv_cap) {
+			mask_word_kernel<<<1, 1, 0, b->stream>>>(b->d_inv + w0, keep);
+			KWG_LAUNCHED();
+			KWG_CUDA(cudaMemsetAsync(b->d_inv + w0 + 1, 0, b->inv_cap - (w0 + 1) * 4, b->stream));
+		}
+	}
+	KWG_CUDA(cudaStreamSynchronize(b->stream));
 	return KWG_OK;
 }
 

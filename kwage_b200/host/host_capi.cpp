@@ -48,7 +48,8 @@ int kwh_pack_2na(uint8_t* packed, uint8_t* mask, uint64_t cursor, const char* ba
 // make_bloom_filter() on a reads file; results through plain out-parameters
 int kwh_make_bloom_file(const char* accession, const char* reads_path, uint64_t num_bp, const char* bloom_dir, uint32_t kmer_len,
 	uint32_t min_kmer_count, float p, uint32_t min_log2, uint32_t max_log2, int device,
-	uint64_t* num_kmer, uint32_t* log2_len, uint32_t* num_hash, uint32_t* log2_count_len, char* error, size_t error_cap)
+	uint64_t* num_kmer, uint32_t* log2_len, uint32_t* num_hash, uint32_t* log2_count_len, char* error, size_t error_cap,
+	uint64_t* progress_out /* NULL or [3]: num_bp, curr_read, curr_fragment of the progress record */)
 {
 	MaestroOptions opt;
 	opt.kmer_len = kmer_len; opt.min_kmer_count = min_kmer_count; opt.false_positive_probability = p;
@@ -66,6 +67,7 @@ int kwh_make_bloom_file(const char* accession, const char* reads_path, uint64_t 
 	catch (const char* e) { progress.error = e; }
 	*num_kmer = progress.num_kmer; *log2_len = param.log_2_filter_len; *num_hash = param.num_hash;
 	*log2_count_len = (uint32_t)progress.log_2_counting_filter_len;
+	if (progress_out) { progress_out[0] = progress.num_bp; progress_out[1] = progress.curr_read; progress_out[2] = progress.curr_fragment; }
 	if (error && error_cap) { std::strncpy(error, progress.error.c_str(), error_cap - 1); error[error_cap - 1] = 0; }
 	return status;
 }

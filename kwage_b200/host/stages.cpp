@@ -367,15 +367,43 @@ unsigned char make_bloom_filter(ReadSource& reads, uint64_t num_bp, const SraAcc
 				progress.curr_read += rb->n_fragments;
 				progress.num_read += rb->n_fragments;
 				if (n_reads) {
-					const int rc = kwg_bloom_add_packed(builder, rb->packed.data(), rb->any_bad ? rb->mask.data() : NULL, rb->offsets.data(), n_reads);
-					pipe.release(rb);                 // (the call has copied the batch: the parser may refill it)
-					cuda_check(rc, __FILE__ ":make_bloom_filter: kwg_bloom_add_packed failed");
+					// The reference tests the limit after every fragment (make_bloom.cpp:208,246,288).  A batch can only
+					// cross it if the k-mers so far plus the bases of the batch exceed it: then the counting state is
+					// saved first, and if the limit is crossed the batch is replayed in prefixes until the fragment
+					// that crossed it is known -- num_kmer, num_bp and the fragment counters at the abort are the reference's.
+					const size_t bp_before = progress.num_bp - rb->n_bases, reads_before = progress.curr_read - rb->n_fragments;
+					const bool at_risk = progress.num_kmer + rb->n_bases > max_num_kmer;
+					if (at_risk) cuda_check(kwg_bloom_checkpoint(builder), __FILE__ ":make_bloom_filter: kwg_bloom_checkpoint failed");
+					const uint8_t* mask = rb->any_bad ? rb->mask.data() : NULL;
+					int rc = kwg_bloom_add_packed(builder, rb->packed.data(), mask, rb->offsets.data(), n_reads);
 					uint64_t n = 0;
-					cuda_check(kwg_bloom_num_valid(builder, &n), __FILE__ ":make_bloom_filter: kwg_bloom_num_valid failed");
+					if (rc == KWG_OK) rc = kwg_bloom_num_valid(builder, &n);
+					if (rc == KWG_OK && at_risk && max_num_kmer < n) {
+						// smallest prefix of the batch that crosses the limit: hi reads do, lo reads do not
+						size_t lo = 0, hi = n_reads;
+						uint64_t n_hi = n;
+						while (rc == KWG_OK && hi - lo > 1) {
+							const size_t mid = lo + (hi - lo) / 2;
+							uint64_t n_mid = 0;
+							rc = kwg_bloom_rollback(builder);
+							if (rc == KWG_OK) rc = kwg_bloom_add_packed(builder, rb->packed.data(), mask, rb->offsets.data(), mid);
+							if (rc == KWG_OK) rc = kwg_bloom_num_valid(builder, &n_mid);
+							if (max_num_kmer < n_mid) { hi = mid; n_hi = n_mid; } else lo = mid;
+						}
+						if (rc == KWG_OK) {
+							progress.num_kmer = n_hi;
+							progress.num_bp = bp_before + (rb->offsets[hi] - rb->offsets[0]);
+							progress.curr_read = reads_before + (hi - 1);      // (the read that crossed the limit is not counted as done)
+							progress.curr_fragment = 1;
+							pipe.release(rb);
+							kwg_bloom_destroy(builder);
+							return STATUS_BLOOM_INVALID;
+						}
+					}
+					pipe.release(rb);                 // (the calls have copied the batch: the parser may refill it)
+					cuda_check(rc, __FILE__ ":make_bloom_filter: kwg_bloom_add_packed failed");
 					progress.num_kmer = n;
-					// the reference tests this after every fragment (make_bloom.cpp:208,246,288); per batch
-					// the outcome (STATUS_BLOOM_INVALID) is the same, only num_kmer at the abort differs
-					if (max_num_kmer < progress.num_kmer) {
+					if (max_num_kmer < progress.num_kmer) {       // (not reached: a batch that can cross the limit is at risk)
 						kwg_bloom_destroy(builder);
 						return STATUS_BLOOM_INVALID;
 					}

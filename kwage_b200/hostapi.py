@@ -30,7 +30,7 @@ def lib():
         L.kwh_str_to_accession.argtypes = [cp]
         L.kwh_accession_to_str.argtypes = [u64, cp, C.c_size_t]
         L.kwh_make_bloom_file.argtypes = [cp, cp, u64, cp, u32, u32, f32, u32, u32, i32, C.POINTER(u64), C.POINTER(u32),
-                                          C.POINTER(u32), C.POINTER(u32), cp, C.c_size_t]
+                                          C.POINTER(u32), C.POINTER(u32), cp, C.c_size_t, C.POINTER(u64)]
         L.kwh_write_bloom_file.argtypes = [cp, cp, u32, u32, u32, C.c_void_p]
         L.kwh_build_db.argtypes = [cp, u32, u32, u32, cp, i32]
         L.kwh_merge_db.argtypes = [cp, cp, u64, i32, cp, C.c_size_t]
@@ -70,9 +70,11 @@ def accession_to_str(a):
 def make_bloom_file(accession, reads_path, num_bp, bloom_dir, *, k=31, min_kmer_count=1, p=0.25, min_log2=18, max_log2=32, device=0):
     n, L, h, lc = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
     err = C.create_string_buffer(512)
+    prog = (C.c_uint64 * 3)()
     status = lib().kwh_make_bloom_file(accession.encode(), reads_path.encode(), num_bp, bloom_dir.encode(), k, min_kmer_count, p,
-                                       min_log2, max_log2, device, C.byref(n), C.byref(L), C.byref(h), C.byref(lc), err, 512)
-    return dict(status=status, num_kmer=n.value, log2_len=L.value, num_hash=h.value, log2_count_len=lc.value, error=err.value.decode())
+                                       min_log2, max_log2, device, C.byref(n), C.byref(L), C.byref(h), C.byref(lc), err, 512, prog)
+    return dict(status=status, num_kmer=n.value, log2_len=L.value, num_hash=h.value, log2_count_len=lc.value, error=err.value.decode(),
+                num_bp=prog[0], curr_read=prog[1], curr_fragment=prog[2])
 
 
 def write_bloom_file(path, accession, k, log2_len, num_hash, bits):

@@ -191,6 +191,49 @@ def test_finalize_seed_pairs_from_the_touched_bitmap(name, split, no_fold, monke
     ob.close()
 
 
+@pytest.mark.parametrize("c,name", [(1, "ragged_k21"), (1, "small_count_filter"), (3, "k15_dups")])
+@pytest.mark.parametrize("two_level", [False, True])
+def test_checkpoint_and_rollback_restore_the_counting_state(c, name, two_level, monkeypatch):
+    """kwg_bloom_checkpoint / kwg_bloom_rollback (what the host needs to stop at the fragment that crosses max_num_kmer,
+    make_bloom.cpp:208-214): after a rollback the handle behaves as if the batches since the checkpoint had never been
+    added -- counts and filters equal the oracle's for every continuation, on all three construction paths."""
+    if two_level:
+        monkeypatch.setenv("KWG_COUNT_TWO_LEVEL", "1")
+    case = dict(S.MAKE_BLOOM_CASES[name])
+    bases, offsets = S.make_bloom_reads(case)
+    lc = O.counting_log2_len(case["num_bp"])
+    n = len(offsets) - 1
+    a, z = n // 3, 2 * n // 3
+
+    def oracle(parts):
+        ob = O.Builder(case["k"], c, lc, case["lmax"])
+        for p0, p1 in parts:
+            ob.add_reads(bases, offsets[p0: p1 + 1])
+        out = (ob.num_valid(), ob.finalize(20, 3), ob.finalize(19, 4))
+        ob.close()
+        return out
+
+    with capi.BloomBuilder(case["k"], min_kmer_count=c, log2_count_len=lc, log2_max_len=case["lmax"]) as b:
+        with pytest.raises(capi.KwageError):
+            b.rollback()                                     # nothing to go back to
+        b.checkpoint()                                       # before the first batch
+        b.add_reads(bases, offsets[0: a + 1])
+        b.rollback()
+        assert b.num_valid() == 0 and not b.finalize(12, 2).any()
+        b.add_reads(bases, offsets[0: a + 1])
+        b.checkpoint()
+        b.add_reads(bases, offsets[a: z + 1])
+        n_all = b.num_valid()
+        for cont in ([(a, a + 7)], [(z, n)], [(a, z), (z, n)]):
+            b.rollback()
+            for p0, p1 in cont:
+                b.add_reads(bases, offsets[p0: p1 + 1])
+            exp = oracle([(0, a)] + cont)
+            assert b.num_valid() == exp[0], cont
+            assert np.array_equal(b.finalize(20, 3), exp[1]) and np.array_equal(b.finalize(19, 4), exp[2]), cont
+        assert n_all == oracle([(0, a), (a, z)])[0]
+
+
 def test_filters_beyond_one_l2_window_are_filled_window_by_window():
     # filters of more than 2^29 bits are filled one 64 MiB window per pass (raw scan and counting-mode finalize alike)
     case = dict(S.MAKE_BLOOM_CASES["uniform_k31"])

@@ -44,6 +44,11 @@ def test_make_bloom_filter_writes_the_reference_file(name, tmp_path):
         assert sha_file(out) == g["file_sha256"]          # header, crc32, FilterInfo and bits all identical
     else:
         assert not os.path.exists(str(tmp_path / (g["accession"] + ".bloom")))
+        if g["status"] == 16 and g["num_kmer"]:
+            # STATUS_BLOOM_INVALID: the reference stops at the fragment that takes num_kmer beyond max_num_kmer
+            # (make_bloom.cpp:208-214); the progress record at the abort is the compiled reference's
+            assert (r["num_kmer"], r["num_bp"]) == (g["num_kmer"], g["num_bp"]), r
+            assert (r["curr_read"], r["curr_fragment"]) == (g["num_bp"] // case["read_len"] - 1, 1)
 
 
 @pytest.mark.parametrize("name,batch", [("ragged_k21", 4096), ("ragged_k21", 100), ("min_count_2", 33000), ("uniform_k31", 64)])
