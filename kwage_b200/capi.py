@@ -25,6 +25,7 @@ EXPORTS = [
     "kwg_bloom_create", "kwg_bloom_create_raw", "kwg_bloom_add_reads", "kwg_bloom_add_reads_dev",
     "kwg_bloom_add_packed", "kwg_bloom_add_packed_dev",
     "kwg_bloom_num_valid", "kwg_bloom_finalize", "kwg_bloom_finalize_dev", "kwg_bloom_finalize_crc", "kwg_bloom_reset",
+    "kwg_bloom_checkpoint", "kwg_bloom_rollback",
     "kwg_bloom_sync", "kwg_bloom_destroy", "kwg_bloom_stream",
     "kwg_transpose", "kwg_transpose_dev", "kwg_transpose_crc", "kwg_crc32_dev", "kwg_host_alloc", "kwg_host_free",
     "kwg_merge_slices", "kwg_release_caches", "kwg_db_upload_rows_async", "kwg_db_upload_columns_async",
