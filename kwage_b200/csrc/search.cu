@@ -173,13 +173,22 @@ struct SearchParams {
 	const uint32_t* n_kmers;      // per query
 	uint32_t* counts;             // [q * count_pitch + f]
 	uint64_t count_pitch;         // multiple of 4
+	float threshold;              // EXIT variant: the match threshold of the call (kwage.cpp:349,388)
 };
 
-template <int NH>
+// EXIT: the caller only wants the filters that reach the threshold (kwg_search*), so a block may stop reading rows as
+// soon as no column of its chunk can reach it any more -- the reference's own early exit (kwage.cpp:397,459-482: "even
+// the best matching Bloom filter does not have enough matches"), taken per 4096-column chunk instead of per file.
+// Every substream publishes an upper bound of what it can still contribute to ANY column: the exact maximum of its
+// partial counts over its columns (a descent through the bit planes) plus the k-mers it has not looked at yet.  The
+// bounds only fall, so a stale one is still a bound and no barrier is needed; when their sum is below the count a hit
+// needs, the warp leaves the loop.  The counts of such a chunk are partial -- and below the threshold, which is all
+// hits_kernel asks.  A chunk that holds a hit never stops: its bound is at least the hit's final count.
+template <int NH, bool EXIT>
 __global__ void __launch_bounds__(SC_THREADS, 4)
 search_count_kernel(const SearchParams P)
 {
-	extern __shared__ uint32_t sm_planes[];   // [substream][plane][lanes_per_row * 4]
+	extern __shared__ uint32_t sm_planes[];   // [substream][plane][lanes_per_row * 4], EXIT: + [substream] bounds
 
 	const uint32_t q = blockIdx.x / P.n_chunks;
 	const uint32_t chunk = blockIdx.x % P.n_chunks;
@@ -198,6 +207,15 @@ search_count_kernel(const SearchParams P)
 	const uint32_t words_per_chunk = lpr * 4;               // 32-bit column words handled by this block
 	const uint32_t seg_cap = search_seg_cap(nsub);
 
+	// EXIT: count a hit needs (hits_kernel::is_hit); single-segment queries, at most 32 substreams (one bound per lane)
+	uint32_t need = 0;
+	bool can_exit = false;
+	volatile uint32_t* s_ub = sm_planes + (uint64_t)nsub * SC_PLANES * words_per_chunk;
+	if (EXIT) {
+		need = (P.threshold == 1.0f) ? n : (uint32_t)__fmul_rn(P.threshold, (float)n);
+		can_exit = n <= seg_cap && need > 0 && nsub <= 32;
+	}
+
 	for (uint32_t seg0 = 0; seg0 == 0 || seg0 < n; seg0 += seg_cap) {
 		const uint32_t seg_n = (n > seg0) ? min(seg_cap, n - seg0) : 0u;
 		const uint32_t* rows = P.rows + (o0 + seg0) * NH;
@@ -207,7 +225,14 @@ search_count_kernel(const SearchParams P)
 		for (int i = 0; i < SC_PLANES; ++i) pl[i] = make_uint4(0, 0, 0, 0);
 
 		const uint32_t n_blk = (seg_n + 16 * nsub - 1) / (16 * nsub);
-		if (active) {
+		const uint32_t my_total = (seg_n > sub) ? (seg_n - sub + nsub - 1) / nsub : 0u;      // k-mers of my substream
+		if (EXIT && can_exit) {
+			if (cl == 0) s_ub[sub] = my_total;
+			__syncthreads();
+		}
+		// the first block of 16 after which a bound can fall below `need`: fewer than `need` k-mers are left
+		const uint32_t blk_first = (EXIT && can_exit) ? (seg_n - min(seg_n, need)) / (16 * nsub) : 0xFFFFFFFFu;
+		if (active || (EXIT && can_exit)) {
 #pragma unroll 1
 			for (uint32_t blk = 0; blk < n_blk; ++blk) {
 				uint4 fA = make_uint4(0, 0, 0, 0), eA = make_uint4(0, 0, 0, 0);
@@ -218,7 +243,7 @@ search_count_kernel(const SearchParams P)
 					for (int u = 0; u < 4; ++u) {
 						const uint32_t i = (blk * 16 + quad * 4 + u) * nsub + sub;
 						v[u] = make_uint4(0, 0, 0, 0);
-						if (i < seg_n) {
+						if (i < seg_n && (!EXIT || active)) {
 							const uint32_t* r = rows + (uint64_t)i * NH;
 							uint4 acc = ld_nc_v4(col_ptr + (uint64_t)__ldg(r) * P.row_pitch);
 #pragma unroll
@@ -247,6 +272,25 @@ search_count_kernel(const SearchParams P)
 							}
 						}
 					}
+				}
+				if (EXIT && blk >= blk_first && ((blk - blk_first) & 1u) == 0 && blk + 1 < n_blk) {
+					// (every lane of the warp is here: with can_exit the loop is not predicated on `active`)
+					const uint32_t gmask = (lpr == 32) ? 0xFFFFFFFFu : (((1u << lpr) - 1u) << (lane & ~(lpr - 1u)));
+					uint4 cand = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+					uint32_t mx = 0;
+#pragma unroll
+					for (int p = SC_PLANES - 1; p >= 0; --p) {
+						const uint4 t = and4(cand, pl[p]);
+						const bool some = (__ballot_sync(0xFFFFFFFFu, (t.x | t.y | t.z | t.w) != 0u) & gmask) != 0u;
+						cand.x = some ? t.x : cand.x; cand.y = some ? t.y : cand.y; cand.z = some ? t.z : cand.z; cand.w = some ? t.w : cand.w;
+						mx |= some ? 1u << p : 0u;
+					}
+					if (cl == 0) s_ub[sub] = mx + (my_total - min(my_total, 16u * (blk + 1u)));
+					__syncwarp();
+					uint32_t left = (lane < nsub) ? s_ub[lane] : 0u;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) left += __shfl_xor_sync(0xFFFFFFFFu, left, o);
+					if (left < need) break;
 				}
 			}
 		}
@@ -376,6 +420,7 @@ struct kwg_db {
 	uint64_t row_pitch = 0;
 	uint32_t k = 0, num_hash = 0, log2_len = 0, n_filters = 0;
 	uint32_t n_filters_total = 0, col_begin = 0;   // file geometry (kwg_db_alloc / kwg_db_load)
+	bool no_exit = false;             // KWG_SEARCH_NO_EXIT=1 (read when the handle is created): kwg_search* read every row (A/B runs)
 	// per-call scratch, grown on demand
 	char* d_bases = nullptr;          size_t bases_cap = 0;
 	uint64_t* d_offsets = nullptr;    size_t offsets_cap = 0;
@@ -416,13 +461,15 @@ static int db_common_init(kwg_db* db, int device, uint32_t kmer_len, uint32_t nu
 	int rc = select_device(device);
 	if (rc) return rc;
 	db->device = device; db->k = kmer_len; db->num_hash = num_hash; db->log2_len = log2_len; db->n_filters = n_filters;
+	db->no_exit = getenv("KWG_SEARCH_NO_EXIT") != nullptr;
 	KWG_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
 	return KWG_OK;
 }
 
 // Device-side pipeline shared by every search entry point.  d_bases/d_offsets on the device.
+// exit_threshold > 0: only the filters that reach this threshold matter to the caller (search_count_kernel<NH, true>)
 static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t* d_offsets, uint32_t n_queries,
-	uint64_t n_bases, uint32_t max_query_len, uint32_t* d_nk, uint32_t* d_counts, uint64_t count_pitch)
+	uint64_t n_bases, uint32_t max_query_len, uint32_t* d_nk, uint32_t* d_counts, uint64_t count_pitch, float exit_threshold = 0.0f)
 {
 	int rc;
 	if ((rc = grow_db((void**)&db->d_table, &db->table_cap, std::max<uint64_t>(n_bases, 1) * 2 * sizeof(uint64_t)))) return rc;
@@ -464,24 +511,31 @@ static int search_counts_device(kwg_db* db, const char* d_bases, const uint64_t*
 	const uint64_t blocks = (uint64_t)n_queries * P.n_chunks;
 	if (blocks > 0x7FFFFFFFull) return fail(KWG_ERR_INVALID_ARG, "too many (query, column chunk) pairs for one launch");
 	const uint32_t nsub = SC_WARPS * (32 / lpr);
-	const size_t smem = (size_t)nsub * SC_PLANES * lpr * 4 * sizeof(uint32_t);
+	const bool early = exit_threshold > 0.0f && !db->no_exit;
+	P.threshold = exit_threshold;
+	const size_t smem = (size_t)nsub * SC_PLANES * lpr * 4 * sizeof(uint32_t) + (early ? nsub * sizeof(uint32_t) : 0);
 	// (the limit is raised when a launch needs more than any launch on this device before it, not on every call -- every
 	// runtime call counts when eight processes drive eight devices through one host -- and it is never lowered: another
 	// handle on the device may still need the larger value)
 	static std::mutex attr_mu;
-	static size_t attr_set[64][KWG_MAX_NUM_HASH + 1];
+	static size_t attr_set[64][KWG_MAX_NUM_HASH + 1][2];
 	bool raise;
 	{
 		std::lock_guard<std::mutex> lock(attr_mu);
-		size_t& cur = attr_set[db->device & 63][db->num_hash];
+		size_t& cur = attr_set[db->device & 63][db->num_hash][early ? 1 : 0];
 		raise = smem > cur;
 		if (raise) cur = smem;
 	}
 	db->timers.begin(KWG_T_SEARCH, db->stream);
 	switch (db->num_hash) {
 #define KWG_CASE(N) case N: \
-		if (raise) KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-		search_count_kernel<N><<<(unsigned)blocks, SC_THREADS, smem, db->stream>>>(P); break;
+		if (early) { \
+			if (raise) KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+			search_count_kernel<N, true><<<(unsigned)blocks, SC_THREADS, smem, db->stream>>>(P); \
+		} else { \
+			if (raise) KWG_CUDA(cudaFuncSetAttribute(search_count_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+			search_count_kernel<N, false><<<(unsigned)blocks, SC_THREADS, smem, db->stream>>>(P); \
+		} break;
 		KWG_CASE(1) KWG_CASE(2) KWG_CASE(3) KWG_CASE(4) KWG_CASE(5) KWG_CASE(6) KWG_CASE(7) KWG_CASE(8)
 #undef KWG_CASE
 	}
@@ -752,7 +806,7 @@ static int search_hits_device(kwg_db* db, const char* bases, const uint64_t* off
 		if ((rc = grow_db((void**)&db->d_counts, &db->counts_cap, (size_t)nq * pitch * sizeof(uint32_t)))) return rc;
 		if ((rc = grow_db((void**)&db->d_hit_count, &db->hit_count_cap, (size_t)nq * sizeof(uint32_t)))) return rc;
 		if ((rc = grow_db((void**)&db->d_hit_base, &db->hit_base_cap, (size_t)nq * sizeof(uint64_t)))) return rc;
-		if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, nq, n_bases, max_len, db->d_nk, db->d_counts, pitch))) return rc;
+		if ((rc = search_counts_device(db, db->d_bases, db->d_offsets, nq, n_bases, max_len, db->d_nk, db->d_counts, pitch, threshold))) return rc;
 
 		const unsigned hgrid = (unsigned)ceil_div((uint64_t)nq * 32, 256);
 		db->timers.begin(KWG_T_HITS, db->stream);

@@ -161,3 +161,53 @@ def test_files_side_by_side_in_one_slab_search_like_one_database(widths):
     with capi.Database.alloc(k, h, L, total) as slab:
         with pytest.raises(capi.KwageError):
             slab.upload_columns(total - 2, 5, 0, np.zeros((4, 1), np.uint8))    # column range outside the slab
+
+
+@pytest.mark.parametrize("n_filters", [300, 600, 1100, 4100, 8200])
+def test_search_stops_reading_a_chunk_that_cannot_reach_the_threshold(n_filters, monkeypatch):
+    """kwg_search reads the rows of a (query, 4096-column chunk) only as long as some column of the chunk can still reach
+    the threshold (search_count_kernel<NH, true>; the reference's early exit, kwage.cpp:397,459-482).  The hit lists must
+    be the reference's whatever stops where: columns planted with 30 .. 100 % of a query's k-mers around every threshold,
+    over a random background, chunks with and without a hit, slabs of 8 / 16 / 32 lanes per row and one (300 filters) that
+    is too narrow for the early exit; KWG_SEARCH_NO_EXIT (every row is read) gives the same lists."""
+    k, h, L = 31, 3, 13
+    rng = np.random.default_rng(n_filters)
+    row = (n_filters + 7) // 8
+    slices = rng.integers(0, 256, ((1 << L), row), dtype=np.uint8) & rng.integers(0, 256, ((1 << L), row), dtype=np.uint8)
+    seqs = [bytes(O.gen_reads(77, i, 1, ln)).decode() for i, ln in enumerate([1000, 1000, 400, 2200, 95, 1000, 31, 20])]
+    fracs = [0.3, 0.45, 0.5, 0.55, 0.75, 0.97, 1.0]
+    planted = {}
+    for qi, s in enumerate(seqs):
+        words = O.query_kmers(s, k)
+        n = len(words)
+        if n == 0:
+            continue
+        for j, f in enumerate(fracs):
+            c = int(rng.integers(0, n_filters))
+            m = min(n, int(np.ceil(f * n)))
+            # the LAST m k-mers of the query (the reference's worst case: no match early, all matches late) or a random subset
+            pick = range(n - m, n) if (qi + j) % 2 == 0 else rng.choice(n, m, replace=False)
+            for i in pick:
+                for sd in range(h):
+                    r = O.murmur3_word(int(words[i]), k, sd) & ((1 << L) - 1)
+                    slices[r, c >> 3] |= np.uint8(1 << (c & 7))
+            planted[(qi, c)] = f
+    if n_filters % 8:
+        slices[:, -1] &= (1 << (n_filters % 8)) - 1
+    results = {}
+    for no_exit in (False, True):
+        if no_exit:
+            monkeypatch.setenv("KWG_SEARCH_NO_EXIT", "1")
+        with capi.Database.load(slices, k, h, L, n_filters) as db:
+            for t in (0.3, 0.5, 0.75, 1.0):
+                hits, nk = db.search(seqs, t)
+                got = hits_by_query(hits)
+                if not no_exit:
+                    for qi, s in enumerate(seqs):
+                        hf, hm, _ = O.search_matches(slices, n_filters, L, h, k, s, t)
+                        exp = sorted((int(f), int(c)) for f, c in zip(hf, hm))
+                        assert sorted(got.get(qi, [])) == exp, (n_filters, t, qi)
+                    assert any(got.values()), (n_filters, t)
+                results.setdefault(t, []).append(got)
+    for t, (a, b) in results.items():
+        assert a == b, t
