@@ -738,7 +738,12 @@ def stage_search(D, args, windows):
                        "unique_query_kmers": n_kmers},
             "e2e": {"value": n * tests * steps / sec_e2e, "unit": "tests/s", "h2d_bytes_per_step": nq * qlen + 8 * (nq + 1), "d2h_bytes_per_step": 12 * n_hits[0] + 4 * nq,
                     "threshold": 0.5, "hits": n_hits[0], "hits_expected_at_least": n * n_planted * len(plant_cols),
-XX: {"bound": "hbm", "kernel": "search_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "planted": "%d of %d queries carry %d bp whose k-mers are inserted into columns %s of every slab" % (n_planted, nq, PLANT, plant_cols),
+                    "early_exit": "off (KWG_SEARCH_NO_EXIT)" if os.environ.get("KWG_SEARCH_NO_EXIT") else
+                                  "kwg_search stops reading the rows of a (query, 4096-column chunk) once no column of it can reach the threshold "
+                                  "(the reference's early exit, kwage.cpp:397,459-482); tests/s counts the nominal filter x k-mer pairs; "
+                                  "`value` (kwg_search_counts_dev) reads every row"},
+            "roofline": {"bound": "hbm", "kernel": "search_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC.get("search_count_kernel") if (F, L, nq, qlen) == (8192, 26, 10000, 1000) else None,
                          "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "kernel_ms": t_k * 1e3, "share_of_step": t_k * 1e3 / (sec / steps * 1e3),
                          "algorithmic_bytes": alg_bytes},
