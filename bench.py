@@ -378,16 +378,16 @@ def stage_construct(D, args, windows):
         # and read once by the insert
         alg = {
             "hash": ("ft_count_kernel + ft_scan_kernel + ft_hash_kernel (encode, canonical k-mer, 4 hashes by dense ordinal)", capi.T_SCAN_A,
-                     2 * ascii_b + 16.0 + 8.0),
+                     2 * ascii_b + 16.0 + 8.0 + 4.0),        # + seed 2's hash, kept behind the words of the list
             "append": ("ft_append_kernel (one-level partition: ring-buffered append into page chains)", capi.T_REGROUP, 16.0 + 24.0),
             "resolve": ("ft_resolve_kernel (stream-ordered first touch against a 1-bit-per-slot tile in shared memory)", capi.T_RESOLVE,
                         24.0 + touched_b + 0.5),
             "finish": ("ft_finish_kernel (invalid bitmap + valid count)", capi.T_SCAN_B, 0.5),
             # seeds (0,1) and (2,3) of the filter are the fold of the counting tables' touched bitmap (2^lc bits read per table);
-            # only a last odd seed is set from the word list (8 B + 1 validity bit per occurrence)
+            # only a last odd seed is set per occurrence: from its kept hash (three hashes: 4 B + 1 validity bit) or from the word (8 B + 1 bit)
             "insert_words": ("fold_touched_kernel (seed pairs out of the touched bitmap) + insert_words_kernel (a last odd seed, L2-resident red.or)",
                              capi.T_INSERT,
-                             ((state["h"] // 2) * (1 << lc) / 8 + (1 << state["L"]) / 8) / kmers + (8.125 if state["h"] & 1 else 0.0)
+                             ((state["h"] // 2) * (1 << lc) / 8 + (1 << state["L"]) / 8) / kmers + ((4.125 if state["h"] == 3 else 8.125) if state["h"] & 1 else 0.0)
                              if state["L"] <= lc and state["h"] >= 2 else 8.125 + (1 << state["L"]) / 8 / kmers),
         }
     else:
@@ -454,8 +454,9 @@ def stage_construct(D, args, windows):
                                          "achieved": round(kmers * (576.0 + READ_LEN / (READ_LEN - K + 1)) / (step_ms / 1e3) / 1e9, 1),
                                          "frac": kmers * (576.0 + READ_LEN / (READ_LEN - K + 1)) / (step_ms / 1e3) / 1e9 / peak},
                      "note": "achieved = algorithmic bytes of this kernel / its mean duration (CUDA events on the handle's stream, single-stream pass); "
-                             "the first-touch pipeline moves 103 B per k-mer occurrence where round 1's radix pipeline moved 155 B, so the same "
-                             "time reads as a lower fraction: compare ms_per_step"},
+                             "the first-touch pipeline moves ~104 B per k-mer occurrence where round 1's radix pipeline moved 155 B and SURVEY 8d's "
+                             "sector read-modify-write model 577 B, so less time reads as a lower fraction: compare ms_per_step; none of its "
+                             "kernels is HBM-bound (instruction issue, shared-memory pipe, L2 atomics: profiles/r3final_ncu_full_construct.md)"},
         "kernel_ms_per_step": kernels,
         "kernels": per_kernel,
         "result": {"num_valid_kmers": state["n_valid"], "log2_filter_len": state["L"], "num_hash": state["h"], "log2_counting_filter_len": lc,
