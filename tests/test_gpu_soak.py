@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("script,budget,seed", [("stress_levels.py", 20, 101), ("stress_other.py", 15, 102), ("stress_medium.py", 25, 103),
-                                                ("stress_thresholds.py", 20, 104), ("stress_first_touch.py", 30, 105)])
+                                                ("stress_thresholds.py", 20, 104), ("stress_first_touch.py", 30, 105), ("stress_search_exit.py", 20, 106)])
 def test_randomised_soak(script, budget, seed):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "soak", script), str(budget), str(seed)],
                        capture_output=True, text=True, timeout=600)
