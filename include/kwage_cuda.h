@@ -107,6 +107,10 @@ int kwg_bloom_num_valid(kwg_bloom_t* b, uint64_t* n);
 
 /* Counting mode: build the final filter for the parameters the host chose with
  * optimal_bloom_param(); identical to folding valid_bits[h < num_hash] (make_bloom.cpp:337-354).
+ * (min_kmer_count 1, log2_len <= log2_count_len: the bits of the seed pairs (0,1) and (2,3) are taken from the
+ * counting tables themselves -- a slot is non-zero iff a valid k-mer put one of its two table hashes there,
+ * make_bloom.cpp:546-601 -- and only a last odd seed is set k-mer by k-mer; KWG_NO_FOLD=1 in the environment when the
+ * handle is created: every seed is.)
  * Raw mode: log2_len/num_hash must equal the creation values.  out_bits: 2^log2_len/8 bytes.
  * May be called more than once (e.g. with different parameters). */
 int kwg_bloom_finalize(kwg_bloom_t* b, uint32_t log2_len, uint32_t num_hash, uint8_t* out_bits);
@@ -232,7 +236,12 @@ void kwg_db_unload(kwg_db_t* db);
  * n_query_kmers[q] (may be NULL) receives the number of unique canonical k-mers of query q
  * (kwage.cpp:368).  threshold in (0,1] with the reference's float arithmetic (kwage.cpp:349,388):
  * 1.0f -> every k-mer must match; otherwise num_match >= (unsigned)(threshold * n).
- * *hits is allocated by the library (release with kwg_free_hits), ordered by (query, filter). */
+ * *hits is allocated by the library (release with kwg_free_hits), ordered by (query, filter).
+ * Like the reference (kwage.cpp:397,459-482: "even the best matching Bloom filter does not have enough matches")
+ * the thresholded calls -- kwg_search, kwg_search_ptrs, kwg_search_hits_dev, kwg_search_gather -- stop reading the
+ * slices of a query once no filter can reach the threshold any more (decided per chunk of 4096 filter columns); the
+ * hit list is the same either way and every hit carries its full num_match.  kwg_search_counts* always read every
+ * slice.  KWG_SEARCH_NO_EXIT=1 in the environment when the handle is created: the thresholded calls do too. */
 int kwg_search(kwg_db_t* db, const char* bases, const uint64_t* offsets, uint32_t n_queries, float threshold,
 	uint32_t* n_query_kmers, kwg_hit_t** hits, uint64_t* n_hits);
 /* Same with one pointer per query (the shape search() is called with, kwage.cpp:119,137). */
