@@ -223,6 +223,29 @@ KWG_DEV uint32_t search_seg_cap(uint32_t nsub)
 	const uint32_t c = nsub * SC_SUB_CAP;
 	return c < SC_SEG_CAP ? c : SC_SEG_CAP;
 }
+// ---- early exit of the thresholded search (search_count_kernel<NH, true>; shared with the host emulation, tests/host_emul)
+// k-mers of a segment of seg_n that substream `sub` of nsub looks at (k-mer i goes to substream i % nsub)
+KWG_DEV uint32_t search_sub_total(uint32_t seg_n, uint32_t sub, uint32_t nsub)
+{
+	return seg_n > sub ? (seg_n - sub + nsub - 1u) / nsub : 0u;
+}
+// ... of which it has not looked at yet after its block `blk` of 16
+KWG_DEV uint32_t search_sub_left(uint32_t sub_total, uint32_t blk)
+{
+	const uint32_t done = 16u * (blk + 1u);
+	return sub_total > done ? sub_total - done : 0u;
+}
+// the first block after which the bounds can fall below `need`: fewer than `need` k-mers of the segment are left
+KWG_DEV uint32_t search_exit_first_blk(uint32_t seg_n, uint32_t need, uint32_t nsub)
+{
+	return (seg_n - (seg_n < need ? seg_n : need)) / (16u * nsub);
+}
+// bounds are refreshed after every second block from there on (not after the last: nothing is left to save)
+KWG_DEV bool search_exit_check_at(uint32_t blk, uint32_t blk_first, uint32_t n_blk)
+{
+	return blk >= blk_first && ((blk - blk_first) & 1u) == 0u && blk + 1u < n_blk;
+}
+
 // total += x, where x has P planes and total has 16 (counts stay below 2^16 per segment)
 template <int P>
 KWG_DEV void bitsliced_add(uint32_t (&tot)[16], const uint32_t (&x)[P])

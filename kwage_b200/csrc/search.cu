@@ -225,13 +225,13 @@ search_count_kernel(const SearchParams P)
 		for (int i = 0; i < SC_PLANES; ++i) pl[i] = make_uint4(0, 0, 0, 0);
 
 		const uint32_t n_blk = (seg_n + 16 * nsub - 1) / (16 * nsub);
-		const uint32_t my_total = (seg_n > sub) ? (seg_n - sub + nsub - 1) / nsub : 0u;      // k-mers of my substream
+		const uint32_t my_total = search_sub_total(seg_n, sub, nsub);                       // k-mers of my substream
 		if (EXIT && can_exit) {
 			if (cl == 0) s_ub[sub] = my_total;
 			__syncthreads();
 		}
 		// the first block of 16 after which a bound can fall below `need`: fewer than `need` k-mers are left
-		const uint32_t blk_first = (EXIT && can_exit) ? (seg_n - min(seg_n, need)) / (16 * nsub) : 0xFFFFFFFFu;
+		const uint32_t blk_first = (EXIT && can_exit) ? search_exit_first_blk(seg_n, need, nsub) : 0xFFFFFFFFu;
 		if (active || (EXIT && can_exit)) {
 #pragma unroll 1
 			for (uint32_t blk = 0; blk < n_blk; ++blk) {
@@ -273,7 +273,7 @@ search_count_kernel(const SearchParams P)
 						}
 					}
 				}
-				if (EXIT && blk >= blk_first && ((blk - blk_first) & 1u) == 0 && blk + 1 < n_blk) {
+				if (EXIT && search_exit_check_at(blk, blk_first, n_blk)) {
 					// (every lane of the warp is here: with can_exit the loop is not predicated on `active`)
 					const uint32_t gmask = (lpr == 32) ? 0xFFFFFFFFu : (((1u << lpr) - 1u) << (lane & ~(lpr - 1u)));
 					uint4 cand = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -285,7 +285,7 @@ search_count_kernel(const SearchParams P)
 						cand.x = some ? t.x : cand.x; cand.y = some ? t.y : cand.y; cand.z = some ? t.z : cand.z; cand.w = some ? t.w : cand.w;
 						mx |= some ? 1u << p : 0u;
 					}
-					if (cl == 0) s_ub[sub] = mx + (my_total - min(my_total, 16u * (blk + 1u)));
+					if (cl == 0) s_ub[sub] = mx + search_sub_left(my_total, blk);
 					__syncwarp();
 					uint32_t left = (lane < nsub) ? s_ub[lane] : 0u;
 #pragma unroll

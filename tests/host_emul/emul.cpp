@@ -219,6 +219,97 @@ void emu_count128(const uint32_t* vecs_all /* n x 4 */, uint32_t n_all, uint32_t
 	}
 }
 
+// Mirrors the early exit of search_count_kernel<NH, true> for a chunk of `n_lanes` 128-column lanes (all of them active):
+// the substreams run as independent workers that take turns in the order `order` (entry = substream; every entry lets
+// that substream do its next block of 16), publish `exact maximum of my partial counts over the chunk's columns + k-mers I
+// have not looked at` after the blocks search_exit_check_at() names, read the bounds the others published last (possibly
+// stale), and stop once the sum is below `need`.  Returns the number of substreams that stopped early; counts (n_lanes x
+// 128) are what the kernel would hand to hits_kernel: full counts when nobody stopped, partial ones otherwise.
+uint32_t emu_count_exit(const uint32_t* vecs /* n x n_lanes x 4 */, uint32_t n, uint32_t n_lanes, uint32_t nsub, uint32_t need,
+	const uint32_t* order, uint32_t n_order, uint32_t* counts)
+{
+	const int LOW = 4, UP = 6, PL = LOW + UP;
+	const uint32_t n_blk = (n + 16 * nsub - 1) / (16 * nsub);
+	const uint32_t blk_first = search_exit_first_blk(n, need, nsub);
+	std::vector<uint4> pl((size_t)nsub * n_lanes * PL, make_uint4(0, 0, 0, 0));
+	std::vector<uint32_t> ub(nsub), next_blk(nsub, 0), stopped(nsub, 0);
+	for (uint32_t s = 0; s < nsub; ++s) ub[s] = search_sub_total(n, s, nsub);
+	uint32_t n_stopped = 0;
+	auto step = [&](uint32_t sub) {
+		if (stopped[sub] || next_blk[sub] >= n_blk) return;
+		const uint32_t blk = next_blk[sub]++;
+		for (uint32_t lane = 0; lane < n_lanes; ++lane) {
+			uint4* P = &pl[((size_t)sub * n_lanes + lane) * PL];
+			uint4 fA = make_uint4(0, 0, 0, 0), eA = make_uint4(0, 0, 0, 0);
+			for (int quad = 0; quad < 4; ++quad) {
+				uint4 v[4];
+				for (int u = 0; u < 4; ++u) {
+					const uint32_t i = (blk * 16 + quad * 4 + u) * nsub + sub;
+					v[u] = make_uint4(0, 0, 0, 0);
+					if (i < n) { const uint32_t* q = vecs + ((size_t)i * n_lanes + lane) * 4; v[u] = make_uint4(q[0], q[1], q[2], q[3]); }
+				}
+				uint4 tA, tB, f;
+				csa(P[0], tA, v[0], v[1]);
+				csa(P[0], tB, v[2], v[3]);
+				csa(P[1], f, tA, tB);
+				if (quad == 0 || quad == 2) fA = f;
+				else {
+					uint4 e;
+					csa(P[2], e, fA, f);
+					if (quad == 1) eA = e;
+					else {
+						uint4 c16;
+						csa(P[3], c16, eA, e);
+						for (int up = LOW; up < PL; ++up) {
+							const uint4 t = and4(P[up], c16);
+							P[up].x ^= c16.x; P[up].y ^= c16.y; P[up].z ^= c16.z; P[up].w ^= c16.w;
+							c16 = t;
+						}
+					}
+				}
+			}
+		}
+		if (!search_exit_check_at(blk, blk_first, n_blk)) return;
+		// exact maximum over the chunk's columns: descent through the planes, the lanes of the substream decide together
+		std::vector<uint4> cand(n_lanes, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+		uint32_t mx = 0;
+		for (int p = PL - 1; p >= 0; --p) {
+			bool some = false;
+			std::vector<uint4> t(n_lanes);
+			for (uint32_t lane = 0; lane < n_lanes; ++lane) {
+				t[lane] = and4(cand[lane], pl[((size_t)sub * n_lanes + lane) * PL + p]);
+				some = some || (t[lane].x | t[lane].y | t[lane].z | t[lane].w) != 0u;
+			}
+			if (some) { cand = t; mx |= 1u << p; }
+		}
+		ub[sub] = mx + search_sub_left(search_sub_total(n, sub, nsub), blk);
+		uint32_t left = 0;
+		for (uint32_t s2 = 0; s2 < nsub; ++s2) left += ub[s2];
+		if (left < need) { stopped[sub] = 1; ++n_stopped; }
+	};
+	for (uint32_t o = 0; o < n_order; ++o) step(order[o] % nsub);
+	for (uint32_t sub = 0; sub < nsub; ++sub) while (!stopped[sub] && next_blk[sub] < n_blk) step(sub);   // whoever is not done finishes
+	for (uint32_t lane = 0; lane < n_lanes; ++lane)
+		for (uint32_t w = 0; w < 4; ++w) {
+			uint32_t tot[16];
+			for (int i = 0; i < 16; ++i) tot[i] = 0;
+			for (uint32_t s2 = 0; s2 < nsub; ++s2) {
+				uint32_t x[PL];
+				for (int i = 0; i < PL; ++i) {
+					const uint4 q = pl[((size_t)s2 * n_lanes + lane) * PL + i];
+					x[i] = w == 0 ? q.x : w == 1 ? q.y : w == 2 ? q.z : q.w;
+				}
+				bitsliced_add<PL>(tot, x);
+			}
+			for (int nb = 0; nb < 8; ++nb) {
+				const uint4 c = expand_counts4(tot, nb);
+				uint32_t* o = counts + (size_t)lane * 128 + w * 32 + nb * 4;
+				o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w;
+			}
+		}
+	return n_stopped;
+}
+
 uint32_t emu_seg_cap(uint32_t nsub) { return search_seg_cap(nsub); }
 
 uint64_t emu_synth_rnd(uint64_t seed, uint64_t stream, uint64_t ctr) { return synth_rnd(seed, stream, ctr); }

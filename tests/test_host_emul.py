@@ -118,6 +118,45 @@ def test_bitsliced_counters(E, n, nsub):
     assert np.array_equal(counts.astype(np.uint64), exp.astype(np.uint64))
 
 
+@pytest.mark.parametrize("nsub,n_lanes", [(8, 2), (16, 1), (32, 1)])
+def test_search_early_exit_never_loses_a_hit(E, nsub, n_lanes):
+    """search_count_kernel<NH, true>: a chunk stops being read once the sum of the substreams' bounds (exact maximum of
+    the partial counts + k-mers not looked at yet, possibly stale) falls below the count a hit needs.  Replayed on the
+    host with the substreams taking turns in random order: whenever somebody stops, every column's TRUE count is below
+    `need`; when a column reaches `need`, nobody stops and the counts are the full ones; and chunks without a hit do stop."""
+    rng = np.random.default_rng(nsub * 7 + n_lanes)
+    cols = 128 * n_lanes
+    stopped_some = 0
+    for trial in range(60):
+        n = int(rng.choice([40, 200, 970, 970, 2000, 5000]))
+        need = max(1, int(n * float(rng.choice([0.2, 0.5, 0.5, 0.9, 1.0]))))
+        dens = float(rng.choice([0.02, 0.125, 0.3]))
+        m = (rng.random((n, cols)) < dens)
+        plant = int(rng.integers(0, 4))                     # 0: no hit; else a column just below / at / above `need`
+        if plant:
+            c = int(rng.integers(0, cols))
+            k_m = min(n, max(0, need + (plant - 2)))
+            m[:, c] = False
+            rows = rng.choice(n, k_m, replace=False) if trial % 2 else np.arange(n - k_m, n)
+            m[rows, c] = True
+        true = m.sum(axis=0)
+        vecs = np.packbits(m.reshape(n, cols // 32, 32), axis=2, bitorder="little").view(np.uint32).reshape(n, n_lanes, 4)
+        order = rng.integers(0, nsub, 4 * ((n + 16 * nsub - 1) // (16 * nsub)) * nsub).astype(np.uint32)
+        if trial % 3 == 0:
+            order = np.sort(order)                          # one substream races ahead of the others
+        counts = np.zeros(cols, np.uint32)
+        n_stop = E.emu_count_exit(p(np.ascontiguousarray(vecs)), C.c_uint32(n), C.c_uint32(n_lanes), C.c_uint32(nsub), C.c_uint32(need),
+                                  p(order), C.c_uint32(len(order)), p(counts))
+        if true.max() >= need:
+            assert n_stop == 0 and np.array_equal(counts, true), (trial, n, need)
+        if n_stop:
+            assert true.max() < need and counts.max() < need and np.all(counts <= true), (trial, n, need)
+            stopped_some += 1
+        else:
+            assert np.array_equal(counts, true)
+    assert stopped_some >= 5
+
+
 @pytest.mark.parametrize("nsub", [8, 16, 32, 64, 256])
 def test_bitsliced_counters_cannot_wrap(E, nsub):
     # ADVICE r1: a filter that holds EVERY k-mer of a long query used to wrap a substream's 10-plane counter (1024 -> 0)
