@@ -258,16 +258,6 @@ insert_words_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint
 	}
 }
 
-// finalize, min_kmer_count == 1: the filter bits of a PAIR of seeds are the fold of a counting table's touched bitmap.
-//
-// Seeds 2t and 2t + 1 index counting table t (make_bloom.cpp:546-551), and the same hash values masked to the filter
-// length index the filter (make_bloom.cpp:573-577).  With min_kmer_count 1 a slot of table t is non-zero iff some
-// occurrence touched it; the FIRST occurrence to touch a slot read a zero counter there, so it was valid and both of
-// its table-t hashes are in the filter; an occurrence that is not valid found all its slots touched and adds nothing
-// to the bitmap.  Hence { h_s & (2^L - 1) : valid occurrences, s in {2t, 2t+1} } = { slot & (2^L - 1) : touched slots
-// of table t } whenever L <= lc and both seeds of the table are in use: 2^lc bits are read instead of two random
-// read-modify-writes per k-mer occurrence.  A last odd seed (num_hash 3 or 5) still goes through insert_words_kernel.
-// filter word w = OR of the words w + j * 2^(L-5) of every table, j < 2^(lc-L).
 // finalize, first-touch path, num_hash 3 with seeds (0,1) folded out of the touched bitmap: seed 2's hash of every entry
 // was kept by ft_hash_kernel behind the words of the list chunk (it is one of the four counting hashes), so the last
 // seed costs one 4-byte load and one red.or per valid occurrence.  Four entries per thread.
@@ -292,8 +282,20 @@ insert_hash_kernel(uint64_t* const* __restrict__ chunks, uint64_t n_words, uint3
 	}
 }
 
+// kwg_bloom_rollback: the boundary word of the invalid bitmap keeps the marks of the entries below the checkpoint
 __global__ void mask_word_kernel(uint32_t* w, uint32_t keep) { *w &= keep; }
 
+// finalize, min_kmer_count == 1: the filter bits of a PAIR of seeds are the fold of a counting table's touched bitmap.
+//
+// Seeds 2t and 2t + 1 index counting table t (make_bloom.cpp:546-551), and the same hash values masked to the filter
+// length index the filter (make_bloom.cpp:573-577).  With min_kmer_count 1 a slot of table t is non-zero iff some
+// occurrence touched it; the FIRST occurrence to touch a slot read a zero counter there, so it was valid and both of
+// its table-t hashes are in the filter; an occurrence that is not valid found all its slots touched and adds nothing
+// to the bitmap.  Hence { h_s & (2^L - 1) : valid occurrences, s in {2t, 2t+1} } = { slot & (2^L - 1) : touched slots
+// of table t } whenever L <= lc and both seeds of the table are in use: 2^lc bits are read instead of two random
+// read-modify-writes per k-mer occurrence.  A last odd seed (num_hash 3 or 5) is still set occurrence by occurrence
+// (insert_hash_kernel / insert_words_kernel).  Filter word w = OR of the words w + j * 2^(L-5) of every table, j < 2^(lc-L).
+// Checked against the oracle on the CPU (tests/test_fold_touched_cpu.py) and on the GPU over every (L, num_hash).
 __device__ __forceinline__ uint32_t vec_or(uint32_t a, uint32_t b) { return a | b; }
 __device__ __forceinline__ uint4 vec_or(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
 
