@@ -1061,8 +1061,8 @@ def main():
     head = out.get("construct") or next(iter(out.values()))
     line = {"metric": "Bloom k-mer inserts/s", "value": head["value"], "unit": "kmer_inserts/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic", "config": config, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
-            "roofline": head["roofline"], "cpu_baseline": cpu, "clocks": sampler.summary(windows),
+            "dtype": "u32", "data": "synthetic", "config": config, "e2e": head["e2e"], "gpu_launches": head.get("gpu_launches"),
+            "roofline": head.get("roofline"), "cpu_baseline": cpu, "clocks": sampler.summary(windows),
             "stages": {k: v for k, v in out.items()}}
     print(json.dumps(line))
     return 0

@@ -1,5 +1,6 @@
 // extern "C" view of the host layer so that tests and bench.py (Python, ctypes) can drive the same
 // C++ entry points a C++ caller uses.  Thin: no logic of its own.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 
@@ -43,6 +44,26 @@ void kwh_accession_to_str(uint64_t acc, char* out, size_t cap)
 int kwh_pack_2na(uint8_t* packed, uint8_t* mask, uint64_t cursor, const char* bases, uint64_t n)
 {
 	return pack_2na(packed, mask, cursor, bases, (size_t)n) ? 1 : 0;
+}
+
+// the read streaming alone (open_read_collection + next_fragment): fragments, bases, longest fragment and an FNV-1a hash of
+// the fragments with a separator after each -- what the parser tests compare with a plain Python parse of the same file
+int kwh_parse_digest(const char* path, uint64_t* out /* [4] */)
+{
+	try {
+		ReadSource* src = open_read_collection(path);
+		std::string frag;
+		uint64_t n = 0, bases = 0, longest = 0, h = 1469598103934665603ull;
+		while (src->next_fragment(frag)) {
+			++n; bases += frag.size(); longest = std::max<uint64_t>(longest, frag.size());
+			for (size_t i = 0; i < frag.size(); ++i) { h ^= (unsigned char)frag[i]; h *= 1099511628211ull; }
+			h ^= 0xFFu; h *= 1099511628211ull;
+		}
+		delete src;
+		out[0] = n; out[1] = bases; out[2] = longest; out[3] = h;
+		return 0;
+	}
+	catch (const char*) { return 1; }
 }
 
 // make_bloom_filter() on a reads file; results through plain out-parameters

@@ -38,14 +38,26 @@ private:
 	std::ifstream fin;
 };
 
-class GzSequenceReads : public ReadSource {  // FASTA / FASTQ, optionally gzip (zlib reads plain files too)
+// FASTA / FASTQ, optionally gzip (zlib reads plain files too): the SequenceIterator role (parse_sequence.cpp:72-262).
+// zlib inflate is what bounds FASTQ.gz -> .bloom, so it gets a thread of its own: the file is inflated block by block
+// into a small ring while the caller (BatchPipeline's parser thread) cuts the previous block into lines and packs them.
+class GzSequenceReads : public ReadSource {
 public:
-	explicit GzSequenceReads(const std::string& path) : gz(gzopen(path.c_str(), "rb")), peeked(false), fastq(false), first(true)
+	explicit GzSequenceReads(const std::string& path) : gz(gzopen(path.c_str(), "rb")), fill(0), drain(0), stop(false), cur(NULL), pos(0),
+		peeked(false), fastq(false), first(true)
 	{
 		if (!gz) throw __FILE__ ":open_read_collection: Unable to open sequence file";
 		gzbuffer(gz, 1 << 20);
+		for (size_t i = 0; i < N_BLOCKS; ++i) blocks[i].data.resize(BLOCK_BYTES);
+		inflater = std::thread(&GzSequenceReads::inflate_loop, this);
 	}
-	~GzSequenceReads() { if (gz) gzclose(gz); }
+	~GzSequenceReads()
+	{
+		{ std::lock_guard<std::mutex> l(mu); stop = true; }
+		cv.notify_all();
+		if (inflater.joinable()) inflater.join();
+		if (gz) gzclose(gz);
+	}
 	bool next_fragment(std::string& bases)
 	{
 		std::string line;
@@ -66,23 +78,83 @@ public:
 		return true;
 	}
 private:
+	static const size_t BLOCK_BYTES = size_t(4) << 20, N_BLOCKS = 3;
+	struct Block { std::vector<char> data; size_t len; bool last; Block() : len(0), last(false) {} };
+
+	void inflate_loop()
+	{
+		for (;;) {
+			Block* b;
+			{
+				std::unique_lock<std::mutex> l(mu);
+				cv.wait(l, [&] { return stop || fill - drain < N_BLOCKS; });
+				if (stop) return;
+				b = &blocks[fill % N_BLOCKS];
+			}
+			const int n = gzread(gz, b->data.data(), (unsigned)BLOCK_BYTES);
+			b->len = n > 0 ? (size_t)n : 0;
+			b->last = n < (int)BLOCK_BYTES;          // short read: end of file (or an error: the stream ends here, like gzgets)
+			{
+				std::lock_guard<std::mutex> l(mu);
+				++fill;
+			}
+			cv.notify_all();
+			if (b->last) return;
+		}
+	}
+	// the next inflated block, or false at the end of the file
+	bool next_block()
+	{
+		if (cur) {
+			const bool was_last = cur->last;
+			{ std::lock_guard<std::mutex> l(mu); ++drain; }
+			cv.notify_all();
+			cur = NULL;
+			if (was_last) { at_end = true; return false; }
+		}
+		if (at_end) return false;
+		std::unique_lock<std::mutex> l(mu);
+		cv.wait(l, [&] { return fill > drain; });
+		cur = &blocks[drain % N_BLOCKS];
+		pos = 0;
+		return true;
+	}
+	// one line without its end-of-line characters; false when nothing is left (a last line without '\n' still counts)
 	bool next_line(std::string& line)
 	{
 		if (peeked) { line = pending; peeked = false; return true; }
 		line.clear();
-		char buf[1 << 16];
 		bool any = false;
-		while (gzgets(gz, buf, sizeof(buf))) {
+		for (;;) {
+			if (!cur || pos >= cur->len) {
+				if (!next_block()) break;
+				if (cur->len == 0) continue;
+			}
 			any = true;
-			size_t n = std::strlen(buf);
-			const bool eol = n && buf[n - 1] == '\n';
-			while (n && (buf[n - 1] == '\n' || buf[n - 1] == '\r')) --n;
-			line.append(buf, n);
-			if (eol) break;
+			const char* p = cur->data.data() + pos;
+			const size_t left = cur->len - pos;
+			const char* nl = (const char*)std::memchr(p, '\n', left);
+			if (nl) {
+				line.append(p, (size_t)(nl - p));
+				pos += (size_t)(nl - p) + 1;
+				break;
+			}
+			line.append(p, left);
+			pos = cur->len;
 		}
+		while (!line.empty() && line[line.size() - 1] == '\r') line.erase(line.size() - 1);
 		return any;
 	}
 	gzFile gz;
+	Block blocks[N_BLOCKS];
+	size_t fill, drain;                      // blocks inflated / handed back (under mu)
+	bool stop;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::thread inflater;
+	Block* cur;
+	size_t pos;
+	bool at_end = false;
 	std::string pending;
 	bool peeked, fastq, first;
 };

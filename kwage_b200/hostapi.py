@@ -67,6 +67,15 @@ def accession_to_str(a):
     return buf.value.decode()
 
 
+def parse_digest(path):
+    """(fragments, bases, longest fragment, FNV-1a hash) of a reads / FASTA / FASTQ(.gz) file as the host layer streams it"""
+    out = (C.c_uint64 * 4)()
+    lib().kwh_parse_digest.argtypes = [C.c_char_p, C.POINTER(C.c_uint64)]
+    if lib().kwh_parse_digest(path.encode(), out):
+        raise RuntimeError("kwh_parse_digest: cannot open " + path)
+    return tuple(int(x) for x in out)
+
+
 def make_bloom_file(accession, reads_path, num_bp, bloom_dir, *, k=31, min_kmer_count=1, p=0.25, min_log2=18, max_log2=32, device=0):
     n, L, h, lc = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
     err = C.create_string_buffer(512)

@@ -1,5 +1,6 @@
 """CPU: host-layer logic (C++ kwage_b200/host) against the reference's golden vectors."""
 import numpy as np
+import pytest
 
 from kwage_b200 import hostapi as H
 from kwage_b200.host import build as hbuild
@@ -66,3 +67,70 @@ def test_host_packer_matches_the_numpy_packer():
             assert not any_bad and not mask.any()
         else:
             assert any_bad and np.array_equal(mask, exp_m[: (n + 7) // 8])
+
+
+def _fnv(frags):
+    h = 1469598103934665603
+    for f in frags:
+        for c in f:
+            h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        h = ((h ^ 0xFF) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _digest(frags):
+    return (len(frags), sum(len(f) for f in frags), max([len(f) for f in frags] or [0]), _fnv(frags))
+
+
+def _rand_frags(rng, n, max_len):
+    alphabet = np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)
+    return [bytes(alphabet[rng.integers(0, len(alphabet), int(rng.integers(0, max_len + 1)))]) for _ in range(n)]
+
+
+@pytest.mark.parametrize("fmt", ["fastq", "fastq.gz", "fasta", "fasta.gz", "fa_crlf", "fastq_no_final_newline", "fasta_long.gz"])
+def test_read_streaming_equals_a_plain_parse(fmt, tmp_path):
+    """FASTA / FASTQ (.gz) streaming of the host layer (stages.cpp::GzSequenceReads: an inflate thread hands 4 MiB blocks to
+    the line cutter; the SequenceIterator role, parse_sequence.cpp:72-262): the fragments are the ones a plain Python parse
+    of the same file yields -- lines that straddle blocks, multi-line FASTA records, CRLF, a last line without a newline,
+    empty reads, files of several blocks."""
+    import gzip
+    rng = np.random.default_rng(len(fmt))
+    big = fmt == "fasta_long.gz"
+    frags = _rand_frags(rng, 40 if big else 3000, 600000 if big else 300)
+    eol = b"\r\n" if fmt == "fa_crlf" else b"\n"
+    out = bytearray()
+    if fmt.startswith("fastq"):
+        for i, f in enumerate(frags):
+            out += b"@r%d" % i + eol + f + eol + b"+" + eol + b"I" * len(f) + eol
+        if fmt == "fastq_no_final_newline":
+            out = out[:-1]
+        exp = frags
+    else:
+        for i, f in enumerate(frags):
+            out += b">s%d some text" % i + eol
+            w = int(rng.choice([60, 70, 1000]))
+            for a in range(0, len(f), w):
+                out += f[a:a + w] + eol
+        exp = frags
+    ext = ".fastq" if fmt.startswith("fastq") else ".fasta"
+    path = str(tmp_path / ("x" + ext + (".gz" if fmt.endswith(".gz") else "")))
+    if fmt.endswith(".gz"):
+        with gzip.open(path, "wb", compresslevel=1) as f:
+            f.write(bytes(out))
+    else:
+        with open(path, "wb") as f:
+            f.write(bytes(out))
+    assert len(out) > (9 << 20) or not big           # the long case spans several 4 MiB blocks
+    assert H.parse_digest(path) == _digest(exp)
+
+
+def test_read_streaming_of_a_reads_file_and_of_an_empty_file(tmp_path):
+    rng = np.random.default_rng(3)
+    frags = _rand_frags(rng, 500, 200)
+    p1 = str(tmp_path / "a.reads")
+    with open(p1, "wb") as f:
+        f.write(b"".join(x + b"\n" for x in frags))
+    assert H.parse_digest(p1) == _digest(frags)
+    p2 = str(tmp_path / "e.fastq")
+    open(p2, "wb").close()
+    assert H.parse_digest(p2) == (0, 0, 0, _fnv([]))
